@@ -1,0 +1,387 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 line-by-line radiative-transfer engine.
+
+Metric (BASELINE.json): line×ν×layer evaluations per second on configs[1] --
+"Earth-like clear sky: synthetic CO2+H2O ~500k Voigt lines, 0-3000 cm^-1 at 0.01 cm^-1, 100 layers, OLR on 1 B200"
+(SURVEY.md section 8d, C2).  One step = one full pass of the hot path: Voigt line summation of both gases at the
+101 levels -> layer optical depths -> 5-stream Schwarzschild sweeps -> spectral reduction to OLR / F+ / F-.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c2small|c1]
+
+N > 1 (launched by torchrun, one rank per GPU): contiguous ν slices balanced by evaluation count, lines within
+slice ± cutoff only, and ONE NCCL all-reduce of the 2*np spectrally integrated fluxes per step.
+`--impl reference` times the CPU restatement of the reference (oracle/, all host threads) on a bounded sample of
+the same workload; the Julia reference itself cannot run in this image (no Julia runtime).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "clearsky.jl_b200"))
+sys.path.insert(0, ROOT)
+
+METRIC = "line×ν×layer evals/s"
+UNIT = "evals/s"
+FLOP_PER_EVAL = 10.0   # Voigt, far-wing dominated
+
+
+# ------------------------------------------------------------------------------------------------
+# workload
+def synthetic_lines(cs, n, seed, M, γs_rng, νmax=3000.0):
+    """SURVEY.md section 8(d) C2 generator: HITRAN .par field widths/rounding, numpy PCG64"""
+    rng = np.random.default_rng(np.random.PCG64(seed))
+    ν = np.sort(np.round(rng.uniform(0.0, νmax, n), 6))
+    ν = np.maximum(ν, 1e-6)
+    S = np.array([float(f"{x:.3E}") for x in 10.0 ** rng.uniform(-30, -19, n)])
+    γa = np.round(rng.uniform(0.05, 0.10, n), 4)
+    γs = np.round(rng.uniform(*γs_rng, n), 3)
+    Epp = np.round(rng.uniform(0, 3000, n), 4)
+    na = np.round(rng.uniform(0.5, 0.8, n), 2)
+    mp = cs.MOLPARAM[M]
+    return cs.SpectralLines(mp.name, mp.formula, n, M, np.ones(n, dtype=np.int16), np.full(n, mp.mu[0]),
+                            np.full(n, mp.A[0]), ν, S, γa, γs, Epp, na)
+
+
+def make_workload(cs, name):
+    if name == "c2":
+        nlines, nν, nlayer = 250_000, 300_000, 100
+    elif name == "c2small":
+        nlines, nν, nlayer = 25_000, 30_000, 20
+    else:
+        raise ValueError(name)
+    co2 = synthetic_lines(cs, nlines, 20261018, 2, (0.06, 0.13))
+    h2o = synthetic_lines(cs, nlines, 20261019, 1, (0.10, 0.50))
+    ν = 0.01 * np.arange(1, nν + 1) * (300_000 / nν)
+    P = cs.pressuregrid(10.0, 1e5, nlayer + 1)
+    Γ = cs.DryAdiabat(288.0, 1e5, 1040.0, 0.029, Ptropo=1e4)
+    T = Γ(P)
+    return dict(name=name, gases=[(co2, 400e-6), (h2o, 1e-3)], ν=ν, P=P, T=T, μ=0.029, g=9.8, cut=25.0,
+                nstream=5, nlob=2, nlayer=nlayer)
+
+
+def balanced_slices(counts, n):
+    """contiguous index slices with ~equal sums of `counts` (per-ν evaluation counts)"""
+    c = np.concatenate(([0], np.cumsum(counts, dtype=np.float64)))
+    edges = [int(np.searchsorted(c, c[-1] * k / n)) for k in range(n + 1)]
+    edges[0], edges[-1] = 0, len(counts)
+    for k in range(1, n + 1):
+        edges[k] = max(edges[k], edges[k - 1])
+    return edges
+
+
+def per_point_counts(ν, νl, cut):
+    lo = np.searchsorted(νl, ν - cut, side="left")
+    hi = np.searchsorted(νl, ν + cut, side="right")
+    return (hi - lo).astype(np.int64)
+
+
+def trapz_weights(ν):
+    """per-point weights of trapz(ν, ·) (util.jl:26-33): every interval counted once across ν slices"""
+    d = np.diff(ν)
+    w = np.zeros(len(ν))
+    w[:-1] += d / 2
+    w[1:] += d / 2
+    return w
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region"""
+
+    def __init__(self, device):
+        self.device = device
+        self.rows = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.device), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows if len(r) > 3 + i)]
+        pw = [float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "reasons": reasons, "samples": len(self.rows)}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_sample(cs, orc, wl, nthreads, target_evals=2.0e9):
+    """bounded CPU sample of the same workload: a contiguous ν slice from the middle of the grid × all levels,
+    both gases, oracle restatement parallel over levels (like bake's @threads, gases.jl:115) then fluxes."""
+    ν, P, T = wl["ν"], wl["P"], wl["T"]
+    nlev = len(P)
+    per_ν = sum(len(sl.ν) for sl, _ in wl["gases"]) * (2 * wl["cut"]) / 3000.0 * nlev
+    n = int(min(len(ν), max(64, target_evals / per_ν)))
+    i0 = (len(ν) - n) // 2
+    νs = ν[i0:i0 + n]
+    evals = sum(orc.count_evals(νs, orc.included_lines(νs, sl.ν, wl["cut"]), wl["cut"]) for sl, _ in wl["gases"]) * nlev
+    m, W = cs.streamnodes(wl["nstream"])
+    x, w = cs.lobattonodes(wl["nlob"])
+    μn = np.full((nlev - 1, wl["nlob"]), wl["μ"])
+
+    def run():
+        σ = np.zeros((nlev, n))
+        for sl, C in wl["gases"]:
+            σ += C * orc.xsec(orc.VOIGT, sl, νs, T, P, C * P, wl["cut"], nthreads=nthreads)
+        return orc.fluxes(νs, P, wl["nlob"], w, μn, T, σ, wl["g"], None, None, 0.841, wl["nstream"], m, W,
+                          nthreads=nthreads, full=False)
+
+    return run, evals, f"ν slice of {n} points (indices {i0}..{i0 + n - 1}) × all {nlev} levels, both gases, Voigt + fluxes"
+
+
+def run_reference(args):
+    import clearsky_b200 as cs   # host-side generators/readers only: no CUDA call on this arm
+    from oracle import oracle as orc
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    orc.build()
+    wl = make_workload(cs, args.workload)
+    nthreads = orc.max_threads()
+    run, evals, sample = cpu_sample(cs, orc, wl, 0, target_evals=args.cpu_evals)
+    for _ in range(args.warmup):
+        run()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        run()
+    dt = (time.perf_counter() - t0) / args.steps
+    v = evals / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl["name"], "note": "CPU restatement of the reference (oracle/, C + OpenMP); the Julia "
+                   "reference cannot run here (no Julia runtime in the image)"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": nthreads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line, ensure_ascii=False))
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import clearsky_b200 as cs
+    from clearsky_b200._lib import check, f64, lib, ptr
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    # run the library on torch's current stream so that torch.cuda.Event brackets its kernels
+    ctx = cs.Context(local, stream=torch.cuda.current_stream().cuda_stream)
+    wl = make_workload(cs, args.workload)
+    ν, P, T = wl["ν"], wl["P"], wl["T"]
+    nlev = len(P)
+    cut = wl["cut"]
+
+    # ---- ν sharding: contiguous slices balanced by evaluations, global trapezoid weights
+    counts = sum(per_point_counts(ν, sl.ν, cut) for sl, _ in wl["gases"])
+    edges = balanced_slices(counts, world)
+    i0, i1 = edges[rank], edges[rank + 1]
+    νs = np.ascontiguousarray(ν[i0:i1])
+    wts = np.ascontiguousarray(trapz_weights(ν)[i0:i1])
+    total_evals = int(counts.sum()) * nlev
+    my_evals = int(counts[i0:i1].sum()) * nlev
+
+    def slice_lines(sl):
+        # every line the slice can see: the per-point rule decides inside the kernel
+        keep = (sl.ν >= νs[0] - cut - 1e-9) & (sl.ν <= νs[-1] + cut + 1e-9)
+        return cs.SpectralLines(sl.name, sl.formula, int(keep.sum()), sl.M, sl.I[keep], sl.μ[keep], sl.A[keep],
+                                sl.ν[keep], sl.S[keep], sl.γa[keep], sl.γs[keep], sl.Epp[keep], sl.na[keep])
+
+    my_gases = [(slice_lines(sl), C) for sl, C in wl["gases"]]
+    m, W = cs.streamnodes(wl["nstream"])
+    x, w = cs.lobattonodes(wl["nlob"])
+    μn = f64(np.full((nlev - 1, wl["nlob"]), wl["μ"]))
+    Tn, Pn = f64(T), f64(P)
+    dF = torch.zeros(2 * nlev, dtype=torch.float64, device=f"cuda:{local}")
+
+    # resident objects for the device-timed loop
+    dls = [cs.DeviceLines(sl, ctx) for sl, _ in my_gases]
+    ws = cs.SigmaWorkspace(νs, nlev, ctx)
+    Cs = [f64(np.full(nlev, C)) for _, C in my_gases]
+    timers_acc = {"linesum": 0.0, "prep": 0.0, "rt": 0.0, "reduce": 0.0}
+
+    # the library accumulates linesum/prep timers across cs_sigma_add_lines calls: read deltas instead
+    def timed_step(acc):
+        t0 = ctx.timers()
+        ws.zero()
+        for dl, C in zip(dls, Cs):
+            check(lib().cs_sigma_add_lines(ws.h, dl.h, cs._lib.CS_VOIGT, ptr(Tn), ptr(Pn), ptr(C), cut))
+        t1 = ctx.timers()
+        acc["linesum"] += t1["linesum"] - t0["linesum"]
+        acc["prep"] += t1["prep"] - t0["prep"]
+        check(lib().cs_fluxes_device(ws.h, nlev, ptr(Pn), wl["nlob"], ptr(f64(w)), ptr(μn), ptr(Tn), wl["g"], None, None,
+                                     0.841, wl["nstream"], ptr(f64(m)), ptr(f64(W)), ptr(wts), dF.data_ptr()))
+        t2 = ctx.timers()
+        acc["rt"] += t2["rt"]
+        acc["reduce"] += t2["reduce"]
+        if world > 1:
+            dist.all_reduce(dF)
+        return dF
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def e2e_step():
+        """the call a user makes, from HOST buffers: upload lines + ν, Σ by exact line-by-line gas, fluxes, read F"""
+        gases = [cs.LineGas(_fresh(sl), C, νs, "voigt", cut, ctx=ctx) for sl, C in my_gases]
+        A = cs.UnifiedAbsorber(*gases)
+        wsx = cs.SigmaWorkspace(νs, nlev, ctx)
+        A.sigma_nodes(wsx, Tn, Pn)
+        check(lib().cs_fluxes_device(wsx.h, nlev, ptr(Pn), wl["nlob"], ptr(f64(w)), ptr(μn), ptr(Tn), wl["g"], None, None,
+                                     0.841, wl["nstream"], ptr(f64(m)), ptr(f64(W)), ptr(wts), dF.data_ptr()))
+        if world > 1:
+            dist.all_reduce(dF)
+        return dF.cpu().numpy()
+
+    def _fresh(sl):
+        import copy
+        c = copy.copy(sl)
+        c.__dict__.pop("_dev", None)
+        return c
+
+    # ---- warm-up
+    for _ in range(max(args.warmup, 1)):
+        timed_step({"linesum": 0.0, "prep": 0.0, "rt": 0.0, "reduce": 0.0})
+    fp64_peak = ctx.fp64_peak(20000)   # burst DFMA rate of this device [FLOP/s]
+
+    # ---- device-timed region (inputs resident in HBM)
+    barrier()
+    l0 = ctx.launches()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        ev0.record()
+        for _ in range(args.steps):
+            timed_step(timers_acc)
+        ev1.record()
+        barrier()
+        dt = ev0.elapsed_time(ev1) * 1e-3
+    launches = ctx.launches() - l0
+    tmax = torch.tensor([dt], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    dt = float(tmax.item())
+    F = dF.cpu().numpy()
+    olr = float(F[0])
+
+    # ---- end-to-end through the public API with host buffers
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    n_e2e = max(1, min(args.steps, 3))
+    for _ in range(n_e2e):
+        e2e_step()
+    barrier()
+    dte = time.perf_counter() - t0
+    te = torch.tensor([dte], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    dte = float(te.item()) / n_e2e
+    h2d = sum(len(sl.ν) * (7 * 8 + 2) for sl, _ in my_gases) + len(νs) * 8 * 2 + nlev * 8 * 6
+    d2h = 2 * nlev * 8
+
+    ms_step = dt / args.steps * 1e3
+    value = total_evals / (dt / args.steps)
+    ls_ms = timers_acc["linesum"] / args.steps            # per step, summed over this rank's line-sum launches
+    n_ls_launch = len(dls)
+    achieved = FLOP_PER_EVAL * my_evals / (ls_ms * 1e-3) / 1e12 if ls_ms > 0 else None
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": wl["name"], "lines": int(sum(len(sl.ν) for sl, _ in wl["gases"])), "n_nu": len(ν),
+                   "layers": wl["nlayer"], "shape": "voigt", "cutoff_cm-1": cut, "nstream": wl["nstream"],
+                   "nlobatto": wl["nlob"], "evals_per_step": total_evals, "parallelism": f"nu-slices x{world}",
+                   "l2": "per-step working set (line records 3.2 GB + sigma 0.24 GB) exceeds the 126 MB L2"},
+        "olr_w_m2": olr, "olr_spectra_per_s": 1.0 / (dt / args.steps),
+        "e2e": {"value": total_evals / dte, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": dte * 1e3},
+        "gpu_launches": int(launches),
+        "clocks": clk.summary(),
+        "roofline": {"bound": "fp64", "kernel": "line_sum_kernel<VOIGT>", "achieved": achieved, "peak": fp64_peak / 1e12,
+                     "unit": "TFLOP/s", "frac": (achieved / (fp64_peak / 1e12)) if achieved else None, "traffic": None,
+                     "peak_source": "cs_fp64_peak DFMA microbenchmark run in this process (FP64 is not in MEASURED_PEAKS.json)",
+                     "flop_per_eval": FLOP_PER_EVAL, "kernel_ms_per_step": ls_ms, "launches_per_step": n_ls_launch,
+                     "kernel_share_of_step": ls_ms / ms_step if ms_step > 0 else None,
+                     "rt_kernel_ms_per_step": timers_acc["rt"] / args.steps,
+                     "prep_kernel_ms_per_step": timers_acc["prep"] / args.steps},
+    }
+
+    # ---- CPU baseline (rank 0, N = 1 only): oracle port on the box's host cores, bounded sample
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle import oracle as orc
+        orc.build()
+        run, evals, sample = cpu_sample(cs, orc, wl, 0, target_evals=args.cpu_evals)
+        run()
+        t0 = time.perf_counter()
+        run()
+        tc = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": evals / tc, "unit": UNIT, "cores": orc.max_threads(), "kind": "port", "sample": sample,
+                                "seconds": tc}
+    if rank == 0:
+        print(json.dumps(line, ensure_ascii=False))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c2small"])
+    ap.add_argument("--cpu-evals", type=float, default=2.0e9, help="size of the bounded CPU sample [evals]")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,263 @@
+// cs_internal.cuh -- shared internals of libclearsky_b200 (sm_100a only; FP64 CUDA cores, no tensor cores).
+//
+// The public boundary is include/clearsky_b200.h (plain C ABI).  Everything here is private.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <math.h>
+#include <mutex>
+#include <string>
+#include <vector>
+#include "../../include/clearsky_b200.h"
+
+// ------------------------------------------------------------------------------------------------
+// constants: bit-exact copies of the reference's values (src/constants.jl:1-27,
+// src/absorption/line_shapes.jl:2-5, src/hitran/molparam.jl:1-2)
+#define CS_C    299792458.0
+#define CS_H    6.62607015e-34
+#define CS_KB   1.38064852e-23      // 2014 CODATA value, as in the reference (constants.jl:6)
+#define CS_R    8.31446262
+#define CS_ATM  101325.0
+#define CS_NA   6.02214076e23
+#define CS_LO2  7.21879268e38
+#define CS_TREF 296.0
+#define CS_T0   273.15
+#define CS_TMIN 25.0
+#define CS_TMAX 1000.0
+#define CS_PI   3.14159265358979323846
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing: status codes + thread-local message, no exceptions across the ABI
+void cs_set_error(const char* fmt, ...);
+
+#define CS_CUDA(call)                                                                        \
+    do {                                                                                     \
+        cudaError_t e__ = (call);                                                            \
+        if (e__ != cudaSuccess) {                                                            \
+            cs_set_error("%s:%d CUDA error %s: %s", __FILE__, __LINE__, #call,               \
+                         cudaGetErrorString(e__));                                           \
+            return CS_ERR_CUDA;                                                              \
+        }                                                                                    \
+    } while (0)
+
+#define CS_REQUIRE(cond, code, ...)                                                          \
+    do {                                                                                     \
+        if (!(cond)) {                                                                       \
+            cs_set_error(__VA_ARGS__);                                                       \
+            return (code);                                                                   \
+        }                                                                                    \
+    } while (0)
+
+#define CS_TRY(expr)                                                                         \
+    do {                                                                                     \
+        int32_t rc__ = (expr);                                                               \
+        if (rc__ != CS_OK) return rc__;                                                      \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// device buffer that only grows (scratch reused across calls: no cudaMalloc in the RCM loop)
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int32_t reserve(size_t bytes)
+    {
+        if (bytes <= cap) return CS_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            cs_set_error("cudaMalloc(%zu bytes) failed: %s", want, cudaGetErrorString(e));
+            p = nullptr;
+            return CS_ERR_NOMEM;
+        }
+        cap = want;
+        return CS_OK;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct cs_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    int sm_count = 148;
+    std::recursive_mutex mtx;
+    // scratch
+    DevBuf s_nu, s_lev, s_rec, s_slow, s_sigma, s_misc, s_part, s_tau, s_planck, s_out0, s_out1, s_out2;
+    DevBuf s_w;
+    // kernel timing of the last call (ms), measured with CUDA events on ctx->stream
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+    double last_kernel_ms[CS_NTIMERS] = {0};
+    int64_t launches = 0;   // number of kernels of this library launched on this context
+};
+
+struct cs_lines {
+    cs_ctx* ctx;
+    int64_t n;
+    // device SoA (sorted by wavenumber, as SpectralLines guarantees: par.jl:267)
+    double *nu, *S, *ga, *gs, *Epp, *na, *mu;
+    int16_t* iso;
+    int32_t niso;
+    int32_t* ncheb;   // [niso]
+    double* cheb;     // [niso][CS_MAXCHEB]
+    std::vector<double> h_nu;  // host copy of line positions (window searches, eval counting)
+};
+
+struct cs_sigma {
+    cs_ctx* ctx;
+    int64_t nnu, nnode;
+    double* nu;      // device [nnu]
+    double* sig;     // device [nnode][nnu], nu fastest
+    std::vector<double> h_nu;
+    bool own_nu;
+};
+
+struct cs_table {
+    cs_ctx* ctx;
+    int64_t nnu;
+    int32_t nT, nP;
+    double Ta, Tb, lnPa, lnPb;   // interpolator bounds = first/last grid coordinates
+    double* coef;                // device [nT*nP][nnu], coefficient-major, nu fastest
+    double* sigma_block;         // optional device copy of the baked block [nT*nP][nnu] (NULL if dropped)
+    int64_t nzeroed;
+};
+
+struct cs_cia {
+    cs_ctx* ctx;
+    int32_t ngrid, nsingle, extrapolate, singles;
+    std::vector<int64_t> g_nnu, g_nT, g_off_nu, g_off_T, g_off_k, s_n, s_off;
+    std::vector<double> h_T;     // host copy of grid temperatures (cell search per node on the host)
+    double *d_nu, *d_T, *d_lnk, *d_snu, *d_slnk;
+    int64_t *d_desc;             // packed descriptors
+};
+
+struct cs_accel {
+    cs_ctx* ctx;
+    int64_t nnu, nlev;
+    std::vector<double> h_lnP;
+    double* lnsig;               // device [nlev][nnu]
+};
+
+// ------------------------------------------------------------------------------------------------
+// launch bookkeeping
+static inline void cs_count_launch(cs_ctx* c, int64_t n = 1) { c->launches += n; }
+
+// ------------------------------------------------------------------------------------------------
+// Device Re w(x+iy): Algorithm 985 (Zaghloul 2017), the arithmetic behind Faddeyeva985.faddeyeva(x,y)
+// (reference call site src/absorption/line_shapes.jl:375).  Written from the published algorithm, real
+// arithmetic only; region borders documented in DESIGN.md.  s must be fma(x,x,y*y).
+struct cplx {
+    double re, im;
+};
+__device__ __forceinline__ cplx cmul(cplx a, cplx b)
+{
+    return {a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re};
+}
+__device__ __forceinline__ cplx cdiv(cplx a, cplx b)
+{
+    double den = b.re * b.re + b.im * b.im;
+    return {(a.re * b.re + a.im * b.im) / den, (a.im * b.re - a.re * b.im) / den};
+}
+__device__ __forceinline__ cplx cadd(cplx a, double r) { return {a.re + r, a.im}; }
+// c - u*acc  (Horner step of the Humlicek polynomials)
+__device__ __forceinline__ cplx hstep(double c, cplx u, cplx acc)
+{
+    cplx p = cmul(u, acc);
+    return {c - p.re, -p.im};
+}
+
+static __device__ __noinline__ double cs_faddeyeva985(double x, double y)
+{
+    const double osqpi = 0.56418958354775628695;  // 1/sqrt(pi)
+    double y2 = y * y;
+    double s = fma(x, x, y2);
+    if (s >= 1.6e4) return y * osqpi / s;                       // 1 convergent
+    cplx z = {x, y};
+    if (s >= 28.5 && (s >= 107.0 || y2 >= 6e-14)) {
+        cplx zz = cmul(z, z);
+        cplx num, den;
+        if (s >= 160.0) {                                       // 2 convergents: i z / (z^2 - 1/2)
+            num = z;
+            den = cadd(zz, -0.5);
+        } else if (s >= 107.0) {                                // 3: i (z^2 - 1) / (z (z^2 - 3/2))
+            num = cadd(zz, -1.0);
+            den = cmul(z, cadd(zz, -1.5));
+        } else {                                                // 4: i z (z^2 - 5/2) / (z^2 (z^2 - 3) + 3/4)
+            num = cmul(z, cadd(zz, -2.5));
+            den = cadd(cmul(zz, cadd(zz, -3.0)), 0.75);
+        }
+        cplx q = cdiv(num, den);
+        return -q.im * osqpi;                                   // Re(i q / sqrt(pi))
+    }
+    cplx t = {y, -x};
+    if (s >= 3.5 && y2 < 0.026) {                               // Humlicek w4, region IV
+        cplx u = cmul(t, t);
+        cplx P = {0.56419, 0.0};
+        P = hstep(1.320522, u, P);
+        P = hstep(35.76683, u, P);
+        P = hstep(219.0313, u, P);
+        P = hstep(1540.787, u, P);
+        P = hstep(3321.9905, u, P);
+        P = hstep(36183.31, u, P);
+        cplx Q = {1.0, 0.0};
+        Q = hstep(1.841439, u, Q);
+        Q = hstep(61.57037, u, Q);
+        Q = hstep(364.2191, u, Q);
+        Q = hstep(2186.181, u, Q);
+        Q = hstep(9022.228, u, Q);
+        Q = hstep(24322.84, u, Q);
+        Q = hstep(32066.6, u, Q);
+        cplx r = cmul(t, cdiv(P, Q));
+        double sn, cs;
+        sincos(u.im, &sn, &cs);
+        return exp(u.re) * cs - r.re;
+    }
+    // Hui, Armstrong & Wray p = 6
+    cplx num = {0.564189583562615, 0.0};
+    num = cadd(cmul(num, t), 5.912626209773153);
+    num = cadd(cmul(num, t), 30.180142196210589);
+    num = cadd(cmul(num, t), 93.155580458138441);
+    num = cadd(cmul(num, t), 181.928533092181549);
+    num = cadd(cmul(num, t), 214.382388694706425);
+    num = cadd(cmul(num, t), 122.607931777104326);
+    cplx den = {1.0, 0.0};
+    den = cadd(cmul(den, t), 10.479857114260399);
+    den = cadd(cmul(den, t), 53.992906912940207);
+    den = cadd(cmul(den, t), 170.354001821091472);
+    den = cadd(cmul(den, t), 348.703917719495792);
+    den = cadd(cmul(den, t), 457.334478783897737);
+    den = cadd(cmul(den, t), 352.730625110963558);
+    den = cadd(cmul(den, t), 122.607931773875350);
+    return cdiv(num, den).re;
+}
+
+// fast reciprocal with full double accuracy for normal, finite, positive arguments:
+// MUFU.RCP64H seed + one cubic and one quadratic Newton step (the sequence nvcc emits for 1.0/x,
+// minus the exponent-range fix-up the callers do not need).
+__device__ __forceinline__ double cs_rcp(double a)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+    double e = fma(-a, r, 1.0);
+    e = fma(e, e, e);
+    r = fma(r, e, r);
+    e = fma(-a, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+}
+
+// internal entry points implemented across the .cu files
+void cs_reset_timers(cs_ctx* c);
+int32_t cs_lines_accumulate(cs_lines* L, int32_t shape, int64_t nnu, const double* d_nu,
+                            const double* h_nu, int64_t nlev, const double* h_T, const double* h_P,
+                            const double* h_Pp, const double* h_scale, double cut, double* d_out,
+                            int accumulate);

@@ -1,0 +1,409 @@
+// cs_rt.cu -- K6 fused optical-depth quadrature + Schwarzschild sweeps, K7 spectral reduction.
+//
+// Replaces, for every wavenumber at once, the body of the reference's threaded loop
+//     d-depth!(tau_j, P, T, mu, A, j, C, nlobatto); d-monoflux!(M+_j, M-_j, tau_j, P, B_j, nu_j, fS, fa, theta_s, nstream)
+// (src/fluxes.jl:270-277; src/core/discretized.jl:136-177, 249-326), planckevaluations
+// (core/discretized.jl:46-58, src/radiation.jl:48-54) and integral-F! (src/core/shared.jl:125-137).
+//
+// One thread owns one wavenumber.  Sigma at the Lobatto nodes is read coalesced from the workspace
+// ([node][nu], nu fastest); the per-layer tau and per-level Planck values needed again by the upward sweep go
+// through an L2-resident scratch ([layer][nu]); all streams advance together in registers.  The spectral
+// integral is fused: each level's monochromatic flux is multiplied by the point's trapezoid weight and reduced
+// with warp shuffles, then across warps in shared memory, and finally across CTAs by a second, fixed-order
+// kernel (run-to-run bit-stable; no atomics).
+#include "cs_internal.cuh"
+#include <algorithm>
+#include <cmath>
+
+namespace {
+
+constexpr int RT_THREADS = 128;
+constexpr int RT_WARPS = RT_THREADS / 32;
+
+struct RtArgs {
+    const double* sig;     // [nnode][nnu]
+    const double* nu;      // [nnu]
+    const double* w;       // [nnu] trapezoid weights
+    const double* fS;      // [nnu] or null (== 0)
+    const double* fa;      // [nnu] or null (== 0)
+    const double* small;   // packed: P[np], mu[nlob*(np-1)], wl[nlob], kT[np], m[ns], W[ns]
+    int64_t nnu;
+    int np, nlob, ns;
+    double Cg, cos_s;
+    double* tau_s;         // scratch [np-1][nnu]
+    double* B_s;           // scratch [np][nnu]
+    double* tau_out;       // optional, Julia tau[i,j] -> i + (np-1)*j
+    double* Mup_out;       // optional, Julia M[i,j]  -> i + np*j
+    double* Mdn_out;
+    double* part;          // [nblocks][2][np] CTA partial sums (0: up, 1: down)
+};
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// layerplanck (core/discretized.jl:85)
+__device__ __forceinline__ double layerplanck(double B1, double B2, double tau, double t)
+{
+    return B2 * (1.0 - t) - (B1 - B2) * t + (1.0 - t) * (B1 - B2) / tau;
+}
+
+template <int NS>
+__global__ void __launch_bounds__(RT_THREADS) rt_kernel(RtArgs a)
+{
+    extern __shared__ double sm[];
+    const int np = a.np, L = np - 1, nlob = a.nlob;
+    const int ns = (NS > 0) ? NS : a.ns;
+    // shared layout: small arrays, then per-warp partial sums [2][np][RT_WARPS]
+    const int nsmall = np + nlob * L + nlob + np + 2 * ns;
+    double* sP = sm;
+    double* smu = sP + np;
+    double* swl = smu + nlob * L;
+    double* skT = swl + nlob;
+    double* sm_m = skT + np;
+    double* sW = sm_m + ns;
+    double* red = sm + nsmall;
+    for (int t = threadIdx.x; t < nsmall; t += RT_THREADS) sm[t] = a.small[t];
+    for (int t = threadIdx.x; t < 2 * np * RT_WARPS; t += RT_THREADS) red[t] = 0.0;
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t jraw = (int64_t)blockIdx.x * RT_THREADS + threadIdx.x;
+    const bool live = jraw < a.nnu;
+    const int64_t j = live ? jraw : a.nnu - 1;
+    const int64_t nnu = a.nnu;
+    const double wj = live ? a.w[j] : 0.0;
+    const double nuj = a.nu[j];
+    // planck (radiation.jl:48-54), same operation order, no expm1
+    const double num = 100.0 * nuj;
+    const double hcn = CS_H * CS_C * num;
+    const double pref = 2 * CS_H * (CS_C * CS_C) * (num * num * num);
+    const double Cg = a.Cg;
+    const double c = a.cos_s;
+
+    constexpr int NSMAX = (NS > 0) ? NS : CS_MAX_STREAMS;
+    double I[NSMAX];
+#pragma unroll
+    for (int k = 0; k < NSMAX; k++) I[k] = 0.0;
+
+    // ---- downward: optical depth of each layer on the fly, diffuse streams, stellar beam
+    double beta1 = Cg * (a.sig[j] / smu[0]);
+    double Bprev = 100.0 * pref / (exp(hcn / skT[0]) - 1.0);
+    a.B_s[j] = Bprev;
+    double beam = c * (a.fS ? a.fS[j] : 0.0);
+    double Mdn = beam;                                   // M-[1] = c*fS(nu)   (discretized.jl:299)
+    if (a.Mdn_out && live) a.Mdn_out[(size_t)np * j] = Mdn;
+    {
+        double r = warp_sum(wj * Mdn);
+        if (lane == 0) red[(np + 0) * RT_WARPS + warp] += r;
+    }
+    for (int i = 0; i < L; i++) {
+        double dP = sP[i + 1] - sP[i];
+        double ti = 0.0;
+        ti += (dP * swl[0]) * beta1;
+        for (int n = 1; n < nlob - 1; n++) {
+            double bn = Cg * (a.sig[(size_t)(n + (nlob - 1) * i) * nnu + j] / smu[n + nlob * i]);
+            ti += (dP * swl[n]) * bn;
+        }
+        double bn = Cg * (a.sig[(size_t)((nlob - 1) * (i + 1)) * nnu + j] / smu[(nlob - 1) + nlob * i]);
+        ti += (dP * swl[nlob - 1]) * bn;
+        beta1 = bn;
+        double tau = fmax(ti, 1e-6);                     // floor on the vertical depth (discretized.jl:174)
+        a.tau_s[(size_t)i * nnu + j] = tau;
+        if (a.tau_out && live) a.tau_out[(size_t)L * j + i] = tau;
+        double Bnext = 100.0 * pref / (exp(hcn / skT[i + 1]) - 1.0);
+        a.B_s[(size_t)(i + 1) * nnu + j] = Bnext;
+        double Msum = 0.0;
+#pragma unroll
+        for (int k = 0; k < NSMAX; k++) {
+            if (k < ns) {
+                double tk = tau * sm_m[k];
+                double tr = exp(-tk);
+                double Be = layerplanck(Bprev, Bnext, tk, tr);
+                I[k] = I[k] * tr + Be;
+                Msum += sW[k] * I[k];
+            }
+        }
+        beam *= exp(-tau / c);                           // discretized.jl:302
+        Mdn = Msum + beam;
+        if (a.Mdn_out && live) a.Mdn_out[(size_t)np * j + i + 1] = Mdn;
+        double r = warp_sum(wj * Mdn);
+        if (lane == 0) red[(np + i + 1) * RT_WARPS + warp] += r;
+        Bprev = Bnext;
+    }
+    // ---- surface: Lambertian reflection + emission (discretized.jl:309-310)
+    const double Is = Mdn * (a.fa ? a.fa[j] : 0.0) / CS_PI + Bprev;
+    {
+        double Mup = Is * CS_PI;
+        if (a.Mup_out && live) a.Mup_out[(size_t)np * j + L] = Mup;
+        double r = warp_sum(wj * Mup);
+        if (lane == 0) red[L * RT_WARPS + warp] += r;
+    }
+    // ---- upward
+#pragma unroll
+    for (int k = 0; k < NSMAX; k++) I[k] = Is;
+    double B1 = Bprev;
+    for (int i = L - 1; i >= 0; i--) {
+        double tau = a.tau_s[(size_t)i * nnu + j];
+        double B2 = a.B_s[(size_t)i * nnu + j];
+        double Msum = 0.0;
+#pragma unroll
+        for (int k = 0; k < NSMAX; k++) {
+            if (k < ns) {
+                double tk = tau * sm_m[k];
+                double tr = exp(-tk);
+                double Be = layerplanck(B1, B2, tk, tr);
+                I[k] = I[k] * tr + Be;
+                Msum += sW[k] * I[k];
+            }
+        }
+        if (a.Mup_out && live) a.Mup_out[(size_t)np * j + i] = Msum;
+        double r = warp_sum(wj * Msum);
+        if (lane == 0) red[i * RT_WARPS + warp] += r;
+        B1 = B2;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < 2 * np; t += RT_THREADS) {
+        double s = 0.0;
+#pragma unroll
+        for (int q = 0; q < RT_WARPS; q++) s += red[t * RT_WARPS + q];
+        a.part[(size_t)blockIdx.x * 2 * np + t] = s;
+    }
+}
+
+// K7 second stage: fixed-order sum over CTAs; F[0..np) = up, F[np..2np) = down
+__global__ void flux_reduce_kernel(const double* part, int nblocks, int n2, double* F)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n2) return;
+    double s = 0.0;
+    for (int b = 0; b < nblocks; b++) s += part[(size_t)b * n2 + t];
+    F[t] = s;
+}
+
+// total slant optical depth, d-depth (core/discretized.jl:92-134): no floor, tau += tau_i*m per layer
+__global__ void __launch_bounds__(RT_THREADS) depth_kernel(const double* sig, const double* small, int64_t nnu, int np,
+                                                           int nlob, double Cg, double mfac, double* out)
+{
+    extern __shared__ double sm[];
+    const int L = np - 1;
+    const int nsmall = np + nlob * L + nlob;
+    for (int t = threadIdx.x; t < nsmall; t += RT_THREADS) sm[t] = small[t];
+    __syncthreads();
+    const double* sP = sm;
+    const double* smu = sP + np;
+    const double* swl = smu + nlob * L;
+    int64_t j = (int64_t)blockIdx.x * RT_THREADS + threadIdx.x;
+    if (j >= nnu) return;
+    double beta1 = Cg * (sig[j] / smu[0]);
+    double acc = 0.0;
+    for (int i = 0; i < L; i++) {
+        double dP = sP[i + 1] - sP[i];
+        double ti = 0.0;
+        ti += (dP * swl[0]) * beta1;
+        for (int n = 1; n < nlob - 1; n++) {
+            double bn = Cg * (sig[(size_t)(n + (nlob - 1) * i) * nnu + j] / smu[n + nlob * i]);
+            ti += (dP * swl[n]) * bn;
+        }
+        double bn = Cg * (sig[(size_t)((nlob - 1) * (i + 1)) * nnu + j] / smu[(nlob - 1) + nlob * i]);
+        ti += (dP * swl[nlob - 1]) * bn;
+        beta1 = bn;
+        acc += ti * mfac;
+    }
+    out[j] = acc;
+}
+
+template <int NS> int32_t launch_rt(cs_ctx* ctx, const RtArgs& a, int nblocks, size_t smem)
+{
+    if (smem > 48 * 1024)
+        CS_CUDA(cudaFuncSetAttribute(rt_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    rt_kernel<NS><<<nblocks, RT_THREADS, smem, ctx->stream>>>(a);
+    CS_CUDA(cudaGetLastError());
+    cs_count_launch(ctx);
+    return CS_OK;
+}
+
+int32_t check_profile_args(cs_sigma* s, int64_t np, const double* P, int32_t nlob)
+{
+    CS_REQUIRE(np >= 2, CS_ERR_ARG, "need at least two pressure levels");
+    CS_REQUIRE(nlob >= 2 && nlob <= CS_MAX_LOBATTO, CS_ERR_ARG, "nlobatto must be in [2,%d]", CS_MAX_LOBATTO);
+    CS_REQUIRE(s->nnode == (np - 1) * (nlob - 1) + 1, CS_ERR_ARG,
+               "sigma workspace has %lld nodes, expected (np-1)*(nlobatto-1)+1 = %lld", (long long)s->nnode,
+               (long long)((np - 1) * (nlob - 1) + 1));
+    // issorted(P) (fluxes.jl:257)
+    for (int64_t i = 1; i < np; i++)
+        CS_REQUIRE(P[i] >= P[i - 1], CS_ERR_ARG, "pressure coordinates must be in ascending order (sorted)");
+    return CS_OK;
+}
+
+int32_t fluxes_impl(cs_sigma* s, int64_t np, const double* P, int32_t nlob, const double* wlob, const double* mu,
+                    const double* Tlev, double g, const double* fS, const double* fa, double theta_s,
+                    int32_t nstream, const double* m, const double* W, const double* nu_weights, double* tau,
+                    double* Mup, double* Mdn, double* h_F, double* d_F)
+{
+    CS_REQUIRE(s && P && wlob && mu && Tlev && m && W, CS_ERR_ARG, "null argument");
+    cs_ctx* ctx = s->ctx;
+    CS_TRY(check_profile_args(s, np, P, nlob));
+    CS_REQUIRE(nstream >= 1 && nstream <= CS_MAX_STREAMS, CS_ERR_ARG, "nstream must be in [1,%d]", CS_MAX_STREAMS);
+    // checkazimuth (fluxes.jl:4-6)
+    CS_REQUIRE(theta_s >= 0 && theta_s < CS_PI / 2, CS_ERR_ARG, "azimuth angle theta must be in [0,pi/2)");
+    CS_REQUIRE(g > 0, CS_ERR_ARG, "gravity must be positive");
+    std::lock_guard<std::recursive_mutex> lk(ctx->mtx);
+    CS_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int64_t nnu = s->nnu;
+    const int L = (int)np - 1;
+
+    // pack the small per-level arrays
+    std::vector<double> small;
+    small.reserve((size_t)(2 * np + nlob * L + nlob + 2 * nstream));
+    small.insert(small.end(), P, P + np);
+    small.insert(small.end(), mu, mu + (size_t)nlob * L);
+    small.insert(small.end(), wlob, wlob + nlob);
+    for (int64_t i = 0; i < np; i++) small.push_back(CS_KB * Tlev[i]);
+    small.insert(small.end(), m, m + nstream);
+    small.insert(small.end(), W, W + nstream);
+
+    // trapezoid weights (util.jl:26-33 rewritten per point): w_j = (dnu_{j-1} + dnu_j)/2
+    std::vector<double> hw;
+    const double* wsrc = nu_weights;
+    if (!wsrc) {
+        hw.resize((size_t)nnu);
+        const double* x = s->h_nu.data();
+        for (int64_t j = 0; j < nnu; j++) {
+            double dl = j > 0 ? x[j] - x[j - 1] : 0.0;
+            double dr = j + 1 < nnu ? x[j + 1] - x[j] : 0.0;
+            hw[(size_t)j] = (dl + dr) / 2;
+        }
+        wsrc = hw.data();
+    }
+    const int nblocks = (int)((nnu + RT_THREADS - 1) / RT_THREADS);
+    size_t off_small = 0;
+    size_t off_w = ((small.size() * sizeof(double) + 255) / 256) * 256;
+    size_t off_fS = off_w + (((size_t)nnu * sizeof(double) + 255) / 256) * 256;
+    size_t off_fa = off_fS + (((size_t)nnu * sizeof(double) + 255) / 256) * 256;
+    size_t off_F = off_fa + (((size_t)nnu * sizeof(double) + 255) / 256) * 256;
+    size_t total = off_F + sizeof(double) * 2 * (size_t)np;
+    CS_TRY(ctx->s_misc.reserve(total));
+    char* base = ctx->s_misc.as<char>();
+    CS_CUDA(cudaMemcpyAsync(base + off_small, small.data(), small.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    CS_CUDA(cudaMemcpyAsync(base + off_w, wsrc, sizeof(double) * (size_t)nnu, cudaMemcpyHostToDevice, st));
+    if (fS) CS_CUDA(cudaMemcpyAsync(base + off_fS, fS, sizeof(double) * (size_t)nnu, cudaMemcpyHostToDevice, st));
+    if (fa) CS_CUDA(cudaMemcpyAsync(base + off_fa, fa, sizeof(double) * (size_t)nnu, cudaMemcpyHostToDevice, st));
+    CS_TRY(ctx->s_tau.reserve(sizeof(double) * (size_t)L * nnu));
+    CS_TRY(ctx->s_planck.reserve(sizeof(double) * (size_t)np * nnu));
+    CS_TRY(ctx->s_part.reserve(sizeof(double) * (size_t)nblocks * 2 * np));
+    if (tau) CS_TRY(ctx->s_out0.reserve(sizeof(double) * (size_t)L * nnu));
+    if (Mup) CS_TRY(ctx->s_out1.reserve(sizeof(double) * (size_t)np * nnu));
+    if (Mdn) CS_TRY(ctx->s_out2.reserve(sizeof(double) * (size_t)np * nnu));
+
+    RtArgs a;
+    a.sig = s->sig; a.nu = s->nu; a.w = (const double*)(base + off_w);
+    a.fS = fS ? (const double*)(base + off_fS) : nullptr;
+    a.fa = fa ? (const double*)(base + off_fa) : nullptr;
+    a.small = (const double*)(base + off_small);
+    a.nnu = nnu; a.np = (int)np; a.nlob = nlob; a.ns = nstream;
+    a.Cg = 1e-4 * CS_NA / g;          // fluxes.jl:259
+    a.cos_s = cos(theta_s);
+    a.tau_s = ctx->s_tau.as<double>(); a.B_s = ctx->s_planck.as<double>();
+    a.tau_out = tau ? ctx->s_out0.as<double>() : nullptr;
+    a.Mup_out = Mup ? ctx->s_out1.as<double>() : nullptr;
+    a.Mdn_out = Mdn ? ctx->s_out2.as<double>() : nullptr;
+    a.part = ctx->s_part.as<double>();
+    size_t smem = sizeof(double) * (small.size() + (size_t)2 * np * RT_WARPS);
+
+    CS_CUDA(cudaEventRecord(ctx->ev0, st));
+    switch (nstream) {
+    case 1: CS_TRY(launch_rt<1>(ctx, a, nblocks, smem)); break;
+    case 2: CS_TRY(launch_rt<2>(ctx, a, nblocks, smem)); break;
+    case 3: CS_TRY(launch_rt<3>(ctx, a, nblocks, smem)); break;
+    case 4: CS_TRY(launch_rt<4>(ctx, a, nblocks, smem)); break;
+    case 5: CS_TRY(launch_rt<5>(ctx, a, nblocks, smem)); break;
+    case 6: CS_TRY(launch_rt<6>(ctx, a, nblocks, smem)); break;
+    case 7: CS_TRY(launch_rt<7>(ctx, a, nblocks, smem)); break;
+    case 8: CS_TRY(launch_rt<8>(ctx, a, nblocks, smem)); break;
+    default: CS_TRY(launch_rt<0>(ctx, a, nblocks, smem)); break;
+    }
+    CS_CUDA(cudaEventRecord(ctx->ev1, st));
+    double* dF = d_F ? d_F : (double*)(base + off_F);
+    flux_reduce_kernel<<<(2 * (int)np + 127) / 128, 128, 0, st>>>(a.part, nblocks, 2 * (int)np, dF);
+    CS_CUDA(cudaGetLastError());
+    cs_count_launch(ctx);
+    CS_CUDA(cudaEventRecord(ctx->ev2, st));
+
+    std::vector<double> F(2 * (size_t)np);
+    if (h_F) CS_CUDA(cudaMemcpyAsync(F.data(), dF, sizeof(double) * 2 * (size_t)np, cudaMemcpyDeviceToHost, st));
+    if (tau) CS_CUDA(cudaMemcpyAsync(tau, a.tau_out, sizeof(double) * (size_t)L * nnu, cudaMemcpyDeviceToHost, st));
+    if (Mup) CS_CUDA(cudaMemcpyAsync(Mup, a.Mup_out, sizeof(double) * (size_t)np * nnu, cudaMemcpyDeviceToHost, st));
+    if (Mdn) CS_CUDA(cudaMemcpyAsync(Mdn, a.Mdn_out, sizeof(double) * (size_t)np * nnu, cudaMemcpyDeviceToHost, st));
+    CS_CUDA(cudaStreamSynchronize(st));
+    float ms;
+    CS_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    ctx->last_kernel_ms[CS_T_RT] = ms;
+    CS_CUDA(cudaEventElapsedTime(&ms, ctx->ev1, ctx->ev2));
+    ctx->last_kernel_ms[CS_T_REDUCE] = ms;
+    if (h_F) std::copy(F.begin(), F.end(), h_F);
+    return CS_OK;
+}
+
+}  // namespace
+
+extern "C" int32_t cs_fluxes(cs_sigma* s, int64_t np, const double* P, int32_t nlob, const double* wlob,
+                             const double* mu, const double* Tlev, double g, const double* fS, const double* fa,
+                             double theta_s, int32_t nstream, const double* m, const double* W,
+                             const double* nu_weights, double* tau, double* Mup, double* Mdn, double* Fup,
+                             double* Fdn, double* Fnet)
+{
+    CS_REQUIRE(Fup && Fdn && Fnet, CS_ERR_ARG, "Fup/Fdn/Fnet outputs are required");
+    std::vector<double> F(2 * (size_t)(np > 0 ? np : 1));
+    CS_TRY(fluxes_impl(s, np, P, nlob, wlob, mu, Tlev, g, fS, fa, theta_s, nstream, m, W, nu_weights, tau, Mup, Mdn,
+                       F.data(), nullptr));
+    for (int64_t i = 0; i < np; i++) {
+        Fup[i] = F[(size_t)i];
+        Fdn[i] = F[(size_t)(np + i)];
+        Fnet[i] = Fup[i] - Fdn[i];     // fluxes.jl:380
+    }
+    return CS_OK;
+}
+
+extern "C" int32_t cs_fluxes_device(cs_sigma* s, int64_t np, const double* P, int32_t nlob, const double* wlob,
+                                    const double* mu, const double* Tlev, double g, const double* fS,
+                                    const double* fa, double theta_s, int32_t nstream, const double* m,
+                                    const double* W, const double* nu_weights, double* d_F)
+{
+    CS_REQUIRE(d_F, CS_ERR_ARG, "null device output");
+    return fluxes_impl(s, np, P, nlob, wlob, mu, Tlev, g, fS, fa, theta_s, nstream, m, W, nu_weights, nullptr, nullptr,
+                       nullptr, nullptr, d_F);
+}
+
+extern "C" int32_t cs_opticaldepth(cs_sigma* s, int64_t np, const double* P, int32_t nlob, const double* wlob,
+                                   const double* mu, double g, double theta, double* tau_total)
+{
+    CS_REQUIRE(s && P && wlob && mu && tau_total, CS_ERR_ARG, "null argument");
+    cs_ctx* ctx = s->ctx;
+    CS_TRY(check_profile_args(s, np, P, nlob));
+    CS_REQUIRE(theta >= 0 && theta < CS_PI / 2, CS_ERR_ARG, "azimuth angle theta must be in [0,pi/2)");
+    std::lock_guard<std::recursive_mutex> lk(ctx->mtx);
+    CS_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int L = (int)np - 1;
+    std::vector<double> small;
+    small.insert(small.end(), P, P + np);
+    small.insert(small.end(), mu, mu + (size_t)nlob * L);
+    small.insert(small.end(), wlob, wlob + nlob);
+    size_t off_out = ((small.size() * sizeof(double) + 255) / 256) * 256;
+    CS_TRY(ctx->s_misc.reserve(off_out + sizeof(double) * (size_t)s->nnu));
+    char* base = ctx->s_misc.as<char>();
+    CS_CUDA(cudaMemcpyAsync(base, small.data(), small.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    int nblocks = (int)((s->nnu + RT_THREADS - 1) / RT_THREADS);
+    depth_kernel<<<nblocks, RT_THREADS, small.size() * sizeof(double), st>>>(
+        s->sig, (const double*)base, s->nnu, (int)np, nlob, 1e-4 * CS_NA / g, 1 / cos(theta), (double*)(base + off_out));
+    CS_CUDA(cudaGetLastError());
+    cs_count_launch(ctx);
+    CS_CUDA(cudaMemcpyAsync(tau_total, base + off_out, sizeof(double) * (size_t)s->nnu, cudaMemcpyDeviceToHost, st));
+    CS_CUDA(cudaStreamSynchronize(st));
+    return CS_OK;
+}

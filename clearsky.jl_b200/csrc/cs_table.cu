@@ -1,0 +1,710 @@
+// cs_table.cu -- K3 opacity-table fit, K4 table evaluation, K4b/K4c accelerated absorber, K5 CIA, and cs_bake.
+//
+// Replaces bake (src/absorption/gases.jl:97-145), the OpacityTable constructor and call (:75-85), the Gas
+// functor (:278), AcceleratedAbsorber update!/Sigma (src/absorption/absorbers.jl:173-203) and the CIA functor
+// (src/absorption/collision_induced_absorption.jl:251-276, 295-303, 378-382, 465).
+//
+// Layout in HBM: every per-wavenumber quantity is stored "coefficient-major", [k][nu] with nu fastest, so that a
+// warp of consecutive wavenumbers always reads one contiguous 256-byte segment per coefficient / node.
+#include "cs_internal.cuh"
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+
+namespace {
+
+constexpr double TINY = DBL_MIN;   // floatmin(Float64)
+
+int32_t upload_d(double** dst, const double* src, size_t n, cudaStream_t st)
+{
+    *dst = nullptr;
+    if (n == 0) return CS_OK;
+    if (cudaMalloc((void**)dst, sizeof(double) * n) != cudaSuccess) {
+        cs_set_error("cudaMalloc(%zu bytes) failed", sizeof(double) * n);
+        return CS_ERR_NOMEM;
+    }
+    CS_CUDA(cudaMemcpyAsync(*dst, src, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+    return CS_OK;
+}
+
+// ---- K3a: zero-mixing repair (gases.jl:131-142) + log with the all-zero rule (gases.jl:75-81), in place
+__global__ void __launch_bounds__(256) table_log_kernel(double* blk, int64_t nnu, int nk, unsigned long long* nzeroed)
+{
+    int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nnu) return;
+    double mn = INFINITY, mx = -INFINITY;
+    bool allz = true;
+    for (int k = 0; k < nk; k++) {
+        double s = blk[(size_t)k * nnu + v];
+        mn = fmin(mn, s);
+        mx = fmax(mx, s);
+        if (!(s <= TINY)) allz = false;
+    }
+    if (mn == 0 && mx > 0) {
+        allz = true;
+        atomicAdd(nzeroed, 1ULL);
+    }
+    const double lt = log(TINY);
+    for (int k = 0; k < nk; k++) {
+        size_t o = (size_t)k * nnu + v;
+        blk[o] = allz ? lt : log(blk[o]);
+    }
+}
+// same decision, but writes sigma (zeroed where mixed) instead of logs: the block handed back to Julia
+__global__ void __launch_bounds__(256) table_zero_kernel(double* blk, int64_t nnu, int nk)
+{
+    int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nnu) return;
+    double mn = INFINITY, mx = -INFINITY;
+    for (int k = 0; k < nk; k++) {
+        double s = blk[(size_t)k * nnu + v];
+        mn = fmin(mn, s);
+        mx = fmax(mx, s);
+    }
+    if (mn == 0 && mx > 0)
+        for (int k = 0; k < nk; k++) blk[(size_t)k * nnu + v] = 0.0;
+}
+
+// ---- K3b: one separable pass of the 2-D Chebyshev transform.  axis 0: along T (index i of k = i + nT*j),
+// axis 1: along ln P (index j).  M is the n x n interpolation-coefficient matrix (row-major, M[out][in]).
+__global__ void __launch_bounds__(128) cheb_pass_kernel(const double* in, double* out, int64_t nnu, int nT, int nP,
+                                                        int axis, const double* M)
+{
+    extern __shared__ double sM[];
+    const int n = axis == 0 ? nT : nP;
+    for (int t = threadIdx.x; t < n * n; t += blockDim.x) sM[t] = M[t];
+    __syncthreads();
+    int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int other = blockIdx.y;   // j for axis 0, i for axis 1
+    if (v >= nnu) return;
+    double f[CS_MAX_NODES];
+    const size_t base = axis == 0 ? (size_t)nT * other : (size_t)other;
+    const size_t step = axis == 0 ? 1 : (size_t)nT;
+    for (int q = 0; q < n; q++) f[q] = in[(base + step * q) * nnu + v];
+    for (int o = 0; o < n; o++) {
+        double acc = 0.0;
+        for (int q = 0; q < n; q++) acc = fma(sM[o * n + q], f[q], acc);
+        out[(base + step * o) * nnu + v] = acc;
+    }
+}
+
+// ---- K4: table evaluation at a block of LB levels.  basis[l][k] = T_i(xi_T(l)) * T_j(xi_P(l)).
+// mode 0: out[l][nu] = exp(.)           (rawsigma, gases.jl:85,256)
+// mode 1: out[l][nu] += C[l]*exp(.)     (Gas functor, gases.jl:278)
+template <int LB>
+__global__ void __launch_bounds__(128) table_eval_kernel(const double* coef, int64_t nnu, int nk, const double* basis,
+                                                         const double* C, int nlev, double* out, int mode)
+{
+    extern __shared__ double sb[];   // [nk][LB]
+    const int l0 = blockIdx.y * LB;
+    for (int t = threadIdx.x; t < nk * LB; t += blockDim.x) {
+        int k = t / LB, l = t % LB;
+        sb[t] = (l0 + l < nlev) ? basis[(size_t)(l0 + l) * nk + k] : 0.0;
+    }
+    __syncthreads();
+    int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nnu) return;
+    double acc[LB];
+#pragma unroll
+    for (int l = 0; l < LB; l++) acc[l] = 0.0;
+    for (int k = 0; k < nk; k++) {
+        double a = coef[(size_t)k * nnu + v];
+#pragma unroll
+        for (int l = 0; l < LB; l++) acc[l] = fma(a, sb[k * LB + l], acc[l]);
+    }
+#pragma unroll
+    for (int l = 0; l < LB; l++) {
+        if (l0 + l < nlev) {
+            size_t o = (size_t)(l0 + l) * nnu + v;
+            double s = exp(acc[l]);
+            out[o] = mode ? out[o] + C[l0 + l] * s : s;
+        }
+    }
+}
+
+// ---- accelerated absorber
+__global__ void accel_snapshot_kernel(const double* sig, double* lnsig, size_t n)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    const double lt = log(TINY);
+    for (; i < n; i += stride) {
+        double l = log(sig[i]);
+        lnsig[i] = (l < lt) ? lt : l;     // absorbers.jl:193-195
+    }
+}
+// node descriptors: cell index and ln P of each node
+__global__ void accel_eval_kernel(const double* lnsig, int64_t nnu, const double* lnP, const int* cell, const double* q,
+                                  int nnode, double* out)
+{
+    int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int m = blockIdx.y;
+    if (v >= nnu || m >= nnode) return;
+    int i = cell[m];
+    double ya = lnsig[(size_t)i * nnu + v], yb = lnsig[(size_t)(i + 1) * nnu + v];
+    double y = (q[m] - lnP[i]) * (yb - ya) / (lnP[i + 1] - lnP[i]) + ya;
+    out[(size_t)m * nnu + v] += exp(y);   // absorbers.jl:203
+}
+
+// ---- K5: CIA
+struct CiaNode {
+    double T, P, P1, P2;
+};
+struct CiaGridNode {   // per (grid, node): how this node uses grid g
+    int use;           // 0: skip, 1: interpolate at (nu, Tq)
+    int jT;
+    double Tq;         // T or the clamped T
+};
+
+__device__ __forceinline__ int findcell_dev(const double* x, int n, double q)
+{
+    if (q <= x[0]) return 0;
+    if (q >= x[n - 1]) return n - 2;
+    int lo = 0, hi = n - 1;
+    while (hi - lo > 1) {
+        int m = (lo + hi) >> 1;
+        if (x[m] > q) hi = m; else lo = m;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(128) cia_kernel(const double* nu, int64_t nnu, int ngrid, const int64_t* desc,
+                                                  const double* gnu, const double* gT, const double* glnk,
+                                                  int nsingle, const int64_t* sdesc, const double* snu,
+                                                  const double* slnk, int use_singles, const CiaNode* nodes,
+                                                  const CiaGridNode* gn, int nnode, double* out)
+{
+    int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nnu) return;
+    const double x = nu[v];
+    for (int m = 0; m < nnode; m++) {
+        double k = 0.0;
+        for (int g = 0; g < ngrid; g++) {
+            const int64_t nx = desc[5 * g + 0], ny = desc[5 * g + 1];
+            const double* gx = gnu + desc[5 * g + 2];
+            const double* gy = gT + desc[5 * g + 3];
+            const double* Z = glnk + desc[5 * g + 4];
+            CiaGridNode d = gn[(size_t)g * nnode + m];
+            if (d.use && gx[0] <= x && x <= gx[nx - 1]) {
+                int i = findcell_dev(gx, (int)nx, x);
+                int j = d.jT;
+                double xx = (x - gx[i]) / (gx[i + 1] - gx[i]);
+                double yy = (d.Tq - gy[j]) / (gy[j + 1] - gy[j]);
+                double z = (1 - xx) * (1 - yy) * Z[i + nx * j] + xx * (1 - yy) * Z[i + 1 + nx * j] +
+                           xx * yy * Z[i + 1 + nx * (j + 1)] + (1 - xx) * yy * Z[i + nx * (j + 1)];
+                k += exp(z);
+            }
+            (void)ny;
+        }
+        if (use_singles) {
+            for (int s = 0; s < nsingle; s++) {
+                const int64_t n = sdesc[2 * s + 0];
+                const double* sx = snu + sdesc[2 * s + 1];
+                const double* sy = slnk + sdesc[2 * s + 1];
+                if (sx[0] <= x && x <= sx[n - 1]) {
+                    int i = findcell_dev(sx, (int)n, x);
+                    double y = (x - sx[i]) * (sy[i + 1] - sy[i]) / (sx[i + 1] - sx[i]) + sy[i];
+                    k += exp(y);
+                }
+            }
+        }
+        CiaNode nd = nodes[m];
+        // cia(k, T, Pa, P1, P2)  (collision_induced_absorption.jl:295-303)
+        double rho1 = (nd.P1 / CS_ATM) * (CS_T0 / nd.T);
+        double rho2 = (nd.P2 / CS_ATM) * (CS_T0 / nd.T);
+        double rhoa = 1e-6 * nd.P / (CS_KB * nd.T);
+        out[(size_t)m * nnu + v] += (k * CS_LO2) * rho1 * rho2 / rhoa;
+    }
+}
+
+// interpolation-coefficient matrix of chebygrid(n) (ascending nodes): c_j = sum_k M[j][k] f_k
+void cheb_matrix(int n, std::vector<double>& M)
+{
+    M.assign((size_t)n * n, 0.0);
+    for (int j = 0; j < n; j++)
+        for (int k = 0; k < n; k++) {
+            double theta = CS_PI * (double)(n - 1 - k) / (double)(n - 1);
+            double w = (k == 0 || k == n - 1) ? 0.5 : 1.0;
+            double s = w * cos(j * theta) * (2.0 / (double)(n - 1));
+            if (j == 0 || j == n - 1) s *= 0.5;
+            M[(size_t)j * n + k] = s;
+        }
+}
+
+int32_t check_grid(int32_t nT, const double* Tg, int32_t nP, const double* Pg)
+{
+    CS_REQUIRE(nT >= 2 && nT <= CS_MAX_NODES && nP >= 2 && nP <= CS_MAX_NODES, CS_ERR_ARG,
+               "table grid must have 2..%d nodes per axis (got %d x %d)", CS_MAX_NODES, nT, nP);
+    for (int i = 1; i < nT; i++) CS_REQUIRE(Tg[i] > Tg[i - 1], CS_ERR_ARG, "temperature grid must ascend");
+    for (int i = 1; i < nP; i++) CS_REQUIRE(Pg[i] > Pg[i - 1], CS_ERR_ARG, "pressure grid must ascend");
+    CS_REQUIRE(Pg[0] > 0, CS_ERR_ARG, "pressure range must be positive");
+    // the interpolator requires Chebyshev (extrema) nodes; verify like BichebyshevInterpolator does
+    for (int i = 0; i < nT; i++) {
+        double xi = cos(CS_PI * (double)(nT - 1 - i) / (double)(nT - 1));
+        double e = (xi + 1) * ((Tg[nT - 1] - Tg[0]) / 2) + Tg[0];
+        CS_REQUIRE(fabs(e - Tg[i]) <= 1e-9 * fabs(Tg[nT - 1]), CS_ERR_ARG, "temperature nodes are not a Chebyshev grid");
+    }
+    for (int i = 0; i < nP; i++) {
+        double a = log(Pg[0]), b = log(Pg[nP - 1]);
+        double xi = cos(CS_PI * (double)(nP - 1 - i) / (double)(nP - 1));
+        double e = (xi + 1) * ((b - a) / 2) + a;
+        CS_REQUIRE(fabs(e - log(Pg[i])) <= 1e-9 * (fabs(a) + fabs(b) + 1), CS_ERR_ARG,
+                   "log-pressure nodes are not a Chebyshev grid");
+    }
+    return CS_OK;
+}
+
+// fit coefficients from a device sigma block [nk][nnu] (destroyed: becomes ln sigma)
+int32_t fit_table(cs_ctx* ctx, cs_table* tb, double* d_block)
+{
+    cudaStream_t st = ctx->stream;
+    const int nT = tb->nT, nP = tb->nP, nk = nT * nP;
+    const int64_t nnu = tb->nnu;
+    std::vector<double> Mx, My;
+    cheb_matrix(nT, Mx);
+    cheb_matrix(nP, My);
+    size_t offy = ((Mx.size() * sizeof(double) + 255) / 256) * 256;
+    size_t offc = offy + ((My.size() * sizeof(double) + 255) / 256) * 256;
+    CS_TRY(ctx->s_misc.reserve(offc + 64));
+    char* base = ctx->s_misc.as<char>();
+    CS_CUDA(cudaMemcpyAsync(base, Mx.data(), Mx.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    CS_CUDA(cudaMemcpyAsync(base + offy, My.data(), My.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    CS_CUDA(cudaMemsetAsync(base + offc, 0, 8, st));
+    CS_CUDA(cudaEventRecord(ctx->ev0, st));
+    unsigned nb = (unsigned)((nnu + 255) / 256);
+    table_log_kernel<<<nb, 256, 0, st>>>(d_block, nnu, nk, (unsigned long long*)(base + offc));
+    CS_CUDA(cudaGetLastError());
+    // pass along T: block -> coef ; pass along ln P: coef -> block ; final copy back into coef
+    dim3 gA((unsigned)((nnu + 127) / 128), (unsigned)nP);
+    cheb_pass_kernel<<<gA, 128, sizeof(double) * nT * nT, st>>>(d_block, tb->coef, nnu, nT, nP, 0, (const double*)base);
+    CS_CUDA(cudaGetLastError());
+    dim3 gB((unsigned)((nnu + 127) / 128), (unsigned)nT);
+    cheb_pass_kernel<<<gB, 128, sizeof(double) * nP * nP, st>>>(tb->coef, d_block, nnu, nT, nP, 1, (const double*)(base + offy));
+    CS_CUDA(cudaGetLastError());
+    CS_CUDA(cudaMemcpyAsync(tb->coef, d_block, sizeof(double) * (size_t)nk * nnu, cudaMemcpyDeviceToDevice, st));
+    cs_count_launch(ctx, 3);
+    CS_CUDA(cudaEventRecord(ctx->ev1, st));
+    unsigned long long nz = 0;
+    CS_CUDA(cudaMemcpyAsync(&nz, base + offc, 8, cudaMemcpyDeviceToHost, st));
+    CS_CUDA(cudaStreamSynchronize(st));
+    float ms;
+    CS_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    ctx->last_kernel_ms[CS_T_TABLE_FIT] += ms;
+    tb->nzeroed = (int64_t)nz;
+    return CS_OK;
+}
+
+cs_table* new_table(cs_ctx* ctx, int64_t nnu, int32_t nT, const double* Tg, int32_t nP, const double* Pg)
+{
+    cs_table* tb = new cs_table();
+    tb->ctx = ctx;
+    tb->nnu = nnu;
+    tb->nT = nT;
+    tb->nP = nP;
+    tb->Ta = Tg[0];
+    tb->Tb = Tg[nT - 1];
+    tb->lnPa = log(Pg[0]);          // the table is built on log.(Omega.P) (gases.jl:78)
+    tb->lnPb = log(Pg[nP - 1]);
+    tb->coef = nullptr;
+    tb->sigma_block = nullptr;
+    tb->nzeroed = 0;
+    return tb;
+}
+
+int32_t eval_table(cs_table* tb, int64_t nlev, const double* T, const double* P, const double* C, double* d_out, int mode)
+{
+    cs_ctx* ctx = tb->ctx;
+    cudaStream_t st = ctx->stream;
+    const int nT = tb->nT, nP = tb->nP, nk = nT * nP;
+    std::vector<double> basis((size_t)nlev * nk);
+    std::vector<double> ct((size_t)nT), cp((size_t)nP);
+    for (int64_t l = 0; l < nlev; l++) {
+        double lp = log(P[l]);
+        // StrictBoundaries: out-of-domain coordinates are an error (gases.jl:85 via BichebyshevInterpolator)
+        CS_REQUIRE(T[l] >= tb->Ta && T[l] <= tb->Tb, CS_ERR_DOMAIN,
+                   "temperature %g K outside the opacity-table domain [%g, %g]", T[l], tb->Ta, tb->Tb);
+        CS_REQUIRE(lp >= tb->lnPa && lp <= tb->lnPb, CS_ERR_DOMAIN,
+                   "pressure %g Pa outside the opacity-table domain [%g, %g]", P[l], exp(tb->lnPa), exp(tb->lnPb));
+        double xt = 2 * (T[l] - tb->Ta) / (tb->Tb - tb->Ta) - 1;
+        double xp = 2 * (lp - tb->lnPa) / (tb->lnPb - tb->lnPa) - 1;
+        ct[0] = 1; ct[1] = xt;
+        for (int k = 2; k < nT; k++) ct[(size_t)k] = 2 * xt * ct[(size_t)k - 1] - ct[(size_t)k - 2];
+        cp[0] = 1; cp[1] = xp;
+        for (int k = 2; k < nP; k++) cp[(size_t)k] = 2 * xp * cp[(size_t)k - 1] - cp[(size_t)k - 2];
+        for (int j = 0; j < nP; j++)
+            for (int i = 0; i < nT; i++) basis[(size_t)l * nk + i + (size_t)nT * j] = ct[(size_t)i] * cp[(size_t)j];
+    }
+    size_t offC = ((basis.size() * sizeof(double) + 255) / 256) * 256;
+    CS_TRY(ctx->s_misc.reserve(offC + sizeof(double) * (size_t)nlev));
+    char* base = ctx->s_misc.as<char>();
+    CS_CUDA(cudaMemcpyAsync(base, basis.data(), basis.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (C) CS_CUDA(cudaMemcpyAsync(base + offC, C, sizeof(double) * (size_t)nlev, cudaMemcpyHostToDevice, st));
+    CS_CUDA(cudaEventRecord(ctx->ev0, st));
+    // levels per CTA limited by shared memory (nk*LB doubles)
+    int LB = 8;
+    while (LB > 1 && (size_t)nk * LB * sizeof(double) > 200 * 1024) LB >>= 1;
+    size_t smem = (size_t)nk * LB * sizeof(double);
+    dim3 grid((unsigned)((tb->nnu + 127) / 128), (unsigned)((nlev + LB - 1) / LB));
+#define CS_LAUNCH_EVAL(LBV)                                                                                         \
+    do {                                                                                                            \
+        if (smem > 48 * 1024)                                                                                       \
+            CS_CUDA(cudaFuncSetAttribute(table_eval_kernel<LBV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        table_eval_kernel<LBV><<<grid, 128, smem, st>>>(tb->coef, tb->nnu, nk, (const double*)base,                \
+                                                        (const double*)(base + offC), (int)nlev, d_out, mode);      \
+    } while (0)
+    if (LB == 8) CS_LAUNCH_EVAL(8);
+    else if (LB == 4) CS_LAUNCH_EVAL(4);
+    else if (LB == 2) CS_LAUNCH_EVAL(2);
+    else CS_LAUNCH_EVAL(1);
+#undef CS_LAUNCH_EVAL
+    CS_CUDA(cudaGetLastError());
+    cs_count_launch(ctx);
+    CS_CUDA(cudaEventRecord(ctx->ev1, st));
+    CS_CUDA(cudaStreamSynchronize(st));
+    float ms;
+    CS_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    ctx->last_kernel_ms[CS_T_TABLE_EVAL] += ms;
+    return CS_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+extern "C" int32_t cs_table_from_block(cs_ctx* ctx, int64_t nnu, int32_t nT, const double* Tg, int32_t nP,
+                                       const double* Pg, const double* block, cs_table** out)
+{
+    CS_REQUIRE(ctx && Tg && Pg && block && out, CS_ERR_ARG, "null argument");
+    *out = nullptr;
+    CS_REQUIRE(nnu > 0, CS_ERR_ARG, "no wavenumbers");
+    CS_TRY(check_grid(nT, Tg, nP, Pg));
+    std::lock_guard<std::recursive_mutex> lk(ctx->mtx);
+    CS_CUDA(cudaSetDevice(ctx->device));
+    cs_table* tb = new_table(ctx, nnu, nT, Tg, nP, Pg);
+    size_t bytes = sizeof(double) * (size_t)nT * nP * nnu;
+    if (cudaMalloc((void**)&tb->coef, bytes) != cudaSuccess) {
+        delete tb;
+        cs_set_error("cudaMalloc(table %zu bytes) failed", bytes);
+        return CS_ERR_NOMEM;
+    }
+    int32_t rc = ctx->s_sigma.reserve(bytes);
+    if (rc) { cs_table_free(tb); return rc; }
+    CS_CUDA(cudaMemcpyAsync(ctx->s_sigma.p, block, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    rc = fit_table(ctx, tb, ctx->s_sigma.as<double>());
+    if (rc) { cs_table_free(tb); return rc; }
+    *out = tb;
+    return CS_OK;
+}
+
+extern "C" int32_t cs_bake(cs_lines* L, int32_t shape, int64_t nnu, const double* nu, int32_t nT, const double* Tg,
+                           int32_t nP, const double* Pg, const double* C, double cut, int32_t keep_block,
+                           cs_table** out)
+{
+    CS_REQUIRE(L && nu && Tg && Pg && C && out, CS_ERR_ARG, "null argument");
+    *out = nullptr;
+    cs_ctx* ctx = L->ctx;
+    CS_TRY(check_grid(nT, Tg, nP, Pg));
+    CS_REQUIRE(nnu > 0, CS_ERR_ARG, "no wavenumbers");
+    for (int64_t i = 1; i < nnu; i++)
+        CS_REQUIRE(nu[i] > nu[i - 1], CS_ERR_ARG, "wavenumbers must be unique and in ascending order");   // gases.jl:92
+    CS_REQUIRE(nu[0] >= 0, CS_ERR_ARG, "wavenumbers must be positive");                                   // gases.jl:93
+    // AtmosphericDomain's Qref/Q range asserts (gases.jl:51-52)
+    CS_REQUIRE(Tg[0] >= CS_TMIN && Tg[nT - 1] <= CS_TMAX, CS_ERR_DOMAIN, "temperature grid outside [%g,%g] K", CS_TMIN, CS_TMAX);
+    const int nk = nT * nP;
+    std::vector<double> T((size_t)nk), P((size_t)nk), Pp((size_t)nk);
+    for (int j = 0; j < nP; j++)
+        for (int i = 0; i < nT; i++) {
+            size_t k = (size_t)i + (size_t)nT * j;
+            // gases.jl:124
+            CS_REQUIRE(C[k] >= 0 && C[k] <= 1, CS_ERR_ARG,
+                       "gas molar concentrations must be in [0,1], not %g (encountered @ %g K, %g Pa)", C[k], Tg[i], Pg[j]);
+            T[k] = Tg[i];
+            P[k] = Pg[j];
+            Pp[k] = C[k] * Pg[j];   // shape!(..., T, P, C*P, cut)  (gases.jl:126)
+        }
+    std::lock_guard<std::recursive_mutex> lk(ctx->mtx);
+    CS_CUDA(cudaSetDevice(ctx->device));
+    cs_reset_timers(ctx);
+    cs_table* tb = new_table(ctx, nnu, nT, Tg, nP, Pg);
+    size_t bytes = sizeof(double) * (size_t)nk * nnu;
+    double* blk = nullptr;
+    if (cudaMalloc((void**)&tb->coef, bytes) != cudaSuccess || cudaMalloc((void**)&blk, bytes) != cudaSuccess) {
+        if (tb->coef) cudaFree(tb->coef);
+        delete tb;
+        cs_set_error("cudaMalloc(table 2 x %zu bytes) failed", bytes);
+        return CS_ERR_NOMEM;
+    }
+    int32_t rc = ctx->s_nu.reserve(sizeof(double) * (size_t)nnu);
+    if (!rc) {
+        cudaMemcpyAsync(ctx->s_nu.p, nu, sizeof(double) * (size_t)nnu, cudaMemcpyHostToDevice, ctx->stream);
+        rc = cs_lines_accumulate(L, shape, nnu, ctx->s_nu.as<double>(), nu, nk, T.data(), P.data(), Pp.data(), nullptr,
+                                 cut, blk, 0);
+    }
+    if (!rc && keep_block) {
+        // keep sigma with the zero-mixing repair applied, exactly what bake hands to OpacityTable
+        if (cudaMalloc((void**)&tb->sigma_block, bytes) != cudaSuccess) {
+            cs_set_error("cudaMalloc(sigma block %zu bytes) failed", bytes);
+            rc = CS_ERR_NOMEM;
+        } else {
+            cudaMemcpyAsync(tb->sigma_block, blk, bytes, cudaMemcpyDeviceToDevice, ctx->stream);
+            table_zero_kernel<<<(unsigned)((nnu + 255) / 256), 256, 0, ctx->stream>>>(tb->sigma_block, nnu, nk);
+            cs_count_launch(ctx);
+        }
+    }
+    if (!rc) rc = fit_table(ctx, tb, blk);
+    cudaFree(blk);
+    if (rc) { cs_table_free(tb); return rc; }
+    *out = tb;
+    return CS_OK;
+}
+
+extern "C" int32_t cs_table_eval(cs_table* tb, int64_t nlev, const double* T, const double* P, double* sigma)
+{
+    CS_REQUIRE(tb && T && P && sigma && nlev > 0, CS_ERR_ARG, "null argument");
+    cs_ctx* ctx = tb->ctx;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mtx);
+    CS_CUDA(cudaSetDevice(ctx->device));
+    cs_reset_timers(ctx);
+    size_t bytes = sizeof(double) * (size_t)nlev * tb->nnu;
+    CS_TRY(ctx->s_sigma.reserve(bytes));
+    CS_TRY(eval_table(tb, nlev, T, P, nullptr, ctx->s_sigma.as<double>(), 0));
+    CS_CUDA(cudaMemcpyAsync(sigma, ctx->s_sigma.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CS_CUDA(cudaStreamSynchronize(ctx->stream));
+    return CS_OK;
+}
+
+extern "C" int32_t cs_sigma_add_table(cs_sigma* s, cs_table* tb, const double* T, const double* P, const double* C)
+{
+    CS_REQUIRE(s && tb && T && P && C, CS_ERR_ARG, "null argument");
+    CS_REQUIRE(s->ctx == tb->ctx, CS_ERR_ARG, "workspace and table live on different contexts");
+    CS_REQUIRE(s->nnu == tb->nnu, CS_ERR_ARG, "gases must have identical wavenumber vectors");   // absorbers.jl:227
+    std::lock_guard<std::recursive_mutex> lk(s->ctx->mtx);
+    CS_CUDA(cudaSetDevice(s->ctx->device));
+    return eval_table(tb, s->nnode, T, P, C, s->sig, 1);
+}
+
+extern "C" int32_t cs_table_block(cs_table* tb, double* block)
+{
+    CS_REQUIRE(tb && block, CS_ERR_ARG, "null argument");
+    CS_REQUIRE(tb->sigma_block, CS_ERR_ARG, "the sigma block was not kept (pass keep_block=1 to cs_bake)");
+    std::lock_guard<std::recursive_mutex> lk(tb->ctx->mtx);
+    CS_CUDA(cudaSetDevice(tb->ctx->device));
+    CS_CUDA(cudaMemcpyAsync(block, tb->sigma_block, sizeof(double) * (size_t)tb->nT * tb->nP * tb->nnu,
+                            cudaMemcpyDeviceToHost, tb->ctx->stream));
+    CS_CUDA(cudaStreamSynchronize(tb->ctx->stream));
+    return CS_OK;
+}
+
+extern "C" int32_t cs_table_info(cs_table* tb, int64_t* nnu, int32_t* nT, int32_t* nP, int64_t* nz)
+{
+    CS_REQUIRE(tb, CS_ERR_ARG, "null argument");
+    if (nnu) *nnu = tb->nnu;
+    if (nT) *nT = tb->nT;
+    if (nP) *nP = tb->nP;
+    if (nz) *nz = tb->nzeroed;
+    return CS_OK;
+}
+
+extern "C" int32_t cs_table_free(cs_table* tb)
+{
+    if (!tb) return CS_OK;
+    cudaSetDevice(tb->ctx->device);
+    cudaStreamSynchronize(tb->ctx->stream);
+    if (tb->coef) cudaFree(tb->coef);
+    if (tb->sigma_block) cudaFree(tb->sigma_block);
+    delete tb;
+    return CS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// accelerated absorber
+extern "C" int32_t cs_accel_from_sigma(cs_sigma* s, const double* P, cs_accel** out)
+{
+    CS_REQUIRE(s && P && out, CS_ERR_ARG, "null argument");
+    *out = nullptr;
+    CS_REQUIRE(s->nnode >= 2, CS_ERR_ARG, "need at least two pressure levels");
+    for (int64_t i = 1; i < s->nnode; i++)
+        CS_REQUIRE(P[i] > P[i - 1], CS_ERR_ARG, "AcceleratedAbsorber pressure levels must ascend (absorbers.jl:141-143)");
+    cs_ctx* ctx = s->ctx;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mtx);
+    CS_CUDA(cudaSetDevice(ctx->device));
+    cs_accel* A = new cs_accel();
+    A->ctx = ctx;
+    A->nnu = s->nnu;
+    A->nlev = s->nnode;
+    A->h_lnP.resize((size_t)s->nnode);
+    for (int64_t i = 0; i < s->nnode; i++) A->h_lnP[(size_t)i] = log(P[i]);
+    size_t n = (size_t)s->nnu * s->nnode;
+    if (cudaMalloc((void**)&A->lnsig, sizeof(double) * n) != cudaSuccess) {
+        delete A;
+        cs_set_error("cudaMalloc(accelerated absorber %zu bytes) failed", sizeof(double) * n);
+        return CS_ERR_NOMEM;
+    }
+    accel_snapshot_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(s->sig, A->lnsig, n);
+    CS_CUDA(cudaGetLastError());
+    cs_count_launch(ctx);
+    CS_CUDA(cudaStreamSynchronize(ctx->stream));
+    *out = A;
+    return CS_OK;
+}
+
+extern "C" int32_t cs_accel_free(cs_accel* A)
+{
+    if (!A) return CS_OK;
+    cudaSetDevice(A->ctx->device);
+    cudaStreamSynchronize(A->ctx->stream);
+    cudaFree(A->lnsig);
+    delete A;
+    return CS_OK;
+}
+
+extern "C" int32_t cs_sigma_add_accel(cs_sigma* s, cs_accel* A, const double* P)
+{
+    CS_REQUIRE(s && A && P, CS_ERR_ARG, "null argument");
+    CS_REQUIRE(s->ctx == A->ctx && s->nnu == A->nnu, CS_ERR_ARG, "workspace and accelerated absorber do not match");
+    cs_ctx* ctx = s->ctx;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mtx);
+    CS_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int64_t nn = s->nnode, nl = A->nlev;
+    std::vector<int> cell((size_t)nn);
+    std::vector<double> q((size_t)nn);
+    const std::vector<double>& x = A->h_lnP;
+    for (int64_t m = 0; m < nn; m++) {
+        double v = log(P[m]);
+        int64_t i;
+        if (v <= x[0]) i = 0;
+        else if (v >= x[(size_t)nl - 1]) i = nl - 2;
+        else i = (std::upper_bound(x.begin(), x.end(), v) - x.begin()) - 1;
+        cell[(size_t)m] = (int)i;
+        q[(size_t)m] = v;
+    }
+    size_t offq = (((size_t)nl * sizeof(double) + 255) / 256) * 256;
+    size_t offc = offq + (((size_t)nn * sizeof(double) + 255) / 256) * 256;
+    CS_TRY(ctx->s_misc.reserve(offc + sizeof(int) * (size_t)nn));
+    char* base = ctx->s_misc.as<char>();
+    CS_CUDA(cudaMemcpyAsync(base, x.data(), sizeof(double) * (size_t)nl, cudaMemcpyHostToDevice, st));
+    CS_CUDA(cudaMemcpyAsync(base + offq, q.data(), sizeof(double) * (size_t)nn, cudaMemcpyHostToDevice, st));
+    CS_CUDA(cudaMemcpyAsync(base + offc, cell.data(), sizeof(int) * (size_t)nn, cudaMemcpyHostToDevice, st));
+    dim3 grid((unsigned)((s->nnu + 255) / 256), (unsigned)nn);
+    accel_eval_kernel<<<grid, 256, 0, st>>>(A->lnsig, s->nnu, (const double*)base, (const int*)(base + offc),
+                                            (const double*)(base + offq), (int)nn, s->sig);
+    CS_CUDA(cudaGetLastError());
+    cs_count_launch(ctx);
+    CS_CUDA(cudaStreamSynchronize(st));
+    return CS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// CIA
+extern "C" int32_t cs_cia_upload(cs_ctx* ctx, int32_t ngrid, const int64_t* g_nnu, const int64_t* g_nT,
+                                 const double* g_nu, const double* g_T, const double* g_lnk, int32_t nsingle,
+                                 const int64_t* s_n, const double* s_nu, const double* s_lnk, int32_t extrapolate,
+                                 int32_t singles, cs_cia** out)
+{
+    CS_REQUIRE(ctx && out, CS_ERR_ARG, "null argument");
+    *out = nullptr;
+    CS_REQUIRE(ngrid >= 0 && nsingle >= 0 && ngrid + nsingle > 0, CS_ERR_ARG, "empty CIA tables");
+    std::lock_guard<std::recursive_mutex> lk(ctx->mtx);
+    CS_CUDA(cudaSetDevice(ctx->device));
+    cs_cia* c = new cs_cia();
+    c->ctx = ctx;
+    c->ngrid = ngrid;
+    c->nsingle = nsingle;
+    c->extrapolate = extrapolate;
+    c->singles = singles;
+    c->d_nu = c->d_T = c->d_lnk = c->d_snu = c->d_slnk = nullptr;
+    c->d_desc = nullptr;
+    int64_t onu = 0, oT = 0, ok = 0;
+    std::vector<int64_t> desc;
+    for (int g = 0; g < ngrid; g++) {
+        CS_REQUIRE(g_nnu[g] >= 2 && g_nT[g] >= 2, CS_ERR_ARG, "CIA grid %d needs >= 2 points per axis", g);
+        c->g_nnu.push_back(g_nnu[g]); c->g_nT.push_back(g_nT[g]);
+        c->g_off_nu.push_back(onu); c->g_off_T.push_back(oT); c->g_off_k.push_back(ok);
+        desc.push_back(g_nnu[g]); desc.push_back(g_nT[g]); desc.push_back(onu); desc.push_back(oT); desc.push_back(ok);
+        onu += g_nnu[g]; oT += g_nT[g]; ok += g_nnu[g] * g_nT[g];
+    }
+    c->h_T.assign(g_T, g_T + oT);
+    int64_t os = 0;
+    for (int s = 0; s < nsingle; s++) {
+        CS_REQUIRE(s_n[s] >= 2, CS_ERR_ARG, "CIA single-temperature table %d needs >= 2 points", s);
+        c->s_n.push_back(s_n[s]); c->s_off.push_back(os);
+        desc.push_back(s_n[s]); desc.push_back(os);
+        os += s_n[s];
+    }
+    cudaStream_t st = ctx->stream;
+    int32_t rc = CS_OK;
+    if ((ngrid && ((rc = upload_d(&c->d_nu, g_nu, (size_t)onu, st)) || (rc = upload_d(&c->d_T, g_T, (size_t)oT, st)) ||
+                   (rc = upload_d(&c->d_lnk, g_lnk, (size_t)ok, st)))) ||
+        (nsingle && ((rc = upload_d(&c->d_snu, s_nu, (size_t)os, st)) || (rc = upload_d(&c->d_slnk, s_lnk, (size_t)os, st))))) {
+        cs_cia_free(c);
+        return rc;
+    }
+    if (cudaMalloc((void**)&c->d_desc, sizeof(int64_t) * desc.size()) != cudaSuccess) {
+        cs_cia_free(c);
+        cs_set_error("cudaMalloc(CIA descriptors) failed");
+        return CS_ERR_NOMEM;
+    }
+    CS_CUDA(cudaMemcpyAsync(c->d_desc, desc.data(), sizeof(int64_t) * desc.size(), cudaMemcpyHostToDevice, st));
+    CS_CUDA(cudaStreamSynchronize(st));
+    *out = c;
+    return CS_OK;
+}
+
+extern "C" int32_t cs_cia_free(cs_cia* c)
+{
+    if (!c) return CS_OK;
+    cudaSetDevice(c->ctx->device);
+    cudaStreamSynchronize(c->ctx->stream);
+    cudaFree(c->d_nu); cudaFree(c->d_T); cudaFree(c->d_lnk); cudaFree(c->d_snu); cudaFree(c->d_slnk); cudaFree(c->d_desc);
+    delete c;
+    return CS_OK;
+}
+
+extern "C" int32_t cs_sigma_add_cia(cs_sigma* s, cs_cia* c, const double* T, const double* P, const double* C1,
+                                    const double* C2)
+{
+    CS_REQUIRE(s && c && T && P && C1 && C2, CS_ERR_ARG, "null argument");
+    CS_REQUIRE(s->ctx == c->ctx, CS_ERR_ARG, "workspace and CIA tables live on different contexts");
+    cs_ctx* ctx = s->ctx;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mtx);
+    CS_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int64_t nn = s->nnode;
+    std::vector<CiaNode> nodes((size_t)nn);
+    std::vector<CiaGridNode> gn((size_t)nn * (size_t)std::max(c->ngrid, 1));
+    for (int64_t m = 0; m < nn; m++) {
+        nodes[(size_t)m] = {T[m], P[m], P[m] * C1[m], P[m] * C2[m]};   // collision_induced_absorption.jl:379-380
+        for (int g = 0; g < c->ngrid; g++) {
+            const double* y = c->h_T.data() + c->g_off_T[(size_t)g];
+            int64_t ny = c->g_nT[(size_t)g];
+            CiaGridNode d = {0, 0, T[m]};
+            if (y[0] <= T[m] && T[m] <= y[ny - 1]) d.use = 1;                       // :257
+            else if (c->extrapolate) { d.use = 1; d.Tq = T[m] > y[ny - 1] ? y[ny - 1] : y[0]; }   // :260-262
+            if (d.use) {
+                int64_t j;
+                if (d.Tq <= y[0]) j = 0;
+                else if (d.Tq >= y[ny - 1]) j = ny - 2;
+                else j = (std::upper_bound(y, y + ny, d.Tq) - y) - 1;
+                d.jT = (int)j;
+            }
+            gn[(size_t)g * nn + m] = d;
+        }
+    }
+    size_t offg = ((nodes.size() * sizeof(CiaNode) + 255) / 256) * 256;
+    CS_TRY(ctx->s_misc.reserve(offg + gn.size() * sizeof(CiaGridNode)));
+    char* base = ctx->s_misc.as<char>();
+    CS_CUDA(cudaMemcpyAsync(base, nodes.data(), nodes.size() * sizeof(CiaNode), cudaMemcpyHostToDevice, st));
+    CS_CUDA(cudaMemcpyAsync(base + offg, gn.data(), gn.size() * sizeof(CiaGridNode), cudaMemcpyHostToDevice, st));
+    CS_CUDA(cudaEventRecord(ctx->ev0, st));
+    cia_kernel<<<(unsigned)((s->nnu + 127) / 128), 128, 0, st>>>(
+        s->nu, s->nnu, c->ngrid, c->d_desc, c->d_nu, c->d_T, c->d_lnk, c->nsingle, c->d_desc + 5 * c->ngrid, c->d_snu,
+        c->d_slnk, c->singles, (const CiaNode*)base, (const CiaGridNode*)(base + offg), (int)nn, s->sig);
+    CS_CUDA(cudaGetLastError());
+    cs_count_launch(ctx);
+    CS_CUDA(cudaEventRecord(ctx->ev1, st));
+    CS_CUDA(cudaStreamSynchronize(st));
+    float ms;
+    CS_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    ctx->last_kernel_ms[CS_T_CIA] += ms;
+    return CS_OK;
+}

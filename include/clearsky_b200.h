@@ -1,0 +1,180 @@
+/*
+ * clearsky_b200.h -- C ABI of libclearsky_b200.so: the B200 (sm_100a) line-by-line radiative-transfer
+ * engine that sits behind ClearSky.jl's Julia API for ONE hot path:
+ *
+ *   HITRAN line summation -> opacity-table build / (T, ln P) interpolation -> CIA -> layer optical depth
+ *   (Gauss-Lobatto) -> Schwarzschild up/down sweep over Gauss-Legendre streams -> spectral reduction.
+ *
+ * The reference (markmbaum/ClearSky.jl) is pure Julia and has no FFI for this path; its extension points
+ * are multiple dispatch and function arguments.  Each entry point below names the reference interface it
+ * replaces (path:line under the reference repository) and is what a `ccall` from the Julia wrapper
+ * (clearsky.jl_b200/julia/ClearSkyB200.jl) binds.
+ *
+ * Conventions
+ *   - plain C, no exceptions: every function returns an int32 status (CS_OK == 0); on failure
+ *     cs_last_error() returns a thread-local message.
+ *   - all sizes int64_t, all real data double (Julia Float64), isotopologue ids int16_t (Julia Int16).
+ *   - arrays are column-major exactly as Julia owns them; "[a][b]" below means b is the fastest index.
+ *   - the caller owns every host array for the duration of the call only; the library copies what it
+ *     keeps.  Device objects are owned by the library and released by cs_*_free.
+ *   - calls are synchronous: outputs are valid when the function returns.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with CS_ERR_CUDA.
+ */
+#ifndef CLEARSKY_B200_H
+#define CLEARSKY_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CS_MAXCHEB 16      /* padded length of one Qref/Q Chebyshev coefficient row */
+#define CS_MAX_NODES 64    /* max temperature / pressure nodes per axis of an opacity table */
+#define CS_MAX_STREAMS 16
+#define CS_MAX_LOBATTO 16
+
+enum {
+    CS_OK = 0,
+    CS_ERR_CUDA = 1,        /* CUDA runtime / launch failure (includes "no device") */
+    CS_ERR_ARG = 2,         /* invalid argument (mirrors a reference @assert) */
+    CS_ERR_NOMEM = 3,
+    CS_ERR_DOMAIN = 4       /* T outside [25,1000] K, (T,P) outside a table domain, ... */
+};
+
+/* line shapes: doppler! / lorentz! / voigt! / PHCO2!  (src/absorption/line_shapes.jl:200,313,412,527) */
+enum { CS_DOPPLER = 0, CS_LORENTZ = 1, CS_VOIGT = 2, CS_PHCO2 = 3 };
+
+/* per-context kernel timers (milliseconds of the most recent call, CUDA events on the context stream) */
+enum { CS_T_PREP = 0, CS_T_LINESUM = 1, CS_T_TABLE_FIT = 2, CS_T_TABLE_EVAL = 3, CS_T_CIA = 4,
+       CS_T_RT = 5, CS_T_REDUCE = 6, CS_T_TOTAL = 7, CS_NTIMERS = 8 };
+
+typedef struct cs_ctx cs_ctx;       /* one CUDA device + stream */
+typedef struct cs_lines cs_lines;   /* SpectralLines resident on the device */
+typedef struct cs_table cs_table;   /* Vector{OpacityTable} of one Gas: Chebyshev coefficients per wavenumber */
+typedef struct cs_cia cs_cia;       /* CIATables resident on the device */
+typedef struct cs_accel cs_accel;   /* AcceleratedAbsorber: ln sigma at fixed levels, per wavenumber */
+typedef struct cs_sigma cs_sigma;   /* device workspace: Sigma(A, idx, T, P) at the quadrature nodes, all wavenumbers */
+
+const char* cs_last_error(void);
+int32_t cs_version(void);
+int32_t cs_device_count(int32_t* n);
+
+/* ---- context ---------------------------------------------------------------------------------- */
+int32_t cs_ctx_create(int32_t device, cs_ctx** out);
+/* same, but run on a caller-owned CUDA stream (cudaStream_t passed as void*), e.g. torch's current stream */
+int32_t cs_ctx_create_on_stream(int32_t device, void* cuda_stream, cs_ctx** out);
+int32_t cs_ctx_free(cs_ctx* ctx);
+int32_t cs_ctx_synchronize(cs_ctx* ctx);
+/* timers[CS_NTIMERS] of the last compute call; launches = kernels launched so far on this context */
+int32_t cs_ctx_timers(cs_ctx* ctx, double* timers_ms);
+int32_t cs_ctx_launches(cs_ctx* ctx, int64_t* launches);
+/* sustained FP64 FMA rate of this device, measured with a register-resident DFMA loop [FLOP/s] */
+int32_t cs_fp64_peak(cs_ctx* ctx, int32_t iters, double* flops_per_s);
+
+/* ---- lines: replaces the SpectralLines argument of shape!(...)  (src/hitran/par.jl:224-284) ----
+ * nu must be ascending (SpectralLines sorts: par.jl:267).  iso[] = 1-based local isotopologue number
+ * (sl.I); cheb[niso][CS_MAXCHEB], ncheb[niso] = MOLPARAM[sl.M].cheb / .ncheb (hitran/molparam.jl);
+ * hascheb[i] == 0 for an isotopologue that is present in iso[] fails like scaleintensity's throw
+ * (line_shapes.jl:115-119). */
+int32_t cs_lines_upload(cs_ctx* ctx, int64_t n, const double* nu, const double* S, const double* gamma_a,
+                        const double* gamma_s, const double* Epp, const double* na, const double* mu,
+                        const int16_t* iso, int32_t niso, const int32_t* ncheb, const double* cheb,
+                        const uint8_t* hascheb, cs_lines** out);
+int32_t cs_lines_free(cs_lines* lines);
+
+/* S1: shape!(sigma, nu, sl, T, P, Pp, cut), batched over nlev (T,P,Pp) nodes
+ * (line_shapes.jl:200-211, 313-324, 412-424, 527-540; surf! :53-87).  sigma is [nlev][nnu] and is
+ * OVERWRITTEN like surf! does.  nu strictly ascending (assert :59); T in [25,1000] (assert :29). */
+int32_t cs_xsec(cs_lines* lines, int32_t shape, int64_t nnu, const double* nu, int64_t nlev,
+                const double* T, const double* P, const double* Pp, double dnu_cut, double* sigma);
+/* exact number of surf! inner-loop iterations for one node: sum_i #{j : |nu_i - nul_j| <= cut}
+ * restricted to the lines the strict prefilter keeps (line_shapes.jl:18-22,75-82) */
+int32_t cs_count_evals(cs_lines* lines, int64_t nnu, const double* nu, double dnu_cut, int64_t* evals);
+
+/* ---- S2: bake(sl, fC, shape!, cut, nu, Omega)  (src/absorption/gases.jl:97-145) ------------------
+ * Tgrid[nT], Pgrid[nP] = Omega.T, Omega.P; C[nT][nP]... Julia C[i,j] = fC(T_i,P_j) at index i + nT*j.
+ * Builds sigma[nnu,nT,nP], applies the zero-mixing repair (:131-142) and fits one Bichebyshev
+ * interpolant of ln(sigma) in (T, ln P) per wavenumber (OpacityTable ctor, gases.jl:75-82).
+ * keep_block != 0 keeps the raw sigma block on the device for cs_table_block. */
+int32_t cs_bake(cs_lines* lines, int32_t shape, int64_t nnu, const double* nu, int32_t nT,
+                const double* Tgrid, int32_t nP, const double* Pgrid, const double* C, double dnu_cut,
+                int32_t keep_block, cs_table** out);
+/* build the same table from a caller-supplied sigma block [nT*nP][nnu] (Julia sigma[nu,i,j]) */
+int32_t cs_table_from_block(cs_ctx* ctx, int64_t nnu, int32_t nT, const double* Tgrid, int32_t nP,
+                            const double* Pgrid, const double* sigma_block, cs_table** out);
+/* rawsigma(g, T, P) for all wavenumbers at nlev nodes: sigma[nlev][nnu] = exp(Phi_nu(T, ln P))
+ * (gases.jl:85,256,263).  (T,P) outside the table domain -> CS_ERR_DOMAIN (StrictBoundaries). */
+int32_t cs_table_eval(cs_table* table, int64_t nlev, const double* T, const double* P, double* sigma);
+/* copy the baked sigma block [nT*nP][nnu] to the host (to build stock OpacityTables in Julia) */
+int32_t cs_table_block(cs_table* table, double* sigma_block);
+int32_t cs_table_info(cs_table* table, int64_t* nnu, int32_t* nT, int32_t* nP, int64_t* nzeroed);
+int32_t cs_table_free(cs_table* table);
+
+/* ---- CIATables  (src/absorption/collision_induced_absorption.jl:145-276) -----------------------
+ * ngrid bilinear grids (>= 2 temperatures): grid g has g_nnu[g] wavenumbers, g_nT[g] temperatures,
+ * lnk[g] = log(k) as [nT][nnu] (Julia Z[i_nu, j_T], nu fastest), non-positive k already replaced by
+ * floatmin (:205).  nsingle single-temperature tables: s_nu / s_lnk concatenated (log(0) = -Inf allowed). */
+int32_t cs_cia_upload(cs_ctx* ctx, int32_t ngrid, const int64_t* g_nnu, const int64_t* g_nT,
+                      const double* g_nu, const double* g_T, const double* g_lnk, int32_t nsingle,
+                      const int64_t* s_n, const double* s_nu, const double* s_lnk, int32_t extrapolate,
+                      int32_t singles, cs_cia** out);
+int32_t cs_cia_free(cs_cia* cia);
+
+/* ---- AcceleratedAbsorber  (src/absorption/absorbers.jl:114-209) --------------------------------- */
+/* snapshot max(log(Sigma), log(floatmin)) of a sigma workspace whose nodes are the nlev levels P
+ * (ascending) -> update!(A, T) (:173-200) */
+int32_t cs_accel_from_sigma(cs_sigma* sig, const double* P, cs_accel** out);
+int32_t cs_accel_free(cs_accel* accel);
+
+/* ---- sigma workspace: Sigma(A, idx, T, P) = sum of absorbers at the Lobatto nodes ---------------
+ * (src/absorption/absorbers.jl:84-97, core/discretized.jl:76-81).  nnode = (np-1)*(nlobatto-1)+1 for
+ * fluxes; node order = ascending pressure.  All cs_sigma_add_* ACCUMULATE into sig[nnode][nnu]. */
+int32_t cs_sigma_create(cs_ctx* ctx, int64_t nnu, const double* nu, int64_t nnode, cs_sigma** out);
+int32_t cs_sigma_zero(cs_sigma* sig);
+int32_t cs_sigma_free(cs_sigma* sig);
+/* Gas functor g(i,T,P) = fC(T,P) * Pi_i(T,P)  (gases.jl:278): += C[node] * table(T[node], P[node]) */
+int32_t cs_sigma_add_table(cs_sigma* sig, cs_table* table, const double* T, const double* P, const double* C);
+/* exact line-by-line gas at the nodes (no table): += C[node] * shape(nu, sl, T, P, C*P, cut) */
+int32_t cs_sigma_add_lines(cs_sigma* sig, cs_lines* lines, int32_t shape, const double* T, const double* P,
+                           const double* C, double dnu_cut);
+/* CIA functor (collision_induced_absorption.jl:378-382,465): += cia(nu, x, T, P, P*C1, P*C2) */
+int32_t cs_sigma_add_cia(cs_sigma* sig, cs_cia* cia, const double* T, const double* P, const double* C1,
+                         const double* C2);
+/* AcceleratedAbsorber Sigma = exp(phi_i(ln P)) (absorbers.jl:203): += */
+int32_t cs_sigma_add_accel(cs_sigma* sig, cs_accel* accel, const double* P);
+/* gray / semigray gases and pre-evaluated user functions sigma(nu,T,P): += host array [nnode][nnu] */
+int32_t cs_sigma_add_host(cs_sigma* sig, const double* sigma_nodes);
+/* += value for nu <= nu_cut (GrayGas: nu_cut = +Inf; SemiGrayGas gases.jl:386) */
+int32_t cs_sigma_add_gray(cs_sigma* sig, double value, double nu_cut);
+int32_t cs_sigma_read(cs_sigma* sig, double* sigma_nodes);
+
+/* ---- S3: monochromaticfluxes!(M+, M-, tau, core::Discretized, ...) + integral-F! + Fnet ----------
+ * (src/fluxes.jl:238-279,357-383; core/discretized.jl:136-177,249-326; core/shared.jl:125-137).
+ * P[np] ascending (index 0 = TOA); mu[nlob][np-1] at the Lobatto nodes (discretized.jl:11-30);
+ * Tlev[np] = fT(P[i]) (planckevaluations :46-58); wlob[nlob] Lobatto weights on [0,1];
+ * m[nstream], W[nstream] = streamnodes (core/shared.jl:4-21); fS[nnu], fa[nnu] pre-evaluated.
+ * Outputs: Fup/Fdn/Fnet[np] always; tau [np-1][nnu]... Julia tau[i,j] at i + (np-1)*j, Mup/Mdn
+ * Julia M[i,j] at i + np*j -- NULL means "do not materialise".
+ * nu_weights: NULL -> trapz over this workspace's own nu (util.jl:26-33); otherwise caller-supplied
+ * per-point trapezoid weights (used by nu-sharded multi-GPU runs so that every interval is counted once). */
+int32_t cs_fluxes(cs_sigma* sig, int64_t np, const double* P, int32_t nlob, const double* wlob,
+                  const double* mu, const double* Tlev, double g, const double* fS, const double* fa,
+                  double theta_s, int32_t nstream, const double* m, const double* W,
+                  const double* nu_weights, double* tau, double* Mup, double* Mdn, double* Fup,
+                  double* Fdn, double* Fnet);
+/* same, but leaves Fup/Fdn (2*np doubles: Fup then Fdn) in DEVICE memory d_F for a following
+ * collective (NCCL all-reduce by the caller) */
+int32_t cs_fluxes_device(cs_sigma* sig, int64_t np, const double* P, int32_t nlob, const double* wlob,
+                         const double* mu, const double* Tlev, double g, const double* fS,
+                         const double* fa, double theta_s, int32_t nstream, const double* m,
+                         const double* W, const double* nu_weights, double* d_F);
+/* opticaldepth(P::Vector, g, T, mu, theta, absorbers...; nlobatto) (src/fluxes.jl:68-97,
+ * core/discretized.jl:92-134): total slant-path optical depth per wavenumber, no floor. */
+int32_t cs_opticaldepth(cs_sigma* sig, int64_t np, const double* P, int32_t nlob, const double* wlob,
+                        const double* mu, double g, double theta, double* tau_total);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,322 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI exactly like the
+Julia wrapper would, against the CPU oracle on the same inputs and against the committed golden fixtures.
+
+Tolerances are BASELINE.json's: relative error <= 1e-9 on cross-sections, <= 1e-8 on OLR and fluxes."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import DATA, GOLDEN, relerr
+from helpers import c1_problem, synthetic_lines
+
+pytestmark = pytest.mark.gpu
+
+XSEC_TOL = 1e-9
+FLUX_TOL = 1e-8
+SHAPES = [("doppler", 0, 25.0), ("lorentz", 1, 25.0), ("voigt", 2, 25.0), ("PHCO2", 3, 500.0)]
+
+
+@pytest.mark.parametrize("name,sid,cut", SHAPES)
+def test_xsec_fixture_c1(cs, orc, co2, name, sid, cut):
+    """BASELINE configs[0] grid (ν = 1 + 2.5 i) on the reference's own CO2 fixture, all four shapes"""
+    ν, P, Γ = c1_problem(cs)
+    T = Γ(P)
+    Pp = 400e-6 * P
+    got = cs.xsec(name, ν, co2, T, P, Pp, cut)
+    ref = orc.xsec(sid, co2, ν, T, P, Pp, cut, nthreads=0)
+    assert relerr(got, ref, 1e-290) < XSEC_TOL
+
+
+def test_xsec_golden(cs, co2):
+    G = np.load(os.path.join(GOLDEN, "c1_co2.npz"))
+    ν, P, T = G["nu"], G["P"], G["T"]
+    for name, key, sl_, Pp, cut in (("voigt", "sigma_voigt", slice(None, None, 5), 400e-6, 25.0),
+                                    ("lorentz", "sigma_lorentz", slice(None, None, 5), 400e-6, 25.0),
+                                    ("doppler", "sigma_doppler", slice(None, None, 5), 400e-6, 25.0),
+                                    ("PHCO2", "sigma_phco2", slice(None, None, 10), 1.0, 500.0)):
+        got = cs.xsec(name, ν, co2, T[sl_], P[sl_], Pp * P[sl_], cut)
+        assert relerr(got, G[key], 1e-290) < XSEC_TOL, name
+
+
+@pytest.mark.parametrize("name,sid,cut", SHAPES)
+def test_xsec_fine_grid_all_regions(cs, orc, name, sid, cut):
+    """0.01 cm^-1 grid over dense synthetic lines from 10 Pa to 1 bar: exercises every Faddeyeva region,
+    the paired fast path, the edge predicate and ragged tiles (nν not a multiple of the tile)"""
+    sl = synthetic_lines(cs, 3000, seed=7, νmax=120.0)
+    ν = 30.0 + 0.01 * np.arange(4999)
+    P = np.array([10.0, 300.0, 5e3, 1e5])
+    T = np.array([150.0, 210.0, 250.0, 296.0])
+    Pp = np.array([1e-3, 0.1, 5.0, 1e5 * 0.5])
+    c = min(cut, 40.0)
+    got = cs.xsec(name, ν, sl, T, P, Pp, c)
+    ref = orc.xsec(sid, sl, ν, T, P, Pp, c, nthreads=0)
+    assert relerr(got, ref, 1e-290) < XSEC_TOL
+
+
+def test_xsec_line_centres(cs, orc, co2):
+    """evaluation points sitting exactly on / next to line centres at low pressure (Hui / Humlicek regions)"""
+    νl = co2.ν[(co2.ν > 600) & (co2.ν < 760)][::7][:150]
+    off = np.array([0.0, 1e-7, 1e-5, 3e-4, 2e-3, 9e-3])
+    ν = np.unique(np.sort((νl[:, None] + off[None, :]).ravel()))
+    T, P = np.array([200.0, 250.0]), np.array([1.0, 50.0])
+    got = cs.xsec("voigt", ν, co2, T, P, 400e-6 * P, 25.0)
+    ref = orc.xsec(orc.VOIGT, co2, ν, T, P, 400e-6 * P, 25.0)
+    assert relerr(got, ref, 1e-290) < XSEC_TOL
+
+
+def test_xsec_cutoff_is_inclusive(cs, orc):
+    """a point exactly Δνcut away from a line is included (line_shapes.jl:10); the strict prefilter
+    (line_shapes.jl:18-22) drops a line sitting exactly at min(ν) - cut"""
+    sl = synthetic_lines(cs, 50, seed=3, νmax=200.0)
+    sl.ν[:] = np.sort(np.round(sl.ν, 2))
+    sl.ν[10] = 100.0
+    sl.ν[:] = np.sort(sl.ν)
+    ν = np.array([75.0, 100.0, 125.0, 125.5, 140.0, 170.0])
+    for shape, sid in (("lorentz", 1), ("voigt", 2)):
+        got = cs.xsec(shape, ν, sl, [260.0], [1e4], [10.0], 25.0)
+        ref = orc.xsec(sid, sl, ν, [260.0], [1e4], [10.0], 25.0)
+        assert relerr(got, ref, 1e-290) < XSEC_TOL
+    ν2 = np.array([sl.ν[0] + 25.0, sl.ν[0] + 30.0])    # first line sits exactly at min(ν) - cut: prefiltered out
+    got = cs.xsec("lorentz", ν2, sl, [260.0], [1e4], [10.0], 25.0)
+    ref = orc.xsec(1, sl, ν2, [260.0], [1e4], [10.0], 25.0)
+    assert relerr(got, ref, 1e-290) < XSEC_TOL
+
+
+def test_xsec_edge_shapes(cs, orc, co2):
+    """single point, two points, no line in range (zeros), gaps in the grid"""
+    for ν in (np.array([667.5]), np.array([100.0, 5000.0]), np.array([20000.0, 20001.0]),
+              np.concatenate([np.linspace(500, 510, 77), np.linspace(2300, 2310, 1031)])):
+        got = cs.xsec("voigt", ν, co2, [220.0, 288.0], [1e3, 1e5], [0.4, 40.0], 25.0)
+        ref = orc.xsec(orc.VOIGT, co2, ν, [220.0, 288.0], [1e3, 1e5], [0.4, 40.0], 25.0)
+        assert relerr(got, ref, 1e-290) < XSEC_TOL
+    assert cs.device_lines(co2).count_evals(np.array([667.5]), 25.0) == \
+        orc.count_evals(np.array([667.5]), orc.included_lines(np.array([667.5]), co2.ν, 25.0), 25.0)
+
+
+def test_xsec_errors(cs, co2):
+    """reference pre-conditions surface as errors, not garbage (line_shapes.jl:29,59)"""
+    with pytest.raises(cs.ClearSkyError):
+        cs.xsec("voigt", np.array([3.0, 2.0, 1.0]), co2, [250.0], [1e4], [1.0], 25.0)
+    with pytest.raises(cs.ClearSkyError):
+        cs.xsec("voigt", np.array([1.0, 2.0]), co2, [20.0], [1e4], [1.0], 25.0)
+    with pytest.raises(cs.ClearSkyError):
+        cs.xsec("voigt", np.array([1.0, 2.0]), co2, [1200.0], [1e4], [1.0], 25.0)
+
+
+def test_linearity_property(cs):
+    """size-independent property at a larger size: σ is linear in S and additive over disjoint line sets"""
+    sl = synthetic_lines(cs, 40000, seed=11, νmax=400.0)
+    ν = 100.0 + 0.01 * np.arange(20000)
+    T, P, Pp = [230.0, 280.0], [2e3, 8e4], [1.0, 30.0]
+    full = cs.xsec("voigt", ν, sl, T, P, Pp, 25.0)
+    import copy
+    a, b = copy.copy(sl), copy.copy(sl)
+    a.__dict__.pop("_dev", None); b.__dict__.pop("_dev", None)
+    a.S = sl.S.copy(); b.S = sl.S.copy()
+    a.S[::2] = 0.0
+    b.S[1::2] = 0.0
+    part = cs.xsec("voigt", ν, a, T, P, Pp, 25.0) + cs.xsec("voigt", ν, b, T, P, Pp, 25.0)
+    assert relerr(part, full, 1e-290) < 1e-12
+    c = copy.copy(sl); c.__dict__.pop("_dev", None); c.S = 2 * sl.S
+    assert relerr(cs.xsec("voigt", ν, c, T, P, Pp, 25.0), 2 * full, 1e-290) < 1e-13
+
+
+def test_bake_and_table(cs, orc, co2):
+    """bake -> OpacityTable fit -> evaluation (gases.jl:75-145) vs the oracle, incl. the golden table run"""
+    ν, P, Γ = c1_problem(cs)
+    Ω = cs.AtmosphericDomain((140, 300), 12, (5, 1.1e5), 24)
+    gas = cs.Gas(co2, 400e-6, ν, Ω, "voigt", 25.0, keep_block=True)
+    Cg = np.full((Ω.nP, Ω.nT), 400e-6)
+    block, nz = orc.bake(orc.VOIGT, co2, ν, Ω.T, Ω.P, Cg, 25.0, nthreads=0)
+    assert gas.nzeroed == nz
+    assert relerr(gas.σblock(), block, 1e-290) < XSEC_TOL
+    A = orc.table_fit(block)
+    T = Γ(P)
+    ref = orc.gas_nodes(A, Ω.T, Ω.P, T, P, np.ones(len(P)))
+    got = gas.rawσ(T, P)
+    assert relerr(got, ref, 1e-290) < XSEC_TOL
+    G = np.load(os.path.join(GOLDEN, "c1_co2.npz"))
+    assert relerr(400e-6 * got[::5], G["tab_sigma_lev"], 1e-290) < XSEC_TOL
+    # random interior (T, P)
+    rng = np.random.default_rng(5)
+    Tq = rng.uniform(141, 299, 9)
+    Pq = np.exp(rng.uniform(np.log(6), np.log(1e5), 9))
+    assert relerr(gas.rawσ(Tq, Pq), orc.gas_nodes(A, Ω.T, Ω.P, Tq, Pq, np.ones(9)), 1e-290) < XSEC_TOL
+    # StrictBoundaries: outside the domain is an error
+    with pytest.raises(cs.ClearSkyError):
+        gas.rawσ(np.array([305.0]), np.array([1e4]))
+    with pytest.raises(cs.ClearSkyError):
+        gas.rawσ(np.array([250.0]), np.array([2e5]))
+
+
+def test_zero_mixing_repair(cs, orc):
+    """a wavenumber whose σ underflows to 0 at some nodes only is zeroed at all nodes (gases.jl:131-142) and its
+    table becomes log(floatmin) everywhere (gases.jl:77-79)"""
+    sl = synthetic_lines(cs, 5, seed=2, νmax=50.0)
+    ν = np.array([10.0, 20.0, 2000.0, 2500.0])
+    Ω = cs.AtmosphericDomain((100, 300), 5, (1, 1e5), 6)
+    gas = cs.Gas(sl, 1e-3, ν, Ω, "doppler", 5000.0, keep_block=True)
+    block, nz = orc.bake(orc.DOPPLER, sl, ν, Ω.T, Ω.P, np.full((Ω.nP, Ω.nT), 1e-3), 5000.0)
+    assert gas.nzeroed == nz
+    assert relerr(gas.σblock(), block, 1e-300) < XSEC_TOL
+    A = orc.table_fit(block)
+    ref = orc.gas_nodes(A, Ω.T, Ω.P, [200.0], [1e3], [1.0])
+    assert relerr(gas.rawσ(200.0, 1e3), ref[0], 0) < 1e-300 or relerr(gas.rawσ(200.0, 1e3), ref[0], 1e-320) < XSEC_TOL
+
+
+def test_cia(cs, orc, co2):
+    ν = np.linspace(1.0, 3000.0, 1234)
+    raw = cs.readcia(os.path.join(DATA, "CO2-CO2_2018.cia.gz"))
+    T = np.array([120.0, 200.0, 233.3, 300.0, 350.0, 800.0])
+    P = np.array([10.0, 1e3, 1e4, 5e4, 1e5, 2e5])
+    C1 = np.full(6, 0.95)
+    for extrapolate, singles in ((False, False), (True, False), (True, True), (False, True)):
+        x = cs.CIATables(raw, extrapolate=extrapolate, singles=singles)
+        ws = cs.SigmaWorkspace(ν, len(T))
+        from clearsky_b200._lib import check, lib, ptr, f64
+        check(lib().cs_sigma_add_cia(ws.h, x.handle(), ptr(f64(T)), ptr(f64(P)), ptr(f64(C1)), ptr(f64(C1))))
+        ref = orc.cia_nodes(x, ν, T, P, C1, C1)
+        assert relerr(ws.read(), ref, 1e-300) < XSEC_TOL, (extrapolate, singles)
+    x = cs.CIATables(cs.readcia(os.path.join(DATA, "CO2-CH4_2018.cia.gz")), extrapolate=True)
+    ws = cs.SigmaWorkspace(ν, len(T))
+    check(lib().cs_sigma_add_cia(ws.h, x.handle(), ptr(f64(T)), ptr(f64(P)), ptr(f64(C1)), ptr(f64(1 - C1))))
+    assert relerr(ws.read(), orc.cia_nodes(x, ν, T, P, C1, 1 - C1), 1e-300) < XSEC_TOL
+
+
+def _oracle_fluxes(orc, cs, ν, P, fT, μ, σnodes, g, nstream, nlob, fS=None, fa=None, θs=0.841):
+    m, W = cs.streamnodes(nstream)
+    x, w = cs.lobattonodes(nlob)
+    μn = np.full((len(P) - 1, nlob), μ)
+    Tlev = np.array([float(fT(p)) for p in P])
+    return orc.fluxes(ν, P, nlob, w, μn, Tlev, σnodes, g, fS, fa, θs, nstream, m, W, nthreads=0)
+
+
+def test_fluxes_c1_linegas(cs, orc, co2):
+    """BASELINE configs[0] with the exact line-by-line gas: OLR, F±, M±, τ vs golden (oracle) -- <= 1e-8"""
+    G = np.load(os.path.join(GOLDEN, "c1_co2.npz"))
+    ν, P, Γ = c1_problem(cs)
+    gas = cs.LineGas(co2, 400e-6, ν, "voigt", 25.0)
+    F = cs.radiate(P, 9.8, Γ, 0.029, None, None, gas, core=cs.Discretized(5, 2))
+    assert relerr(F.Fup, G["lbl_Fup"]) < FLUX_TOL
+    assert relerr(F.Fdn[1:], G["lbl_Fdn"][1:]) < FLUX_TOL
+    assert relerr(F.τ, G["lbl_tau"]) < FLUX_TOL
+    assert relerr(F.Mup[:, 0], G["lbl_Mup_toa"], 1e-300) < FLUX_TOL
+    assert relerr(F.Fnet, G["lbl_Fup"] - G["lbl_Fdn"]) < FLUX_TOL
+    Fup, Fdn = cs.fluxes(P, 9.8, Γ, 0.029, None, None, gas)
+    assert relerr(Fup, G["lbl_Fup"]) < FLUX_TOL and abs(Fup[0] - 378.8388262928894) < 1e-5
+
+
+def test_fluxes_c1_table(cs, orc, co2):
+    """BASELINE configs[0] through Gas + OpacityTable, the reference's own route (fluxes.jl:311-340)"""
+    G = np.load(os.path.join(GOLDEN, "c1_co2.npz"))
+    ν, P, Γ = c1_problem(cs)
+    Ω = cs.AtmosphericDomain((140, 300), 12, (5, 1.1e5), 24)
+    gas = cs.Gas(co2, 400e-6, ν, Ω)
+    Fup, Fdn = cs.fluxes(P, 9.8, Γ, 0.029, None, None, gas)
+    assert relerr(Fup, G["tab_Fup"]) < FLUX_TOL
+    assert relerr(Fdn[1:], G["tab_Fdn"][1:]) < FLUX_TOL
+    net = cs.netfluxes(P, 9.8, Γ, 0.029, None, None, gas)
+    assert relerr(net, G["tab_Fup"] - G["tab_Fdn"]) < FLUX_TOL
+
+
+@pytest.mark.parametrize("nstream,nlob", [(1, 2), (3, 3), (5, 4), (8, 2), (11, 5)])
+def test_fluxes_streams_lobatto_sun_albedo(cs, orc, co2, h2o, nstream, nlob):
+    """two gases + CIA-free mix, stellar beam and albedo, ragged ν count, every stream/Lobatto template"""
+    ν = np.linspace(50.0, 2400.0, 1177)
+    P = cs.pressuregrid(20.0, 9e4, 14)
+    Γ = cs.DryAdiabat(280.0, 9e4, 1040.0, 0.029, Ptropo=1.2e4)
+    Ω = cs.AtmosphericDomain((150, 300), 8, (10, 1e5), 12)
+    g1 = cs.Gas(co2, 400e-6, ν, Ω)
+    g2 = cs.Gas(h2o, lambda T, P: min(1e-2, 1e-6 + 1e-7 * P / 1e3), ν, Ω, "lorentz", 25.0)
+    gray = cs.SemiGrayGas(1e-27, ν, 1000.0)
+    fun = lambda x, T, P: 1e-28 * (1 + x / 1e3) * (T / 250.0)
+    fS = lambda x: 1.5 * np.exp(-((x - 1500) / 600.0) ** 2)
+    fa = lambda x: 0.2 + 0.1 * np.sin(x / 300.0)
+    F = cs.radiate(P, 9.8, Γ, 0.029, fS, fa, g1, g2, gray, fun, core=cs.Discretized(nstream, nlob), θs=0.6)
+    # oracle: same Σ assembled on the CPU
+    from clearsky_b200.fluxes import lobattoevaluations, _unique_nodes, formprofile
+    Tl, μl, Pn = lobattoevaluations(P, Γ, formprofile(P, 0.029), nlob)
+    Tn, Pq = _unique_nodes(P, Tl, Pn, nlob)
+    σ = np.zeros((len(Tn), len(ν)))
+    for gas, shp, fC in ((co2, orc.VOIGT, g1.fC), (h2o, orc.LORENTZ, g2.fC)):
+        Cg = np.array([[fC(T, Pj) for T in Ω.T] for Pj in Ω.P])
+        blk, _ = orc.bake(shp, gas, ν, Ω.T, Ω.P, Cg, 25.0, nthreads=0)
+        σ += orc.gas_nodes(orc.table_fit(blk), Ω.T, Ω.P, Tn, Pq, np.array([fC(t, p) for t, p in zip(Tn, Pq)]))
+    σ += np.where(ν <= 1000.0, 1e-27, 0.0)[None, :]
+    σ += np.array([fun(ν, t, p) for t, p in zip(Tn, Pq)])
+    ref = _oracle_fluxes(orc, cs, ν, P, Γ, 0.029, σ, 9.8, nstream, nlob, fS(ν), fa(ν), 0.6)
+    assert relerr(F.Fup, ref["Fup"]) < FLUX_TOL
+    assert relerr(F.Fdn, ref["Fdn"]) < FLUX_TOL
+    assert relerr(F.Mup, ref["Mup"], 1e-300) < FLUX_TOL
+    assert relerr(F.Mdn, ref["Mdn"], 1e-300) < FLUX_TOL
+    assert relerr(F.τ, ref["τ"]) < FLUX_TOL
+
+
+def test_gray_olr_analytic_gpu(cs):
+    """GrayGas on a dry adiabat vs the analytic solution (test/test_gray.jl), rel. err < 1 %"""
+    from test_oracle_pins import _gray_analytic
+    g, μ, cp, Ps, Ts = 10.0, 0.01, 1e3, 1e5, 300.0
+    ν = np.concatenate([np.linspace(1e-3, 10, 60)[:-1], np.linspace(10, 6000, 3000)])
+    P = np.exp(np.linspace(np.log(1e-2), np.log(Ps), 601))
+    Γ = cs.DryAdiabat(Ts, Ps, cp, μ)
+    m, W = cs.streamnodes(5)
+    for σ in (1e-27, 1e-26, 1e-25):
+        Fup, _ = cs.fluxes(P, g, Γ, μ, None, None, cs.GrayGas(σ, ν))
+        assert abs(Fup[0] / _gray_analytic(σ, g, μ, cp, Ps, Ts, m, W) - 1) < 0.01
+
+
+def test_accelerated_absorber_and_cia_mars(cs, orc, co2):
+    """config-3 flavour: pure CO2, PHCO2 shape, CO2-CO2 CIA with extrapolation, through an AcceleratedAbsorber
+    built at the cell edges and used at finer radiative levels (radiative_convective.jl:72-89)"""
+    ν = np.linspace(20.0, 2000.0, 700)
+    Pe = cs.pressuregrid(50.0, 2e5, 9)
+    Γ = cs.DryAdiabat(250.0, 2e5, 770.0, 0.044, Ptropo=1e4)
+    Te = Γ(Pe)
+    Ω = cs.AtmosphericDomain((100, 300), 7, (10, 2.1e5), 10)
+    gas = cs.Gas(co2, 1.0, ν, Ω, "PHCO2", 500.0)
+    x = cs.CIATables(cs.readcia(os.path.join(DATA, "CO2-CO2_2018.cia.gz")), extrapolate=True)
+    A = cs.AcceleratedAbsorber(Te, Pe, gas, x)
+    Pr = np.sort(np.concatenate([Pe, (Pe[:-1] + Pe[1:]) / 2]))
+    prof = cs.AtmosphericProfile(Pe, Te)
+    F = cs.radiate(Pr, 3.71, prof, 0.044, None, None, A)
+    # oracle
+    blk, _ = orc.bake(orc.PHCO2, co2, ν, Ω.T, Ω.P, np.ones((Ω.nP, Ω.nT)), 500.0, nthreads=0)
+    Ac = orc.table_fit(blk)
+    σe = orc.gas_nodes(Ac, Ω.T, Ω.P, Te, Pe, np.ones(len(Pe))) + orc.cia_nodes(x, ν, Te, Pe, np.ones(len(Pe)), np.ones(len(Pe)))
+    lnσ = np.maximum(np.log(σe), np.log(np.finfo(float).tiny))
+    σr = orc.accel_nodes(np.log(Pe), lnσ, Pr)
+    ref = _oracle_fluxes(orc, cs, ν, Pr, prof, 0.044, σr, 3.71, 5, 2)
+    assert relerr(F.Fup, ref["Fup"]) < FLUX_TOL and relerr(F.Fdn[1:], ref["Fdn"][1:]) < FLUX_TOL
+    # update! with a new temperature profile
+    A.update(Te + 5.0)
+    σe = orc.gas_nodes(Ac, Ω.T, Ω.P, Te + 5, Pe, np.ones(len(Pe))) + orc.cia_nodes(x, ν, Te + 5, Pe, np.ones(len(Pe)), np.ones(len(Pe)))
+    σr = orc.accel_nodes(np.log(Pe), np.maximum(np.log(σe), np.log(np.finfo(float).tiny)), Pr)
+    ref = _oracle_fluxes(orc, cs, ν, Pr, prof, 0.044, σr, 3.71, 5, 2)
+    F = cs.radiate(Pr, 3.71, prof, 0.044, None, None, A)
+    assert relerr(F.Fup, ref["Fup"]) < FLUX_TOL
+
+
+def test_opticaldepth(cs, orc, co2):
+    """opticaldepth(P::Vector, ...; nlobatto=4) (fluxes.jl:68-97): unsorted P accepted, no τ floor"""
+    ν, P, Γ = c1_problem(cs, nν=300)
+    gas = cs.LineGas(co2, 400e-6, ν, "voigt", 25.0)
+    τ = cs.opticaldepth(P[::-1], 9.8, Γ, 0.029, 0.3, gas, nlobatto=4)
+    from clearsky_b200.fluxes import lobattoevaluations, _unique_nodes, formprofile
+    Tl, μl, Pn = lobattoevaluations(P, Γ, formprofile(P, 0.029), 4)
+    Tn, Pq = _unique_nodes(P, Tl, Pn, 4)
+    σ = 400e-6 * orc.xsec(orc.VOIGT, co2, ν, Tn, Pq, 400e-6 * Pq, 25.0, nthreads=0)
+    x, w = cs.lobattonodes(4)
+    ref = orc.opticaldepth(P, 4, w, μl, σ, 9.8, 0.3)
+    assert relerr(τ, ref, 1e-300) < FLUX_TOL
+
+
+def test_flux_errors(cs, co2):
+    ν, P, Γ = c1_problem(cs, nν=64)
+    gas = cs.GrayGas(1e-26, ν)
+    with pytest.raises(AssertionError):
+        cs.fluxes(P[::-1], 9.8, Γ, 0.029, None, None, gas)        # issorted(P) (fluxes.jl:257)
+    with pytest.raises(AssertionError):
+        cs.fluxes(P, 9.8, Γ, 0.029, None, None, gas, θs=2.0)       # checkazimuth (fluxes.jl:4-6)
+    with pytest.raises(AssertionError):
+        cs.Gas(co2, 1.5, ν, cs.AtmosphericDomain((150, 300), 4, (10, 1e5), 4))   # gases.jl:124
