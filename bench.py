@@ -374,7 +374,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=["c2", "c2small"])
-    ap.add_argument("--cpu-evals", type=float, default=2.0e9, help="size of the bounded CPU sample [evals]")
+    ap.add_argument("--cpu-evals", type=float, default=4.0e10, help="size of the bounded CPU sample [evals]")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -195,6 +195,8 @@ extern "C" int32_t cs_lines_upload(cs_ctx* ctx, int64_t n, const double* nu, con
     L->n = n;
     L->niso = niso;
     L->h_nu.assign(nu, nu + n);
+    L->mu_min = mu[0];
+    for (int64_t j = 1; j < n; j++) L->mu_min = std::min(L->mu_min, mu[j]);
     cudaStream_t st = ctx->stream;
     int32_t rc = CS_OK;
     if ((rc = upload(&L->nu, nu, n, st)) || (rc = upload(&L->S, S, n, st)) || (rc = upload(&L->ga, ga, n, st)) ||

@@ -110,6 +110,7 @@ struct cs_lines {
     int32_t* ncheb;   // [niso]
     double* cheb;     // [niso][CS_MAXCHEB]
     std::vector<double> h_nu;  // host copy of line positions (window searches, eval counting)
+    double mu_min;             // lightest isotopologue present (bounds the Doppler width)
 };
 
 struct cs_sigma {

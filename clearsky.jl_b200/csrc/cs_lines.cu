@@ -23,18 +23,20 @@
 //   Evaluations that are not safely in the far wing take the general Algorithm-985 routine.
 #include "cs_internal.cuh"
 #include <algorithm>
+#include <cstdlib>
 
 namespace {
 
-constexpr int LS_WARPS = 8;                       // consumer warps per CTA
-constexpr int LS_THREADS = (LS_WARPS + 1) * 32;   // + 1 producer warp
-constexpr int LS_CHUNK = 256;                     // lines per shared-memory stage (8 KB)
-constexpr int LS_STAGES = 4;
+constexpr int LS_WARPS = 8;                       // warps per CTA; every warp is an independent work unit
+constexpr int LS_THREADS = LS_WARPS * 32;
+constexpr int LS_CHUNK = 128;                     // lines per shared-memory stage (4 KB), one ring per warp
+constexpr int LS_STAGES = 3;
 
 struct LevelParams {
     double T, P, Pp, scale;
     double B1, B2;   // PHCO2 chi coefficients of this level (line_shapes.jl:472,476)
-    double pad0, pad1;
+    double cnear;    // lines with |nul - nu| > cnear*nul are safely in the far wing at this level (< 0: no near range)
+    double pad1;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -172,19 +174,27 @@ struct LineSumArgs {
     double cut;
     double* out;            // [nlev][nnu]
     int accumulate;         // 0: out = scale*sigma (surf! overwrites), 1: out += scale*sigma
+    int64_t ntiles;
+    const int64_t* ranges;  // [ntiles][6], see tile_ranges_kernel
 };
 
-// general (any region) Voigt evaluation of one (line, point): A * Re w(dnu*d + i*y)
-__device__ __noinline__ double voigt_general(const double4* __restrict__ slow, int64_t j, double dnu)
+// Voigt evaluation of one (line, point) that is not safely in the far wing: decides the region exactly like
+// the reference's faddeyeva(x, y) (same s = fma(x,x,y^2)), with the 1- and 2-convergent forms inlined.
+__device__ __noinline__ double voigt_near(const double4* __restrict__ slow, int64_t j, double dnu, double chi)
 {
+    const double osqpi = 0.56418958354775628695;
     double4 s = slow[j];
-    return s.z * cs_faddeyeva985(dnu * s.x, s.y);
-}
-// PHCO2: gamma scaled by chi before forming y (line_shapes.jl:496-499)
-__device__ __noinline__ double phco2_general(const double4* __restrict__ slow, int64_t j, double dnu, double chi)
-{
-    double4 s = slow[j];
-    return s.z * cs_faddeyeva985(dnu * s.x, (chi * s.w) * s.x);
+    double x = dnu * s.x;
+    double y = (chi * s.w) * s.x;          // (chi*gamma)*d ; chi == 1 for plain Voigt (line_shapes.jl:373,498)
+    double y2 = y * y;
+    double sq = fma(x, x, y2);
+    if (sq >= 1.6e4) return s.z * (y * osqpi / sq);
+    if (sq >= 160.0) {
+        // Re[i z/(sqrt(pi)(z^2-1/2))] = y (s+1/2) / (sqrt(pi) ((s-1/2)^2 + 2 y^2))
+        double sm = sq - 0.5;
+        return s.z * (osqpi * y * (sq + 0.5) / fma(sm, sm, 2.0 * y2));
+    }
+    return s.z * cs_faddeyeva985(x, y);
 }
 
 // chi factor of Perrin & Hartmann (line_shapes.jl:467-481), strict '<' at 3, 30, 120
@@ -196,214 +206,221 @@ __device__ __forceinline__ double chi_phco2(double adnu, double B1, double B2)
     return exp(-B1 * 27.0 - B2 * 90.0 - 0.0232 * (adnu - 120.0));
 }
 
-// one (line, point) evaluation, any shape, any region; used on edge lines and for shapes without pairing
+// one (line, point) evaluation, any shape, any Faddeyeva region (edge and near-centre lines)
 template <int SHAPE>
-__device__ __forceinline__ double eval_one(const double4 rc, double dnu, const double4* __restrict__ slow,
-                                           int64_t j, double B1, double B2)
+__device__ __forceinline__ double eval_checked(const double4 rc, double dnu, const double4* __restrict__ slow,
+                                               int64_t j, double B1, double B2)
 {
     if (SHAPE == CS_LORENTZ) {
         double q = fma(dnu, dnu, rc.y);
         return rc.z * cs_rcp(q);
     } else if (SHAPE == CS_DOPPLER) {
         double t = dnu * dnu * rc.y;
-        return (t < 746.0) ? rc.z * exp(-t) : 0.0;
+        return (t < 746.0) ? rc.z * exp(-t) : 0.0;   // exp(-t) is exactly 0 beyond (as in the reference)
     } else if (SHAPE == CS_VOIGT) {
         double q = fma(dnu, dnu, rc.y);
         if (__double2hiint(q) > __double2hiint(rc.w)) return rc.z * cs_rcp(q);
-        return voigt_general(slow, j, dnu);
+        return voigt_near(slow, j, dnu, 1.0);
     } else {
         double chi = chi_phco2(fabs(dnu), B1, B2);
         double ge = chi * rc.y;
         double q = fma(dnu, dnu, ge * ge);
         if (__double2hiint(q) > __double2hiint(rc.w)) return (rc.z * ge) * cs_rcp(q);
-        return phco2_general(slow, j, dnu, chi);
+        return voigt_near(slow, j, dnu, chi);
     }
 }
 
+// per-tile line classification, computed once per call (it does not depend on the level):
+// ranges[tile][0..5] = wlo, whi, ilo, ihi, nlo, nhi over the prefiltered sorted line positions
+//   [wlo,whi): lines within the cut-off of SOME point of the tile (exact FP64 rule of line_shapes.jl:10)
+//   [ilo,ihi): lines within the cut-off of ALL points (no per-point predicate needed)
+//   [nlo,nhi): lines whose centre is within cn*nul of the tile: the far-wing form may not apply there
+__global__ void tile_ranges_kernel(const double* __restrict__ nu, int64_t nnu, const double* __restrict__ nul,
+                                   int64_t nl, double cut, double cn, int tile_pts, int64_t ntiles,
+                                   int64_t* __restrict__ ranges)
+{
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ntiles * 6) return;
+    int64_t tile = t / 6;
+    int k = (int)(t % 6);
+    int64_t i0 = tile * tile_pts, i1 = min(i0 + (int64_t)tile_pts, nnu);
+    const double tmin = nu[i0], tmax = nu[i1 - 1];
+    int64_t v;
+    switch (k) {
+    case 0: v = first_false(nul, 0, nl, [=](double x) { return (tmin - x) > cut; }); break;
+    case 1: v = first_false(nul, 0, nl, [=](double x) { return !((x - tmax) > cut); }); break;
+    case 2: v = first_false(nul, 0, nl, [=](double x) { return (tmax - x) > cut; }); break;
+    case 3: v = first_false(nul, 0, nl, [=](double x) { return !((x - tmin) > cut); }); break;
+    case 4: v = first_false(nul, 0, nl, [=](double x) { return x * (1.0 + cn) < tmin; }); break;
+    default: v = first_false(nul, 0, nl, [=](double x) { return !(x * (1.0 - cn) > tmax); }); break;
+    }
+    ranges[t] = v;
+}
+
+// K2.  Work unit = one warp = (tile of 32*R consecutive wavenumbers, level).  Each warp streams the records of
+// ITS OWN line window through a private 3-stage shared-memory ring fed by TMA bulk copies (one elected lane
+// issues cp.async.bulk, completion on a per-stage mbarrier), so warps never wait for each other.  The 8 warps of
+// a CTA take 8 adjacent tiles of the same level: their windows overlap by ~98 %, so the copies hit L2.
 template <int SHAPE, int R>
-__global__ void __launch_bounds__(LS_THREADS) line_sum_kernel(LineSumArgs a)
+__global__ void __launch_bounds__(LS_THREADS, 2) line_sum_kernel(LineSumArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t full_bar[LS_STAGES];
-    __shared__ __align__(8) uint64_t empty_bar[LS_STAGES];
-    __shared__ int64_t s_tile[2];
+    __shared__ __align__(8) uint64_t full_bar[LS_WARPS][LS_STAGES];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int lev = blockIdx.y;
-    constexpr int TILE = LS_WARPS * 32 * R;
-    const int64_t tile0 = (int64_t)blockIdx.x * TILE;
-    const int64_t tile1 = min(tile0 + (int64_t)TILE, a.nnu);   // exclusive
+    constexpr int TILE = 32 * R;
+    const int64_t tile = (int64_t)blockIdx.x * LS_WARPS + warp;
+    if (tile >= a.ntiles) return;
+    const int64_t tile0 = tile * TILE;
     const double cut = a.cut;
+    const LevelParams lp = a.lev[lev];
+    double4* ring = reinterpret_cast<double4*>(smem_raw) + (size_t)warp * LS_STAGES * LS_CHUNK;
 
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < LS_STAGES; s++) {
-            mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], LS_WARPS);
-        }
+    if (lane == 0) {
+        for (int s = 0; s < LS_STAGES; s++) mbar_init(&full_bar[warp][s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        // lines that can touch this tile: not too far below its lowest point, not too far above its highest
-        double tmin = a.nu[tile0], tmax = a.nu[tile1 - 1];
-        int64_t lo = first_false(a.nul, 0, a.nl, [=](double x) { return (tmin - x) > cut; });
-        int64_t hi = first_false(a.nul, lo, a.nl, [=](double x) { return !((x - tmax) > cut); });
-        s_tile[0] = lo;
-        s_tile[1] = hi;
     }
-    __syncthreads();
-    const int64_t lo = s_tile[0], hi = s_tile[1];
-    const int nchunk = (int)((hi - lo + LS_CHUNK - 1) / LS_CHUNK);
+    __syncwarp();
+
+    const int64_t* rg = a.ranges + tile * 6;
+    const int64_t wlo = rg[0], whi = rg[1];
+    int64_t ilo = rg[2], ihi = rg[3], nlo = rg[4], nhi = rg[5];
+    if (ilo >= ihi) { ilo = whi; ihi = whi; }        // cut-off window narrower than the tile: every line is an edge line
+    ilo = min(max(ilo, wlo), whi);
+    ihi = min(max(ihi, ilo), whi);
+    if (SHAPE == CS_LORENTZ) { nlo = ilo; nhi = ilo; }   // no near-centre branch
+    nlo = min(max(nlo, ilo), ihi);
+    nhi = min(max(nhi, nlo), ihi);
+    const int nchunk = (int)((whi - wlo + LS_CHUNK - 1) / LS_CHUNK);
     const double4* rec_lev = a.rec + (size_t)lev * a.nl;
     const double4* slow_lev = a.slow ? a.slow + (size_t)lev * a.nl : nullptr;
 
-    if (warp == LS_WARPS) {
-        // ---------------- producer warp: one elected lane feeds the ring with TMA bulk copies
-        if (lane == 0) {
-            for (int c = 0; c < nchunk; c++) {
-                int s = c % LS_STAGES;
-                uint32_t ph = (c / LS_STAGES) & 1;
-                mbar_wait(&empty_bar[s], ph ^ 1);
-                int64_t c0 = lo + (int64_t)c * LS_CHUNK;
-                uint32_t nrec = (uint32_t)min((int64_t)LS_CHUNK, hi - c0);
-                uint32_t bytes = nrec * (uint32_t)sizeof(double4);
-                mbar_arrive_expect_tx(&full_bar[s], bytes);
-                tma_bulk_g2s(smem_raw + (size_t)s * LS_CHUNK * sizeof(double4), rec_lev + c0, bytes, &full_bar[s]);
-            }
-        }
-        return;
-    }
+    auto issue = [&](int c) {   // lane 0 only
+        int s = c % LS_STAGES;
+        int64_t c0 = wlo + (int64_t)c * LS_CHUNK;
+        uint32_t bytes = (uint32_t)min((int64_t)LS_CHUNK, whi - c0) * (uint32_t)sizeof(double4);
+        mbar_arrive_expect_tx(&full_bar[warp][s], bytes);
+        tma_bulk_g2s(ring + (size_t)s * LS_CHUNK, rec_lev + c0, bytes, &full_bar[warp][s]);
+    };
+    if (lane == 0)
+        for (int c = 0; c < LS_STAGES && c < nchunk; c++) issue(c);
 
-    // ---------------- consumer warps
-    const int64_t wbase = tile0 + (int64_t)warp * (32 * R);
     double nup[R], acc[R];
-    bool valid[R];
 #pragma unroll
     for (int r = 0; r < R; r++) {
-        int64_t i = wbase + 32 * r + lane;
-        valid[r] = i < a.nnu;
-        nup[r] = a.nu[valid[r] ? i : (a.nnu - 1)];
+        int64_t i = tile0 + 32 * r + lane;
+        nup[r] = a.nu[i < a.nnu ? i : (a.nnu - 1)];
         acc[r] = 0.0;
     }
-    // warp's line ranges: [wlo, whi) touches some point, [ilo, ihi) is inside the cut-off for all points
-    int64_t wlo = hi, whi = hi, ilo = hi, ihi = hi;
-    if (wbase < a.nnu) {
-        double wmin = a.nu[wbase];
-        double wmax = a.nu[min(wbase + 32 * R, a.nnu) - 1];
-        int64_t v = 0;
-        if (lane == 0) v = first_false(a.nul, lo, hi, [=](double x) { return (wmin - x) > cut; });
-        if (lane == 1) v = first_false(a.nul, lo, hi, [=](double x) { return !((x - wmax) > cut); });
-        if (lane == 2) v = first_false(a.nul, lo, hi, [=](double x) { return (wmax - x) > cut; });
-        if (lane == 3) v = first_false(a.nul, lo, hi, [=](double x) { return !((x - wmin) > cut); });
-        wlo = __shfl_sync(0xffffffffu, v, 0);
-        whi = __shfl_sync(0xffffffffu, v, 1);
-        ilo = __shfl_sync(0xffffffffu, v, 2);
-        ihi = __shfl_sync(0xffffffffu, v, 3);
-        if (ilo >= ihi) { ilo = whi; ihi = whi; }   // window narrower than the warp's span: all edge
-        ilo = min(max(ilo, wlo), whi);
-        ihi = min(max(ihi, ilo), whi);
-    }
-    const double B1 = a.lev[lev].B1, B2 = a.lev[lev].B2;
+    const double B1 = lp.B1, B2 = lp.B2;
 
     for (int c = 0; c < nchunk; c++) {
-        int s = c % LS_STAGES;
-        uint32_t ph = (c / LS_STAGES) & 1;
-        const int64_t c0 = lo + (int64_t)c * LS_CHUNK;
-        const int64_t c1 = min(c0 + (int64_t)LS_CHUNK, hi);
-        // every warp waits for every chunk (even one it skips) so that its release below can never run
-        // ahead of the ring phase
-        mbar_wait(&full_bar[s], ph);
-        // chunk-local line indices of this warp's three segments
-        const int j0 = (int)(max(c0, wlo) - c0), j1 = (int)(min(c1, whi) - c0);
-        if (j0 < j1) {
-            const double4* st = reinterpret_cast<const double4*>(smem_raw + (size_t)s * LS_CHUNK * sizeof(double4));
-            const int ia = (int)(min(max(ilo, c0), c1) - c0), ib = (int)(min(max(ihi, c0), c1) - c0);
-            // segment A: edge lines below the interior, exact inclusive per-point predicate
-            int e = min(j1, ia);
-            for (int j = j0; j < e; j++) {
+        const int s = c % LS_STAGES;
+        const uint32_t ph = (c / LS_STAGES) & 1;
+        const int64_t c0 = wlo + (int64_t)c * LS_CHUNK;
+        const int64_t c1 = min(c0 + (int64_t)LS_CHUNK, whi);
+        mbar_wait(&full_bar[warp][s], ph);
+        const double4* st = ring + (size_t)s * LS_CHUNK;
+        auto seg = [&](int64_t s0, int64_t s1, int& x0, int& x1) {   // chunk-local part of a class
+            x0 = (int)(max(c0, s0) - c0);
+            x1 = (int)(min(c1, s1) - c0);
+        };
+        // edge lines: exact inclusive per-point predicate (line_shapes.jl:10)
+        auto edge = [&](int e0, int e1) {
+            for (int j = e0; j < e1; j++) {
                 double4 rc = st[j];
 #pragma unroll
                 for (int r = 0; r < R; r++) {
                     double dnu = nup[r] - rc.x;
-                    if (!(fabs(dnu) > cut)) acc[r] += eval_one<SHAPE>(rc, dnu, slow_lev, c0 + j, B1, B2);
+                    if (!(fabs(dnu) > cut)) acc[r] += eval_checked<SHAPE>(rc, dnu, slow_lev, c0 + j, B1, B2);
                 }
             }
-            // segment B: interior lines, no predicate
-            const int b0 = max(j0, ia), b1 = min(j1, ib);
+        };
+        // far lines: inside the cut-off for every point and safely in the far wing -> no test of any kind
+        auto far = [&](int f0, int f1) {
+            if (SHAPE == CS_DOPPLER) return;       // exp(-(dnu/alpha)^2) underflows to exactly 0 out here
+            int j = f0;
             if (SHAPE == CS_VOIGT || SHAPE == CS_LORENTZ) {
-                int j = b0;
-                for (; j + 1 < b1; j += 2) {
+                for (; j + 1 < f1; j += 2) {
                     double4 ra = st[j], rb = st[j + 1];
-                    double qa[R], qb[R];
-                    bool slowp = false;
 #pragma unroll
                     for (int r = 0; r < R; r++) {
                         double da = nup[r] - ra.x, db = nup[r] - rb.x;
-                        qa[r] = fma(da, da, ra.y);
-                        qb[r] = fma(db, db, rb.y);
-                        if (SHAPE == CS_VOIGT)
-                            slowp |= (__double2hiint(qa[r]) <= __double2hiint(ra.w)) |
-                                     (__double2hiint(qb[r]) <= __double2hiint(rb.w));
+                        double qa = fma(da, da, ra.y), qb = fma(db, db, rb.y);
+                        double num = ra.z * qb;
+                        num = fma(rb.z, qa, num);
+                        acc[r] = fma(num, cs_rcp(qa * qb), acc[r]);
                     }
-                    if (!slowp) {
-#pragma unroll
-                        for (int r = 0; r < R; r++) {
-                            double num = ra.z * qb[r];
-                            num = fma(rb.z, qa[r], num);
-                            double den = qa[r] * qb[r];
-                            acc[r] = fma(num, cs_rcp(den), acc[r]);
-                        }
-                    } else {
-#pragma unroll 1
-                        for (int r = 0; r < R; r++) {
-                            acc[r] += eval_one<SHAPE>(ra, nup[r] - ra.x, slow_lev, c0 + j, B1, B2);
-                            acc[r] += eval_one<SHAPE>(rb, nup[r] - rb.x, slow_lev, c0 + j + 1, B1, B2);
-                        }
-                    }
-                }
-                if (j < b1) {
-                    double4 rc = st[j];
-#pragma unroll
-                    for (int r = 0; r < R; r++) acc[r] += eval_one<SHAPE>(rc, nup[r] - rc.x, slow_lev, c0 + j, B1, B2);
-                }
-            } else {
-                for (int j = b0; j < b1; j++) {
-                    double4 rc = st[j];
-#pragma unroll
-                    for (int r = 0; r < R; r++) acc[r] += eval_one<SHAPE>(rc, nup[r] - rc.x, slow_lev, c0 + j, B1, B2);
                 }
             }
-            // segment C: edge lines above the interior
-            for (int j = max(j0, ib); j < j1; j++) {
+            for (; j < f1; j++) {
                 double4 rc = st[j];
 #pragma unroll
                 for (int r = 0; r < R; r++) {
                     double dnu = nup[r] - rc.x;
-                    if (!(fabs(dnu) > cut)) acc[r] += eval_one<SHAPE>(rc, dnu, slow_lev, c0 + j, B1, B2);
+                    if (SHAPE == CS_PHCO2) {
+                        double ge = chi_phco2(fabs(dnu), B1, B2) * rc.y;
+                        acc[r] = fma(rc.z * ge, cs_rcp(fma(dnu, dnu, ge * ge)), acc[r]);
+                    } else {
+                        acc[r] = fma(rc.z, cs_rcp(fma(dnu, dnu, rc.y)), acc[r]);
+                    }
                 }
             }
-        }
+        };
+        // near lines: inside the cut-off for every point, Faddeyeva region decided per evaluation
+        auto near = [&](int n0, int n1) {
+            for (int j = n0; j < n1; j++) {
+                double4 rc = st[j];
+#pragma unroll
+                for (int r = 0; r < R; r++) acc[r] += eval_checked<SHAPE>(rc, nup[r] - rc.x, slow_lev, c0 + j, B1, B2);
+            }
+        };
+        int x0, x1;
+        seg(wlo, ilo, x0, x1); edge(x0, x1);
+        seg(ilo, nlo, x0, x1); far(x0, x1);
+        seg(nlo, nhi, x0, x1); near(x0, x1);
+        seg(nhi, ihi, x0, x1); far(x0, x1);
+        seg(ihi, whi, x0, x1); edge(x0, x1);
+        // stage s is free again: refill it with chunk c + LS_STAGES
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty_bar[s]);
+        if (lane == 0 && c + LS_STAGES < nchunk) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue(c + LS_STAGES);
+        }
     }
-    const double scale = a.lev[lev].scale;
 #pragma unroll
     for (int r = 0; r < R; r++) {
-        int64_t i = wbase + 32 * r + lane;
-        if (valid[r]) {
+        int64_t i = tile0 + 32 * r + lane;
+        if (i < a.nnu) {
             size_t o = (size_t)lev * a.nnu + i;
-            double v = scale * acc[r];
+            double v = lp.scale * acc[r];
             a.out[o] = a.accumulate ? a.out[o] + v : v;
         }
     }
 }
 
-template <int SHAPE, int R> int32_t launch_line_sum(cs_ctx* ctx, const LineSumArgs& a, int nlev)
+template <int SHAPE, int R> int32_t launch_line_sum(cs_ctx* ctx, LineSumArgs a, int nlev, double cn)
 {
-    constexpr int TILE = LS_WARPS * 32 * R;
-    size_t smem = (size_t)LS_STAGES * LS_CHUNK * sizeof(double4);
-    dim3 grid((unsigned)((a.nnu + TILE - 1) / TILE), (unsigned)nlev);
-    line_sum_kernel<SHAPE, R><<<grid, LS_THREADS, smem, ctx->stream>>>(a);
+    constexpr int TILE = 32 * R;
+    cudaStream_t st = ctx->stream;
+    a.ntiles = (a.nnu + TILE - 1) / TILE;
+    CS_TRY(ctx->s_w.reserve(sizeof(int64_t) * 6 * (size_t)a.ntiles));
+    a.ranges = ctx->s_w.as<int64_t>();
+    tile_ranges_kernel<<<(unsigned)((a.ntiles * 6 + 127) / 128), 128, 0, st>>>(a.nu, a.nnu, a.nul, a.nl, a.cut, cn, TILE,
+                                                                               a.ntiles, ctx->s_w.as<int64_t>());
     CS_CUDA(cudaGetLastError());
-    cs_count_launch(ctx);
+    size_t smem = (size_t)LS_WARPS * LS_STAGES * LS_CHUNK * sizeof(double4);
+    static bool attr_set = false;
+    if (!attr_set) {
+        CS_CUDA(cudaFuncSetAttribute(line_sum_kernel<SHAPE, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    dim3 grid((unsigned)((a.ntiles + LS_WARPS - 1) / LS_WARPS), (unsigned)nlev);
+    line_sum_kernel<SHAPE, R><<<grid, LS_THREADS, smem, st>>>(a);
+    CS_CUDA(cudaGetLastError());
+    cs_count_launch(ctx, 2);
     return CS_OK;
 }
 
@@ -460,7 +477,15 @@ int32_t cs_lines_accumulate(cs_lines* L, int32_t shape, int64_t nnu, const doubl
             lp.scale = h_scale ? h_scale[k0 + k] : 1.0;
             lp.B1 = 0.0888 - 0.16 * exp(-0.0041 * lp.T);   // line_shapes.jl:472
             lp.B2 = 0.0526 * exp(-0.00152 * lp.T);          // line_shapes.jl:476
-            lp.pad0 = lp.pad1 = 0;
+            // near-centre half width as a fraction of the line position: sqrt(thr_j) = nul_j * f(T, mu_j)
+            double vth = sqrt(2.0 * CS_R * lp.T / L->mu_min) / CS_C;
+            if (shape == CS_VOIGT || shape == CS_PHCO2)
+                lp.cnear = sqrt(1.6e4 * (1.0 + 1e-9)) / 0.83255461115769775635 * vth * (1.0 + 1e-6);
+            else if (shape == CS_DOPPLER)
+                lp.cnear = sqrt(746.0) * vth * (1.0 + 1e-6);
+            else
+                lp.cnear = -1.0;
+            lp.pad1 = 0;
         }
         // pageable H2D of a few KB; synchronous with respect to the host buffer
         CS_CUDA(cudaMemcpyAsync(ctx->s_lev.p, hl.data(), sizeof(LevelParams) * (size_t)kb, cudaMemcpyHostToDevice, st));
@@ -484,11 +509,13 @@ int32_t cs_lines_accumulate(cs_lines* L, int32_t shape, int64_t nnu, const doubl
         la.nu = d_nu; la.nnu = nnu; la.nul = L->nu + j0; la.nl = nl;
         la.rec = pa.rec; la.slow = pa.slow; la.lev = pa.lev; la.cut = cut;
         la.out = d_out + (size_t)k0 * nnu; la.accumulate = accumulate;
+        double cn = 0.0;
+        for (int64_t k = 0; k < kb; k++) cn = std::max(cn, hl[(size_t)k].cnear);
         switch (shape) {
-        case CS_DOPPLER: CS_TRY((launch_line_sum<CS_DOPPLER, 4>(ctx, la, (int)kb))); break;
-        case CS_LORENTZ: CS_TRY((launch_line_sum<CS_LORENTZ, 4>(ctx, la, (int)kb))); break;
-        case CS_VOIGT:   CS_TRY((launch_line_sum<CS_VOIGT, 4>(ctx, la, (int)kb))); break;
-        default:         CS_TRY((launch_line_sum<CS_PHCO2, 4>(ctx, la, (int)kb))); break;
+        case CS_DOPPLER: CS_TRY((launch_line_sum<CS_DOPPLER, 4>(ctx, la, (int)kb, cn))); break;
+        case CS_LORENTZ: CS_TRY((launch_line_sum<CS_LORENTZ, 4>(ctx, la, (int)kb, cn))); break;
+        case CS_VOIGT:   CS_TRY((launch_line_sum<CS_VOIGT, 4>(ctx, la, (int)kb, cn))); break;
+        default:         CS_TRY((launch_line_sum<CS_PHCO2, 4>(ctx, la, (int)kb, cn))); break;
         }
         CS_CUDA(cudaEventRecord(ctx->ev2, st));
         CS_CUDA(cudaEventSynchronize(ctx->ev2));
