@@ -99,13 +99,12 @@ __global__ void __launch_bounds__(256) prep_kernel(PrepArgs a)
     } else {
         double beta = 1 / alpha;
         double dd = sqln2 * beta;
-        // far-wing test |z|^2 >= 1.6e4 in Lorentz variables: dnu^2 + gamma^2 >= 1.6e4/d^2; the margin
-        // sends the rounding-ambiguous sliver to the general routine, which decides like the reference
-        double thr = (1.6e4 / (dd * dd)) * (1.0 + 1e-9);
+        // |z|^2 = x^2 + y^2 = d^2 (dnu^2 + gamma^2): the record carries d^2 so that the Faddeyeva region can be
+        // decided from Lorentz variables; ambiguous slivers go to the general routine (decides like the reference)
         if (a.shape == CS_VOIGT)
-            r = make_double4(nul, gamma * gamma, S * gamma / CS_PI, thr);
+            r = make_double4(nul, gamma * gamma, S * gamma / CS_PI, dd * dd);
         else
-            r = make_double4(nul, gamma, S / CS_PI, thr);
+            r = make_double4(nul, gamma, S / CS_PI, dd * dd);
         s = make_double4(dd, gamma * dd, S * (osqpiln2 * beta), gamma);
     }
     size_t o = (size_t)k * a.nl + jj;
@@ -206,6 +205,14 @@ __device__ __forceinline__ double chi_phco2(double adnu, double B1, double B2)
     return exp(-B1 * 27.0 - B2 * 90.0 - 0.0232 * (adnu - 120.0));
 }
 
+// hi-word thresholds of |z|^2 with a 1e-6 guard band (the hi word of a double resolves 2^-20 ~ 1e-6):
+//   hi(s) >  S1_HI              =>  s > 1.6e4 (1+1e-6)   : 1 convergent, certainly
+//   S2_HI < hi(s) < S1_LO       =>  160 (1+1e-6) < s < 1.6e4 (1-1e-6) : 2 convergents, certainly
+// anything else is decided by the general routine with the reference's own s = fma(x,x,y^2).
+#define CS_S1_HI 0x40CF4004   /* hi word of 1.6e4*(1+1.0e-6) rounded up   (1.6e4 = 0x40CF4000 00000000) */
+#define CS_S1_LO 0x40CF3FFB   /* hi word of 1.6e4*(1-1.0e-6) rounded down */
+#define CS_S2_HI 0x40640002   /* hi word of 160*(1+1.0e-6) rounded up     (160 = 0x40640000 00000000) */
+
 // one (line, point) evaluation, any shape, any Faddeyeva region (edge and near-centre lines)
 template <int SHAPE>
 __device__ __forceinline__ double eval_checked(const double4 rc, double dnu, const double4* __restrict__ slow,
@@ -218,14 +225,24 @@ __device__ __forceinline__ double eval_checked(const double4 rc, double dnu, con
         double t = dnu * dnu * rc.y;
         return (t < 746.0) ? rc.z * exp(-t) : 0.0;   // exp(-t) is exactly 0 beyond (as in the reference)
     } else if (SHAPE == CS_VOIGT) {
+        // branch-free choice between the 1- and 2-convergent forms, both written in Lorentz variables:
+        //   1: K/q          2: K d^2 (s+1/2) / ((s-1/2)^2 + 2 y^2),   s = d^2 q,  y^2 = d^2 gamma^2
         double q = fma(dnu, dnu, rc.y);
-        if (__double2hiint(q) > __double2hiint(rc.w)) return rc.z * cs_rcp(q);
-        return voigt_near(slow, j, dnu, 1.0);
+        double s = rc.w * q;
+        int hs = __double2hiint(s);
+        bool one = hs > CS_S1_HI;
+        bool two = (hs < CS_S1_LO) & (hs > CS_S2_HI);
+        double sm = s - 0.5;
+        double den2 = fma(sm, sm, 2.0 * (rc.w * rc.y));
+        double num2 = (rc.z * rc.w) * (s + 0.5);
+        double v = (one ? rc.z : num2) * cs_rcp(one ? q : den2);
+        if (!(one | two)) v = voigt_near(slow, j, dnu, 1.0);
+        return v;
     } else {
         double chi = chi_phco2(fabs(dnu), B1, B2);
         double ge = chi * rc.y;
         double q = fma(dnu, dnu, ge * ge);
-        if (__double2hiint(q) > __double2hiint(rc.w)) return (rc.z * ge) * cs_rcp(q);
+        if (__double2hiint(rc.w * q) > CS_S1_HI) return (rc.z * ge) * cs_rcp(q);
         return voigt_near(slow, j, dnu, chi);
     }
 }
