@@ -205,8 +205,10 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    # run the library on torch's current stream so that torch.cuda.Event brackets its kernels
-    ctx = cs.Context(local, stream=torch.cuda.current_stream().cuda_stream)
+    # run the library on torch's current (non-default) stream so that torch.cuda.Event brackets its kernels
+    stream = torch.cuda.Stream(device=local)
+    torch.cuda.set_stream(stream)
+    ctx = cs.Context(local, stream=stream.cuda_stream)
     wl = make_workload(cs, args.workload)
     ν, P, T = wl["ν"], wl["P"], wl["T"]
     nlev = len(P)

@@ -77,7 +77,7 @@ class CIATables:
         self._dev = {}
 
     def flat(self):
-        """flattened arrays in the C-ABI's order (also what the oracle consumes)"""
+        """flattened arrays in the order the C ABI takes them (cs_cia_upload)"""
         g_nnu = np.array([len(g[0]) for g in self.grids], dtype=np.int64)
         g_nT = np.array([len(g[1]) for g in self.grids], dtype=np.int64)
         cat = lambda xs: f64(np.concatenate(xs)) if xs else np.zeros(0)
