@@ -29,8 +29,9 @@ namespace {
 
 constexpr int LS_WARPS = 8;                       // warps per CTA; every warp is an independent work unit
 constexpr int LS_THREADS = LS_WARPS * 32;
-constexpr int LS_CHUNK = 128;                     // lines per shared-memory stage (4 KB), one ring per warp
-constexpr int LS_STAGES = 3;
+constexpr int LS_CHUNK = 64;                      // lines per shared-memory stage (2 KB), one ring per warp
+constexpr int LS_STAGES = 4;
+constexpr int LS_QCAP = 256;                      // per-warp queue of evaluations that need the general routine
 
 struct LevelParams {
     double T, P, Pp, scale;
@@ -213,6 +214,23 @@ __device__ __forceinline__ double chi_phco2(double adnu, double B1, double B2)
 #define CS_S1_LO 0x40CF3FFB   /* hi word of 1.6e4*(1-1.0e-6) rounded down */
 #define CS_S2_HI 0x40640002   /* hi word of 160*(1+1.0e-6) rounded up     (160 = 0x40640000 00000000) */
 
+// branch-free choice between the 1- and 2-convergent forms, both written in Lorentz variables:
+//   1: K/q          2: K d^2 (s+1/2) / ((s-1/2)^2 + 2 y^2),   s = d^2 q,  y^2 = d^2 gamma^2
+// need = true when neither form is certain (guard bands, |z|^2 < 160): the caller must use the general routine
+__device__ __forceinline__ double voigt_12(const double4 rc, double dnu, bool& need)
+{
+    double q = fma(dnu, dnu, rc.y);
+    double s = rc.w * q;
+    int hs = __double2hiint(s);
+    bool one = hs > CS_S1_HI;
+    bool two = (hs < CS_S1_LO) & (hs > CS_S2_HI);
+    double sm = s - 0.5;
+    double den2 = fma(sm, sm, 2.0 * (rc.w * rc.y));
+    double num2 = (rc.z * rc.w) * (s + 0.5);
+    need = !(one | two);
+    return (one ? rc.z : num2) * cs_rcp(one ? q : den2);
+}
+
 // one (line, point) evaluation, any shape, any Faddeyeva region (edge and near-centre lines)
 template <int SHAPE>
 __device__ __forceinline__ double eval_checked(const double4 rc, double dnu, const double4* __restrict__ slow,
@@ -225,18 +243,9 @@ __device__ __forceinline__ double eval_checked(const double4 rc, double dnu, con
         double t = dnu * dnu * rc.y;
         return (t < 746.0) ? rc.z * exp(-t) : 0.0;   // exp(-t) is exactly 0 beyond (as in the reference)
     } else if (SHAPE == CS_VOIGT) {
-        // branch-free choice between the 1- and 2-convergent forms, both written in Lorentz variables:
-        //   1: K/q          2: K d^2 (s+1/2) / ((s-1/2)^2 + 2 y^2),   s = d^2 q,  y^2 = d^2 gamma^2
-        double q = fma(dnu, dnu, rc.y);
-        double s = rc.w * q;
-        int hs = __double2hiint(s);
-        bool one = hs > CS_S1_HI;
-        bool two = (hs < CS_S1_LO) & (hs > CS_S2_HI);
-        double sm = s - 0.5;
-        double den2 = fma(sm, sm, 2.0 * (rc.w * rc.y));
-        double num2 = (rc.z * rc.w) * (s + 0.5);
-        double v = (one ? rc.z : num2) * cs_rcp(one ? q : den2);
-        if (!(one | two)) v = voigt_near(slow, j, dnu, 1.0);
+        bool need;
+        double v = voigt_12(rc, dnu, need);
+        if (need) v = voigt_near(slow, j, dnu, 1.0);
         return v;
     } else {
         double chi = chi_phco2(fabs(dnu), B1, B2);
@@ -293,6 +302,12 @@ __global__ void __launch_bounds__(LS_THREADS, 2) line_sum_kernel(LineSumArgs a)
     const double cut = a.cut;
     const LevelParams lp = a.lev[lev];
     double4* ring = reinterpret_cast<double4*>(smem_raw) + (size_t)warp * LS_STAGES * LS_CHUNK;
+    // per-warp extras behind the rings: copy of the tile's wavenumbers, deferred-evaluation accumulators, queue
+    constexpr size_t EXTRA = (size_t)2 * TILE * sizeof(double) + LS_QCAP * sizeof(uint32_t);
+    unsigned char* xb = smem_raw + (size_t)LS_WARPS * LS_STAGES * LS_CHUNK * sizeof(double4) + (size_t)warp * EXTRA;
+    double* nutile = reinterpret_cast<double*>(xb);
+    double* cacc = nutile + TILE;
+    uint32_t* queue = reinterpret_cast<uint32_t*>(cacc + TILE);
 
     if (lane == 0) {
         for (int s = 0; s < LS_STAGES; s++) mbar_init(&full_bar[warp][s], 1);
@@ -330,8 +345,16 @@ __global__ void __launch_bounds__(LS_THREADS, 2) line_sum_kernel(LineSumArgs a)
         int64_t i = tile0 + 32 * r + lane;
         nup[r] = a.nu[i < a.nnu ? i : (a.nnu - 1)];
         acc[r] = 0.0;
+        nutile[32 * r + lane] = nup[r];
+        cacc[32 * r + lane] = 0.0;
     }
+    __syncwarp();
     const double B1 = lp.B1, B2 = lp.B2;
+    int qn = 0;   // entries in the queue (warp-uniform)
+    // edge lines are normally ~cut-off away from every point, i.e. far wing; only when the near-centre range
+    // reaches into the edge classes (tiny cut-offs, very coarse grids) do they need the per-evaluation region test
+    const bool edge_is_far = (SHAPE == CS_LORENTZ) || (SHAPE == CS_VOIGT && rg[4] >= ilo && rg[5] <= ihi && ilo < ihi);
+    const unsigned lt_mask = (1u << lane) - 1u;
 
     for (int c = 0; c < nchunk; c++) {
         const int s = c % LS_STAGES;
@@ -344,9 +367,48 @@ __global__ void __launch_bounds__(LS_THREADS, 2) line_sum_kernel(LineSumArgs a)
             x0 = (int)(max(c0, s0) - c0);
             x1 = (int)(min(c1, s1) - c0);
         };
+        // general-routine evaluations deferred by the near loop: one dense pass with all lanes busy
+        auto flush = [&]() {
+            for (int e = lane; e < qn; e += 32) {
+                uint32_t en = queue[e];
+                int j = (int)(en >> 8), p = (int)(en & 255u);
+                double4 rc = st[j];
+                atomicAdd(&cacc[p], voigt_near(slow_lev, c0 + j, nutile[p] - rc.x, 1.0));
+            }
+            __syncwarp();
+            qn = 0;
+        };
         // edge lines: exact inclusive per-point predicate (line_shapes.jl:10)
         auto edge = [&](int e0, int e1) {
-            for (int j = e0; j < e1; j++) {
+            int j = e0;
+            if ((SHAPE == CS_VOIGT || SHAPE == CS_LORENTZ) && edge_is_far) {
+                // far-wing pairs with the predicate folded into the numerators; a 32-point slice that is outside
+                // both windows is skipped warp-wide
+                for (; j + 1 < e1; j += 2) {
+                    double4 ra = st[j], rb = st[j + 1];
+#pragma unroll
+                    for (int r = 0; r < R; r++) {
+                        double da = nup[r] - ra.x, db = nup[r] - rb.x;
+                        bool ia = !(fabs(da) > cut), ib = !(fabs(db) > cut);
+                        if (!__any_sync(0xffffffffu, ia | ib)) continue;
+                        double qa = fma(da, da, ra.y), qb = fma(db, db, rb.y);
+                        double num = (ia ? ra.z : 0.0) * qb;
+                        num = fma(ib ? rb.z : 0.0, qa, num);
+                        acc[r] = fma(num, cs_rcp(qa * qb), acc[r]);
+                    }
+                }
+                for (; j < e1; j++) {
+                    double4 rc = st[j];
+#pragma unroll
+                    for (int r = 0; r < R; r++) {
+                        double dnu = nup[r] - rc.x;
+                        bool in = !(fabs(dnu) > cut);
+                        acc[r] = fma(in ? rc.z : 0.0, cs_rcp(fma(dnu, dnu, rc.y)), acc[r]);
+                    }
+                }
+                return;
+            }
+            for (; j < e1; j++) {
                 double4 rc = st[j];
 #pragma unroll
                 for (int r = 0; r < R; r++) {
@@ -390,8 +452,23 @@ __global__ void __launch_bounds__(LS_THREADS, 2) line_sum_kernel(LineSumArgs a)
         auto near = [&](int n0, int n1) {
             for (int j = n0; j < n1; j++) {
                 double4 rc = st[j];
+                if (SHAPE == CS_VOIGT) {
+                    if (qn > LS_QCAP - TILE) flush();
 #pragma unroll
-                for (int r = 0; r < R; r++) acc[r] += eval_checked<SHAPE>(rc, nup[r] - rc.x, slow_lev, c0 + j, B1, B2);
+                    for (int r = 0; r < R; r++) {
+                        bool need;
+                        double v = voigt_12(rc, nup[r] - rc.x, need);
+                        acc[r] += need ? 0.0 : v;
+                        unsigned m = __ballot_sync(0xffffffffu, need);
+                        if (m) {   // defer: compact (line, point) into the queue, order fixed by (line, slice, lane)
+                            if (need) queue[qn + __popc(m & lt_mask)] = ((uint32_t)j << 8) | (uint32_t)(32 * r + lane);
+                            qn += __popc(m);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int r = 0; r < R; r++) acc[r] += eval_checked<SHAPE>(rc, nup[r] - rc.x, slow_lev, c0 + j, B1, B2);
+                }
             }
         };
         int x0, x1;
@@ -400,6 +477,7 @@ __global__ void __launch_bounds__(LS_THREADS, 2) line_sum_kernel(LineSumArgs a)
         seg(nlo, nhi, x0, x1); near(x0, x1);
         seg(nhi, ihi, x0, x1); far(x0, x1);
         seg(ihi, whi, x0, x1); edge(x0, x1);
+        if (SHAPE == CS_VOIGT && qn > 0) { __syncwarp(); flush(); }
         // stage s is free again: refill it with chunk c + LS_STAGES
         __syncwarp();
         if (lane == 0 && c + LS_STAGES < nchunk) {
@@ -412,7 +490,7 @@ __global__ void __launch_bounds__(LS_THREADS, 2) line_sum_kernel(LineSumArgs a)
         int64_t i = tile0 + 32 * r + lane;
         if (i < a.nnu) {
             size_t o = (size_t)lev * a.nnu + i;
-            double v = lp.scale * acc[r];
+            double v = lp.scale * (SHAPE == CS_VOIGT ? acc[r] + cacc[32 * r + lane] : acc[r]);
             a.out[o] = a.accumulate ? a.out[o] + v : v;
         }
     }
@@ -428,7 +506,7 @@ template <int SHAPE, int R> int32_t launch_line_sum(cs_ctx* ctx, LineSumArgs a, 
     tile_ranges_kernel<<<(unsigned)((a.ntiles * 6 + 127) / 128), 128, 0, st>>>(a.nu, a.nnu, a.nul, a.nl, a.cut, cn, TILE,
                                                                                a.ntiles, ctx->s_w.as<int64_t>());
     CS_CUDA(cudaGetLastError());
-    size_t smem = (size_t)LS_WARPS * LS_STAGES * LS_CHUNK * sizeof(double4);
+    size_t smem = (size_t)LS_WARPS * (LS_STAGES * LS_CHUNK * sizeof(double4) + 2 * TILE * sizeof(double) + LS_QCAP * sizeof(uint32_t));
     static bool attr_set = false;
     if (!attr_set) {
         CS_CUDA(cudaFuncSetAttribute(line_sum_kernel<SHAPE, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
