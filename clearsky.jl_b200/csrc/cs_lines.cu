@@ -27,6 +27,9 @@
 
 namespace {
 
+#ifndef CS_LS_QUAD
+#define CS_LS_QUAD 1
+#endif
 constexpr int LS_WARPS = 8;                       // warps per CTA; every warp is an independent work unit
 constexpr int LS_THREADS = LS_WARPS * 32;
 constexpr int LS_CHUNK = 64;                      // lines per shared-memory stage (2 KB), one ring per warp
@@ -422,6 +425,22 @@ __global__ void __launch_bounds__(LS_THREADS, 2) line_sum_kernel(LineSumArgs a)
             if (SHAPE == CS_DOPPLER) return;       // exp(-(dnu/alpha)^2) underflows to exactly 0 out here
             int j = f0;
             if (SHAPE == CS_VOIGT || SHAPE == CS_LORENTZ) {
+#if CS_LS_QUAD
+                // four lines per reciprocal: (n1/d1 + n2/d2) = (n1 d2 + n2 d1)/(d1 d2) applied twice -> 5.75 FP64 ops/eval
+                for (; j + 3 < f1; j += 4) {
+                    double4 ra = st[j], rb = st[j + 1], rc = st[j + 2], rd = st[j + 3];
+#pragma unroll
+                    for (int r = 0; r < R; r++) {
+                        double da = nup[r] - ra.x, db = nup[r] - rb.x, dc = nup[r] - rc.x, dd = nup[r] - rd.x;
+                        double qa = fma(da, da, ra.y), qb = fma(db, db, rb.y);
+                        double qc = fma(dc, dc, rc.y), qd = fma(dd, dd, rd.y);
+                        double n1 = fma(rb.z, qa, ra.z * qb), d1 = qa * qb;
+                        double n2 = fma(rd.z, qc, rc.z * qd), d2 = qc * qd;
+                        double num = fma(n2, d1, n1 * d2);
+                        acc[r] = fma(num, cs_rcp(d1 * d2), acc[r]);
+                    }
+                }
+#endif
                 for (; j + 1 < f1; j += 2) {
                     double4 ra = st[j], rb = st[j + 1];
 #pragma unroll
