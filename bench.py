@@ -30,6 +30,9 @@ sys.path.insert(0, ROOT)
 METRIC = "line×ν×layer evals/s"
 UNIT = "evals/s"
 FLOP_PER_EVAL = 10.0   # Voigt, far-wing dominated
+# dram__bytes_read.sum + dram__bytes_write.sum of one line_sum_kernel<VOIGT> launch (one gas, 101 levels) on C2, from the
+# ncu --set full capture summarised in profiles/r1_ncu_full_line_sum_voigt.csv
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 1.658598e9 + 0.235005e9
 
 
 # ------------------------------------------------------------------------------------------------
@@ -93,26 +96,57 @@ def trapz_weights(ν):
 
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region"""
+    """SM clock, power and throttle reasons sampled DURING the timed region (NVML in-process: a few microseconds per
+    sample, no nvidia-smi process spawns competing with the launches; nvidia-smi is the fallback)."""
 
-    def __init__(self, device):
-        self.device = device
-        self.rows = []
+    def __init__(self, device, period=0.1):
+        self.device, self.period = device, period
+        self.rows = []          # (sm_mhz, sm_max_mhz, power_w, reasons bitmask)
         self._stop = threading.Event()
         self._t = None
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[device]) if vis and vis.split(",")[device].isdigit() else device
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self._nvml = pynvml
+        except Exception:
+            self._nvml = None
 
-    def _run(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        while not self._stop.is_set():
+    def _sample(self):
+        nv = self._nvml
+        if nv is not None:
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.device), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
+                sm = nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)
+                mx = nv.nvmlDeviceGetMaxClockInfo(self._h, nv.NVML_CLOCK_SM)
+                pw = nv.nvmlDeviceGetPowerUsage(self._h) / 1000.0
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                self.rows.append((float(sm), float(mx), pw, int(rs)))
+                return
             except Exception:
                 pass
-            self._stop.wait(0.2)
+        try:
+            q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+            out = subprocess.run(["nvidia-smi", "-i", str(self.device), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                 capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+            bits = 0
+            for i, b in enumerate((0x8, 0x40, 0x20, 0x4)):
+                if out[3 + i].strip().lower().startswith("active"):
+                    bits |= b
+            self.rows.append((float(out[0]), float(out[1]), float(out[2]), bits))
+        except Exception:
+            pass
+
+    def _run(self):
+        while not self._stop.is_set():
+            self._sample()
+            self._stop.wait(self.period if self._nvml is not None else 1.0)
 
     def __enter__(self):
         self._t = threading.Thread(target=self._run, daemon=True)
@@ -126,13 +160,13 @@ class ClockSampler:
     def summary(self):
         if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows if len(r) > 3 + i)]
-        pw = [float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()]
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "reasons": reasons, "samples": len(self.rows)}
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+        bits = 0
+        for r in self.rows:
+            bits |= r[3]
+        return {"sm_mhz": float(np.median([r[0] for r in self.rows])), "sm_max_mhz": max(r[1] for r in self.rows),
+                "power_w_max": max(r[2] for r in self.rows), "reasons": [n for b, n in names.items() if bits & b],
+                "samples": len(self.rows), "source": "nvml" if self._nvml is not None else "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -344,7 +378,8 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "clocks": clk.summary(),
         "roofline": {"bound": "fp64", "kernel": "line_sum_kernel<VOIGT>", "achieved": achieved, "peak": fp64_peak / 1e12,
-                     "unit": "TFLOP/s", "frac": (achieved / (fp64_peak / 1e12)) if achieved else None, "traffic": None,
+                     "unit": "TFLOP/s", "frac": (achieved / (fp64_peak / 1e12)) if achieved else None,
+                     "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH if wl["name"] == "c2" and world == 1 else None,
                      "peak_source": "cs_fp64_peak DFMA microbenchmark run in this process (FP64 is not in MEASURED_PEAKS.json)",
                      "flop_per_eval": FLOP_PER_EVAL, "kernel_ms_per_step": ls_ms, "launches_per_step": n_ls_launch,
                      "kernel_share_of_step": ls_ms / ms_step if ms_step > 0 else None,

@@ -61,6 +61,13 @@ static int32_t ctx_create(int32_t device, void* stream, bool own, cs_ctx** out)
         c->stream = (cudaStream_t)stream;
     }
     c->own_stream = own;
+    {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long thr = ~0ULL;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+    }
     cudaEventCreate(&c->ev0);
     cudaEventCreate(&c->ev1);
     cudaEventCreate(&c->ev2);
@@ -160,7 +167,7 @@ template <typename T> static int32_t upload(T** dst, const T* src, size_t n, cud
 {
     *dst = nullptr;
     if (n == 0) return CS_OK;
-    cudaError_t e = cudaMalloc((void**)dst, sizeof(T) * n);
+    cudaError_t e = cs_malloc((void**)dst, sizeof(T) * n, st);
     if (e != cudaSuccess) {
         cs_set_error("cudaMalloc(%zu bytes) failed: %s", sizeof(T) * n, cudaGetErrorString(e));
         return CS_ERR_NOMEM;
@@ -216,8 +223,9 @@ extern "C" int32_t cs_lines_free(cs_lines* L)
 {
     if (!L) return CS_OK;
     cudaSetDevice(L->ctx->device);
-    cudaFree(L->nu); cudaFree(L->S); cudaFree(L->ga); cudaFree(L->gs); cudaFree(L->Epp); cudaFree(L->na);
-    cudaFree(L->mu); cudaFree(L->iso); cudaFree(L->ncheb); cudaFree(L->cheb);
+    cudaStream_t st = L->ctx->stream;
+    cs_free(L->nu, st); cs_free(L->S, st); cs_free(L->ga, st); cs_free(L->gs, st); cs_free(L->Epp, st); cs_free(L->na, st);
+    cs_free(L->mu, st); cs_free(L->iso, st); cs_free(L->ncheb, st); cs_free(L->cheb, st);
     delete L;
     return CS_OK;
 }
@@ -290,9 +298,9 @@ extern "C" int32_t cs_sigma_create(cs_ctx* ctx, int64_t nnu, const double* nu, i
     s->sig = nullptr;
     int32_t rc = upload(&s->nu, nu, (size_t)nnu, ctx->stream);
     if (rc) { delete s; return rc; }
-    cudaError_t e = cudaMalloc((void**)&s->sig, sizeof(double) * (size_t)nnu * nnode);
+    cudaError_t e = cs_malloc((void**)&s->sig, sizeof(double) * (size_t)nnu * nnode, ctx->stream);
     if (e != cudaSuccess) {
-        cudaFree(s->nu);
+        cs_free(s->nu, ctx->stream);
         delete s;
         cs_set_error("cudaMalloc(sigma workspace %zu bytes): %s", sizeof(double) * (size_t)nnu * nnode, cudaGetErrorString(e));
         return CS_ERR_NOMEM;
@@ -316,9 +324,8 @@ extern "C" int32_t cs_sigma_free(cs_sigma* s)
 {
     if (!s) return CS_OK;
     cudaSetDevice(s->ctx->device);
-    cudaStreamSynchronize(s->ctx->stream);
-    if (s->own_nu) cudaFree(s->nu);
-    cudaFree(s->sig);
+    if (s->own_nu) cs_free(s->nu, s->ctx->stream);
+    cs_free(s->sig, s->ctx->stream);
     delete s;
     return CS_OK;
 }

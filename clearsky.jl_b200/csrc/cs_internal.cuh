@@ -149,6 +149,16 @@ struct cs_accel {
 };
 
 // ------------------------------------------------------------------------------------------------
+// stream-ordered allocation of the long-lived device objects (lines, tables, workspaces): the default memory pool
+// keeps freed blocks (release threshold = max), so re-creating objects of the same size every call costs no
+// cudaMalloc/cudaFree and no device synchronisation
+static inline cudaError_t cs_malloc(void** p, size_t bytes, cudaStream_t st) { return cudaMallocAsync(p, bytes, st); }
+static inline void cs_free(void* p, cudaStream_t st)
+{
+    if (p) cudaFreeAsync(p, st);
+}
+
+// ------------------------------------------------------------------------------------------------
 // launch bookkeeping
 static inline void cs_count_launch(cs_ctx* c, int64_t n = 1) { c->launches += n; }
 

@@ -568,12 +568,16 @@ int32_t cs_lines_accumulate(cs_lines* L, int32_t shape, int64_t nnu, const doubl
         return CS_OK;
     }
     // level batches sized so that the per-level records stay within a fixed HBM budget
-    size_t free_b = 0, total_b = 0;
-    CS_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    size_t budget = std::min<size_t>((size_t)8 << 30, free_b / 4 + ctx->s_rec.cap + ctx->s_slow.cap);
     bool need_slow = (shape == CS_VOIGT || shape == CS_PHCO2);
     size_t per_level = (size_t)nl * sizeof(double4) * (need_slow ? 2 : 1);
-    int64_t nb = std::max<int64_t>(1, std::min<int64_t>(nlev, (int64_t)(budget / per_level)));
+    size_t have = need_slow ? 2 * std::min(ctx->s_rec.cap, ctx->s_slow.cap) : ctx->s_rec.cap;
+    int64_t nb = nlev;
+    if (per_level * (size_t)nlev > have) {   // scratch must grow: size the level batch against free HBM
+        size_t free_b = 0, total_b = 0;
+        CS_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        size_t budget = std::min<size_t>((size_t)8 << 30, free_b / 4 + ctx->s_rec.cap + ctx->s_slow.cap);
+        nb = std::max<int64_t>(1, std::min<int64_t>(nlev, (int64_t)(budget / per_level)));
+    }
     nb = std::min<int64_t>(nb, 32768);
     CS_TRY(ctx->s_rec.reserve((size_t)nb * nl * sizeof(double4)));
     if (need_slow) CS_TRY(ctx->s_slow.reserve((size_t)nb * nl * sizeof(double4)));

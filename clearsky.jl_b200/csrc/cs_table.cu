@@ -19,7 +19,7 @@ int32_t upload_d(double** dst, const double* src, size_t n, cudaStream_t st)
 {
     *dst = nullptr;
     if (n == 0) return CS_OK;
-    if (cudaMalloc((void**)dst, sizeof(double) * n) != cudaSuccess) {
+    if (cs_malloc((void**)dst, sizeof(double) * n, st) != cudaSuccess) {
         cs_set_error("cudaMalloc(%zu bytes) failed", sizeof(double) * n);
         return CS_ERR_NOMEM;
     }
@@ -381,7 +381,7 @@ extern "C" int32_t cs_table_from_block(cs_ctx* ctx, int64_t nnu, int32_t nT, con
     CS_CUDA(cudaSetDevice(ctx->device));
     cs_table* tb = new_table(ctx, nnu, nT, Tg, nP, Pg);
     size_t bytes = sizeof(double) * (size_t)nT * nP * nnu;
-    if (cudaMalloc((void**)&tb->coef, bytes) != cudaSuccess) {
+    if (cs_malloc((void**)&tb->coef, bytes, ctx->stream) != cudaSuccess) {
         delete tb;
         cs_set_error("cudaMalloc(table %zu bytes) failed", bytes);
         return CS_ERR_NOMEM;
@@ -427,8 +427,8 @@ extern "C" int32_t cs_bake(cs_lines* L, int32_t shape, int64_t nnu, const double
     cs_table* tb = new_table(ctx, nnu, nT, Tg, nP, Pg);
     size_t bytes = sizeof(double) * (size_t)nk * nnu;
     double* blk = nullptr;
-    if (cudaMalloc((void**)&tb->coef, bytes) != cudaSuccess || cudaMalloc((void**)&blk, bytes) != cudaSuccess) {
-        if (tb->coef) cudaFree(tb->coef);
+    if (cs_malloc((void**)&tb->coef, bytes, ctx->stream) != cudaSuccess || cs_malloc((void**)&blk, bytes, ctx->stream) != cudaSuccess) {
+        if (tb->coef) cs_free(tb->coef, ctx->stream);
         delete tb;
         cs_set_error("cudaMalloc(table 2 x %zu bytes) failed", bytes);
         return CS_ERR_NOMEM;
@@ -441,7 +441,7 @@ extern "C" int32_t cs_bake(cs_lines* L, int32_t shape, int64_t nnu, const double
     }
     if (!rc && keep_block) {
         // keep sigma with the zero-mixing repair applied, exactly what bake hands to OpacityTable
-        if (cudaMalloc((void**)&tb->sigma_block, bytes) != cudaSuccess) {
+        if (cs_malloc((void**)&tb->sigma_block, bytes, ctx->stream) != cudaSuccess) {
             cs_set_error("cudaMalloc(sigma block %zu bytes) failed", bytes);
             rc = CS_ERR_NOMEM;
         } else {
@@ -451,7 +451,7 @@ extern "C" int32_t cs_bake(cs_lines* L, int32_t shape, int64_t nnu, const double
         }
     }
     if (!rc) rc = fit_table(ctx, tb, blk);
-    cudaFree(blk);
+    cs_free(blk, ctx->stream);
     if (rc) { cs_table_free(tb); return rc; }
     *out = tb;
     return CS_OK;
@@ -508,9 +508,8 @@ extern "C" int32_t cs_table_free(cs_table* tb)
 {
     if (!tb) return CS_OK;
     cudaSetDevice(tb->ctx->device);
-    cudaStreamSynchronize(tb->ctx->stream);
-    if (tb->coef) cudaFree(tb->coef);
-    if (tb->sigma_block) cudaFree(tb->sigma_block);
+    cs_free(tb->coef, tb->ctx->stream);
+    cs_free(tb->sigma_block, tb->ctx->stream);
     delete tb;
     return CS_OK;
 }
@@ -534,7 +533,7 @@ extern "C" int32_t cs_accel_from_sigma(cs_sigma* s, const double* P, cs_accel** 
     A->h_lnP.resize((size_t)s->nnode);
     for (int64_t i = 0; i < s->nnode; i++) A->h_lnP[(size_t)i] = log(P[i]);
     size_t n = (size_t)s->nnu * s->nnode;
-    if (cudaMalloc((void**)&A->lnsig, sizeof(double) * n) != cudaSuccess) {
+    if (cs_malloc((void**)&A->lnsig, sizeof(double) * n, ctx->stream) != cudaSuccess) {
         delete A;
         cs_set_error("cudaMalloc(accelerated absorber %zu bytes) failed", sizeof(double) * n);
         return CS_ERR_NOMEM;
@@ -551,8 +550,7 @@ extern "C" int32_t cs_accel_free(cs_accel* A)
 {
     if (!A) return CS_OK;
     cudaSetDevice(A->ctx->device);
-    cudaStreamSynchronize(A->ctx->stream);
-    cudaFree(A->lnsig);
+    cs_free(A->lnsig, A->ctx->stream);
     delete A;
     return CS_OK;
 }
@@ -639,7 +637,7 @@ extern "C" int32_t cs_cia_upload(cs_ctx* ctx, int32_t ngrid, const int64_t* g_nn
         cs_cia_free(c);
         return rc;
     }
-    if (cudaMalloc((void**)&c->d_desc, sizeof(int64_t) * desc.size()) != cudaSuccess) {
+    if (cs_malloc((void**)&c->d_desc, sizeof(int64_t) * desc.size(), st) != cudaSuccess) {
         cs_cia_free(c);
         cs_set_error("cudaMalloc(CIA descriptors) failed");
         return CS_ERR_NOMEM;
@@ -654,8 +652,8 @@ extern "C" int32_t cs_cia_free(cs_cia* c)
 {
     if (!c) return CS_OK;
     cudaSetDevice(c->ctx->device);
-    cudaStreamSynchronize(c->ctx->stream);
-    cudaFree(c->d_nu); cudaFree(c->d_T); cudaFree(c->d_lnk); cudaFree(c->d_snu); cudaFree(c->d_slnk); cudaFree(c->d_desc);
+    cudaStream_t st = c->ctx->stream;
+    cs_free(c->d_nu, st); cs_free(c->d_T, st); cs_free(c->d_lnk, st); cs_free(c->d_snu, st); cs_free(c->d_slnk, st); cs_free(c->d_desc, st);
     delete c;
     return CS_OK;
 }

@@ -31,3 +31,25 @@ for it in range(int(sys.argv[2]) if len(sys.argv) > 2 else 3):
     d = np.diff(t) * 1e3
     print(f"iter {it}: zero {d[0]:.2f} ms, add_lines {d[1]:.2f} + {d[2]:.2f} ms, fluxes {d[3]:.2f} ms, total {sum(d):.2f}; timers {ctx.timers()}")
 print("OLR", Fu[0])
+
+# ---- e2e pieces (host buffers -> result)
+import copy
+for it in range(4):
+    t = [time.perf_counter()]
+    dls2 = []
+    for sl, _ in wl["gases"]:
+        c = copy.copy(sl); c.__dict__.pop("_dev", None)
+        dls2.append(cs.DeviceLines(c, ctx))
+    t.append(time.perf_counter())
+    ws2 = cs.SigmaWorkspace(ν, nlev, ctx); t.append(time.perf_counter())
+    tm0 = ctx.timers()
+    for dl, C in zip(dls2, Cs):
+        check(lib().cs_sigma_add_lines(ws2.h, dl.h, 2, ptr(Tn), ptr(Pn), ptr(C), 25.0))
+    t.append(time.perf_counter())
+    tm1 = ctx.timers()
+    print("   kernel deltas: linesum", tm1["linesum"] - tm0["linesum"], "prep", tm1["prep"] - tm0["prep"])
+    check(lib().cs_fluxes(ws2.h, nlev, ptr(Pn), 2, ptr(f64(w)), ptr(μn), ptr(Tn), 9.8, None, None, 0.841, 5, ptr(f64(m)), ptr(f64(W)),
+                          None, None, None, None, ptr(Fu), ptr(Fd), ptr(Fn))); t.append(time.perf_counter())
+    del dls2, ws2; t.append(time.perf_counter())
+    d = np.diff(t) * 1e3
+    print(f"e2e {it}: upload lines {d[0]:.2f} ms, workspace {d[1]:.2f} ms, add_lines {d[2]:.2f} ms, fluxes {d[3]:.2f} ms, free {d[4]:.2f} ms")
