@@ -30,7 +30,10 @@ namespace {
 #ifndef CS_LS_QUAD
 #define CS_LS_QUAD 1
 #endif
-constexpr int LS_WARPS = 8;                       // warps per CTA; every warp is an independent work unit
+#ifndef CS_LS_WARPS
+#define CS_LS_WARPS 1
+#endif
+constexpr int LS_WARPS = CS_LS_WARPS;                       // warps per CTA; every warp is an independent work unit
 constexpr int LS_THREADS = LS_WARPS * 32;
 constexpr int LS_CHUNK = 64;                      // lines per shared-memory stage (2 KB), one ring per warp
 constexpr int LS_STAGES = 4;
@@ -286,12 +289,123 @@ __global__ void tile_ranges_kernel(const double* __restrict__ nu, int64_t nnu, c
     ranges[t] = v;
 }
 
-// K2.  Work unit = one warp = (tile of 32*R consecutive wavenumbers, level).  Each warp streams the records of
-// ITS OWN line window through a private 3-stage shared-memory ring fed by TMA bulk copies (one elected lane
-// issues cp.async.bulk, completion on a per-stage mbarrier), so warps never wait for each other.  The 8 warps of
-// a CTA take 8 adjacent tiles of the same level: their windows overlap by ~98 %, so the copies hit L2.
+// ---- cold paths of K2 (edge lines, near-centre lines, deferred general evaluations).  They are kept out of line
+// and accumulate into the warp's shared-memory accumulators (each lane only touches its own R slots, except for
+// the deferred pass which uses shared atomics), so that the register allocation and instruction schedule of the
+// hot far-wing loop are not polluted by them.
+struct WarpCold {
+    const double* nutile;      // [32*R] wavenumbers of this warp's tile (shared memory)
+    double* cacc;              // [32*R] accumulators of the cold paths (shared memory)
+    uint32_t* queue;           // [LS_QCAP] deferred (line, point) pairs
+    const double4* slow_lev;   // near-centre parameters of this level (global)
+    double cut, B1, B2;
+    int lane;
+    bool edge_is_far;
+};
+
 template <int SHAPE, int R>
-__global__ void __launch_bounds__(LS_THREADS, 2) line_sum_kernel(LineSumArgs a)
+__device__ __noinline__ void cold_flush(const WarpCold& w, const double4* st, int64_t c0, int qn)
+{
+    for (int e = w.lane; e < qn; e += 32) {
+        uint32_t en = w.queue[e];
+        int j = (int)(en >> 8), p = (int)(en & 255u);
+        double4 rc = st[j];
+        atomicAdd(&w.cacc[p], voigt_near(w.slow_lev, c0 + j, w.nutile[p] - rc.x, 1.0));
+    }
+    __syncwarp();
+}
+
+// edge lines: exact inclusive per-point predicate (line_shapes.jl:10)
+template <int SHAPE, int R>
+__device__ __noinline__ void cold_edge(const WarpCold& w, const double4* st, int64_t c0, int e0, int e1)
+{
+    const int lane = w.lane;
+    const double cut = w.cut;
+    double nup[R], acc[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) { nup[r] = w.nutile[32 * r + lane]; acc[r] = 0.0; }
+    int j = e0;
+    if ((SHAPE == CS_VOIGT || SHAPE == CS_LORENTZ) && w.edge_is_far) {
+        // far-wing pairs with the predicate folded into the numerators; a 32-point slice that is outside both
+        // windows is skipped warp-wide
+        for (; j + 1 < e1; j += 2) {
+            double4 ra = st[j], rb = st[j + 1];
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                double da = nup[r] - ra.x, db = nup[r] - rb.x;
+                bool ia = !(fabs(da) > cut), ib = !(fabs(db) > cut);
+                if (!__any_sync(0xffffffffu, ia | ib)) continue;
+                double qa = fma(da, da, ra.y), qb = fma(db, db, rb.y);
+                double num = (ia ? ra.z : 0.0) * qb;
+                num = fma(ib ? rb.z : 0.0, qa, num);
+                acc[r] = fma(num, cs_rcp(qa * qb), acc[r]);
+            }
+        }
+        for (; j < e1; j++) {
+            double4 rc = st[j];
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                double dnu = nup[r] - rc.x;
+                bool in = !(fabs(dnu) > cut);
+                acc[r] = fma(in ? rc.z : 0.0, cs_rcp(fma(dnu, dnu, rc.y)), acc[r]);
+            }
+        }
+    } else {
+        for (; j < e1; j++) {
+            double4 rc = st[j];
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                double dnu = nup[r] - rc.x;
+                if (!(fabs(dnu) > cut)) acc[r] += eval_checked<SHAPE>(rc, dnu, w.slow_lev, c0 + j, w.B1, w.B2);
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < R; r++) w.cacc[32 * r + lane] += acc[r];
+}
+
+// near lines: inside the cut-off for every point, Faddeyeva region decided per evaluation.  Returns the new
+// queue length.
+template <int SHAPE, int R>
+__device__ __noinline__ int cold_near(const WarpCold& w, const double4* st, int64_t c0, int n0, int n1, int qn)
+{
+    const int lane = w.lane;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    double nup[R], acc[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) { nup[r] = w.nutile[32 * r + lane]; acc[r] = 0.0; }
+    for (int j = n0; j < n1; j++) {
+        double4 rc = st[j];
+        if (SHAPE == CS_VOIGT) {
+            if (qn > LS_QCAP - 32 * R) { cold_flush<SHAPE, R>(w, st, c0, qn); qn = 0; }
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                bool need;
+                double v = voigt_12(rc, nup[r] - rc.x, need);
+                acc[r] += need ? 0.0 : v;
+                unsigned m = __ballot_sync(0xffffffffu, need);
+                if (m) {   // defer: compact (line, point) into the queue, order fixed by (line, slice, lane)
+                    if (need) w.queue[qn + __popc(m & lt_mask)] = ((uint32_t)j << 8) | (uint32_t)(32 * r + lane);
+                    qn += __popc(m);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < R; r++) acc[r] += eval_checked<SHAPE>(rc, nup[r] - rc.x, w.slow_lev, c0 + j, w.B1, w.B2);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < R; r++) w.cacc[32 * r + lane] += acc[r];
+    __syncwarp();
+    return qn;
+}
+
+// K2.  Work unit = one warp = (tile of 32*R consecutive wavenumbers, level).  Each warp streams the records of
+// ITS OWN line window through a private shared-memory ring fed by TMA bulk copies (one elected lane issues
+// cp.async.bulk, completion on a per-stage mbarrier), so warps never wait for each other.  The 8 warps of a CTA
+// take 8 adjacent tiles of the same level: their windows overlap by ~98 %, so the copies hit L2.
+template <int SHAPE, int R>
+__global__ void __launch_bounds__(LS_THREADS, 16 / LS_WARPS) line_sum_kernel(LineSumArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[LS_WARPS][LS_STAGES];
@@ -302,15 +416,17 @@ __global__ void __launch_bounds__(LS_THREADS, 2) line_sum_kernel(LineSumArgs a)
     const int64_t tile = (int64_t)blockIdx.x * LS_WARPS + warp;
     if (tile >= a.ntiles) return;
     const int64_t tile0 = tile * TILE;
-    const double cut = a.cut;
     const LevelParams lp = a.lev[lev];
     double4* ring = reinterpret_cast<double4*>(smem_raw) + (size_t)warp * LS_STAGES * LS_CHUNK;
-    // per-warp extras behind the rings: copy of the tile's wavenumbers, deferred-evaluation accumulators, queue
+    // per-warp extras behind the rings: copy of the tile's wavenumbers, cold-path accumulators, deferred queue
     constexpr size_t EXTRA = (size_t)2 * TILE * sizeof(double) + LS_QCAP * sizeof(uint32_t);
     unsigned char* xb = smem_raw + (size_t)LS_WARPS * LS_STAGES * LS_CHUNK * sizeof(double4) + (size_t)warp * EXTRA;
-    double* nutile = reinterpret_cast<double*>(xb);
-    double* cacc = nutile + TILE;
-    uint32_t* queue = reinterpret_cast<uint32_t*>(cacc + TILE);
+    WarpCold w;
+    w.nutile = reinterpret_cast<double*>(xb);
+    w.cacc = reinterpret_cast<double*>(xb) + TILE;
+    w.queue = reinterpret_cast<uint32_t*>(w.cacc + TILE);
+    w.slow_lev = a.slow ? a.slow + (size_t)lev * a.nl : nullptr;
+    w.cut = a.cut; w.B1 = lp.B1; w.B2 = lp.B2; w.lane = lane;
 
     if (lane == 0) {
         for (int s = 0; s < LS_STAGES; s++) mbar_init(&full_bar[warp][s], 1);
@@ -325,12 +441,14 @@ __global__ void __launch_bounds__(LS_THREADS, 2) line_sum_kernel(LineSumArgs a)
     if (ilo >= ihi) { ilo = whi; ihi = whi; }        // cut-off window narrower than the tile: every line is an edge line
     ilo = min(max(ilo, wlo), whi);
     ihi = min(max(ihi, ilo), whi);
+    // edge lines are normally ~cut-off away from every point, i.e. far wing; only when the near-centre range
+    // reaches into the edge classes (tiny cut-offs, very coarse grids) do they need the per-evaluation region test
+    w.edge_is_far = (SHAPE == CS_LORENTZ) || (SHAPE == CS_VOIGT && nlo >= ilo && nhi <= ihi && ilo < ihi);
     if (SHAPE == CS_LORENTZ) { nlo = ilo; nhi = ilo; }   // no near-centre branch
     nlo = min(max(nlo, ilo), ihi);
     nhi = min(max(nhi, nlo), ihi);
     const int nchunk = (int)((whi - wlo + LS_CHUNK - 1) / LS_CHUNK);
     const double4* rec_lev = a.rec + (size_t)lev * a.nl;
-    const double4* slow_lev = a.slow ? a.slow + (size_t)lev * a.nl : nullptr;
 
     auto issue = [&](int c) {   // lane 0 only
         int s = c % LS_STAGES;
@@ -348,16 +466,11 @@ __global__ void __launch_bounds__(LS_THREADS, 2) line_sum_kernel(LineSumArgs a)
         int64_t i = tile0 + 32 * r + lane;
         nup[r] = a.nu[i < a.nnu ? i : (a.nnu - 1)];
         acc[r] = 0.0;
-        nutile[32 * r + lane] = nup[r];
-        cacc[32 * r + lane] = 0.0;
+        const_cast<double*>(w.nutile)[32 * r + lane] = nup[r];
+        w.cacc[32 * r + lane] = 0.0;
     }
     __syncwarp();
-    const double B1 = lp.B1, B2 = lp.B2;
-    int qn = 0;   // entries in the queue (warp-uniform)
-    // edge lines are normally ~cut-off away from every point, i.e. far wing; only when the near-centre range
-    // reaches into the edge classes (tiny cut-offs, very coarse grids) do they need the per-evaluation region test
-    const bool edge_is_far = (SHAPE == CS_LORENTZ) || (SHAPE == CS_VOIGT && rg[4] >= ilo && rg[5] <= ihi && ilo < ihi);
-    const unsigned lt_mask = (1u << lane) - 1u;
+    int qn = 0;   // entries in the deferred queue (warp-uniform)
 
     for (int c = 0; c < nchunk; c++) {
         const int s = c % LS_STAGES;
@@ -366,137 +479,64 @@ __global__ void __launch_bounds__(LS_THREADS, 2) line_sum_kernel(LineSumArgs a)
         const int64_t c1 = min(c0 + (int64_t)LS_CHUNK, whi);
         mbar_wait(&full_bar[warp][s], ph);
         const double4* st = ring + (size_t)s * LS_CHUNK;
-        auto seg = [&](int64_t s0, int64_t s1, int& x0, int& x1) {   // chunk-local part of a class
-            x0 = (int)(max(c0, s0) - c0);
-            x1 = (int)(min(c1, s1) - c0);
-        };
-        // general-routine evaluations deferred by the near loop: one dense pass with all lanes busy
-        auto flush = [&]() {
-            for (int e = lane; e < qn; e += 32) {
-                uint32_t en = queue[e];
-                int j = (int)(en >> 8), p = (int)(en & 255u);
-                double4 rc = st[j];
-                atomicAdd(&cacc[p], voigt_near(slow_lev, c0 + j, nutile[p] - rc.x, 1.0));
-            }
-            __syncwarp();
-            qn = 0;
-        };
-        // edge lines: exact inclusive per-point predicate (line_shapes.jl:10)
-        auto edge = [&](int e0, int e1) {
-            int j = e0;
-            if ((SHAPE == CS_VOIGT || SHAPE == CS_LORENTZ) && edge_is_far) {
-                // far-wing pairs with the predicate folded into the numerators; a 32-point slice that is outside
-                // both windows is skipped warp-wide
-                for (; j + 1 < e1; j += 2) {
-                    double4 ra = st[j], rb = st[j + 1];
+        // chunk-local boundaries of the five classes: [0,xa) edge | [xa,xb) far | [xb,xc) near | [xc,xd) far | [xd,n) edge
+        const int n = (int)(c1 - c0);
+        const int xa = (int)(min(max(ilo, c0), c1) - c0), xb_ = (int)(min(max(nlo, c0), c1) - c0);
+        const int xc = (int)(min(max(nhi, c0), c1) - c0), xd = (int)(min(max(ihi, c0), c1) - c0);
+        if (xa > 0) cold_edge<SHAPE, R>(w, st, c0, 0, xa);
+#pragma unroll 1
+        for (int pass = 0; pass < 2; pass++) {
+            // far lines: inside the cut-off for every point and safely in the far wing -> no test of any kind
+            int j = pass ? xc : xa;
+            const int f1 = pass ? xd : xb_;
+            if (SHAPE != CS_DOPPLER) {      // Doppler: exp(-(dnu/alpha)^2) underflows to exactly 0 out here
+                if (SHAPE == CS_VOIGT || SHAPE == CS_LORENTZ) {
+#if CS_LS_QUAD
+                    // four lines per reciprocal: n1/d1 + n2/d2 = (n1 d2 + n2 d1)/(d1 d2), twice -> 5.75 FP64 ops/eval
+                    for (; j + 3 < f1; j += 4) {
+                        double4 ra = st[j], rb = st[j + 1], rc = st[j + 2], rd = st[j + 3];
 #pragma unroll
-                    for (int r = 0; r < R; r++) {
-                        double da = nup[r] - ra.x, db = nup[r] - rb.x;
-                        bool ia = !(fabs(da) > cut), ib = !(fabs(db) > cut);
-                        if (!__any_sync(0xffffffffu, ia | ib)) continue;
-                        double qa = fma(da, da, ra.y), qb = fma(db, db, rb.y);
-                        double num = (ia ? ra.z : 0.0) * qb;
-                        num = fma(ib ? rb.z : 0.0, qa, num);
-                        acc[r] = fma(num, cs_rcp(qa * qb), acc[r]);
+                        for (int r = 0; r < R; r++) {
+                            double da = nup[r] - ra.x, db = nup[r] - rb.x, dc = nup[r] - rc.x, dd = nup[r] - rd.x;
+                            double qa = fma(da, da, ra.y), qb = fma(db, db, rb.y);
+                            double qc = fma(dc, dc, rc.y), qd = fma(dd, dd, rd.y);
+                            double n1 = fma(rb.z, qa, ra.z * qb), d1 = qa * qb;
+                            double n2 = fma(rd.z, qc, rc.z * qd), d2 = qc * qd;
+                            double num = fma(n2, d1, n1 * d2);
+                            acc[r] = fma(num, cs_rcp(d1 * d2), acc[r]);
+                        }
+                    }
+#endif
+                    for (; j + 1 < f1; j += 2) {
+                        double4 ra = st[j], rb = st[j + 1];
+#pragma unroll
+                        for (int r = 0; r < R; r++) {
+                            double da = nup[r] - ra.x, db = nup[r] - rb.x;
+                            double qa = fma(da, da, ra.y), qb = fma(db, db, rb.y);
+                            double num = ra.z * qb;
+                            num = fma(rb.z, qa, num);
+                            acc[r] = fma(num, cs_rcp(qa * qb), acc[r]);
+                        }
                     }
                 }
-                for (; j < e1; j++) {
+                for (; j < f1; j++) {
                     double4 rc = st[j];
 #pragma unroll
                     for (int r = 0; r < R; r++) {
                         double dnu = nup[r] - rc.x;
-                        bool in = !(fabs(dnu) > cut);
-                        acc[r] = fma(in ? rc.z : 0.0, cs_rcp(fma(dnu, dnu, rc.y)), acc[r]);
-                    }
-                }
-                return;
-            }
-            for (; j < e1; j++) {
-                double4 rc = st[j];
-#pragma unroll
-                for (int r = 0; r < R; r++) {
-                    double dnu = nup[r] - rc.x;
-                    if (!(fabs(dnu) > cut)) acc[r] += eval_checked<SHAPE>(rc, dnu, slow_lev, c0 + j, B1, B2);
-                }
-            }
-        };
-        // far lines: inside the cut-off for every point and safely in the far wing -> no test of any kind
-        auto far = [&](int f0, int f1) {
-            if (SHAPE == CS_DOPPLER) return;       // exp(-(dnu/alpha)^2) underflows to exactly 0 out here
-            int j = f0;
-            if (SHAPE == CS_VOIGT || SHAPE == CS_LORENTZ) {
-#if CS_LS_QUAD
-                // four lines per reciprocal: (n1/d1 + n2/d2) = (n1 d2 + n2 d1)/(d1 d2) applied twice -> 5.75 FP64 ops/eval
-                for (; j + 3 < f1; j += 4) {
-                    double4 ra = st[j], rb = st[j + 1], rc = st[j + 2], rd = st[j + 3];
-#pragma unroll
-                    for (int r = 0; r < R; r++) {
-                        double da = nup[r] - ra.x, db = nup[r] - rb.x, dc = nup[r] - rc.x, dd = nup[r] - rd.x;
-                        double qa = fma(da, da, ra.y), qb = fma(db, db, rb.y);
-                        double qc = fma(dc, dc, rc.y), qd = fma(dd, dd, rd.y);
-                        double n1 = fma(rb.z, qa, ra.z * qb), d1 = qa * qb;
-                        double n2 = fma(rd.z, qc, rc.z * qd), d2 = qc * qd;
-                        double num = fma(n2, d1, n1 * d2);
-                        acc[r] = fma(num, cs_rcp(d1 * d2), acc[r]);
-                    }
-                }
-#endif
-                for (; j + 1 < f1; j += 2) {
-                    double4 ra = st[j], rb = st[j + 1];
-#pragma unroll
-                    for (int r = 0; r < R; r++) {
-                        double da = nup[r] - ra.x, db = nup[r] - rb.x;
-                        double qa = fma(da, da, ra.y), qb = fma(db, db, rb.y);
-                        double num = ra.z * qb;
-                        num = fma(rb.z, qa, num);
-                        acc[r] = fma(num, cs_rcp(qa * qb), acc[r]);
-                    }
-                }
-            }
-            for (; j < f1; j++) {
-                double4 rc = st[j];
-#pragma unroll
-                for (int r = 0; r < R; r++) {
-                    double dnu = nup[r] - rc.x;
-                    if (SHAPE == CS_PHCO2) {
-                        double ge = chi_phco2(fabs(dnu), B1, B2) * rc.y;
-                        acc[r] = fma(rc.z * ge, cs_rcp(fma(dnu, dnu, ge * ge)), acc[r]);
-                    } else {
-                        acc[r] = fma(rc.z, cs_rcp(fma(dnu, dnu, rc.y)), acc[r]);
-                    }
-                }
-            }
-        };
-        // near lines: inside the cut-off for every point, Faddeyeva region decided per evaluation
-        auto near = [&](int n0, int n1) {
-            for (int j = n0; j < n1; j++) {
-                double4 rc = st[j];
-                if (SHAPE == CS_VOIGT) {
-                    if (qn > LS_QCAP - TILE) flush();
-#pragma unroll
-                    for (int r = 0; r < R; r++) {
-                        bool need;
-                        double v = voigt_12(rc, nup[r] - rc.x, need);
-                        acc[r] += need ? 0.0 : v;
-                        unsigned m = __ballot_sync(0xffffffffu, need);
-                        if (m) {   // defer: compact (line, point) into the queue, order fixed by (line, slice, lane)
-                            if (need) queue[qn + __popc(m & lt_mask)] = ((uint32_t)j << 8) | (uint32_t)(32 * r + lane);
-                            qn += __popc(m);
+                        if (SHAPE == CS_PHCO2) {
+                            double ge = chi_phco2(fabs(dnu), w.B1, w.B2) * rc.y;
+                            acc[r] = fma(rc.z * ge, cs_rcp(fma(dnu, dnu, ge * ge)), acc[r]);
+                        } else {
+                            acc[r] = fma(rc.z, cs_rcp(fma(dnu, dnu, rc.y)), acc[r]);
                         }
                     }
-                } else {
-#pragma unroll
-                    for (int r = 0; r < R; r++) acc[r] += eval_checked<SHAPE>(rc, nup[r] - rc.x, slow_lev, c0 + j, B1, B2);
                 }
             }
-        };
-        int x0, x1;
-        seg(wlo, ilo, x0, x1); edge(x0, x1);
-        seg(ilo, nlo, x0, x1); far(x0, x1);
-        seg(nlo, nhi, x0, x1); near(x0, x1);
-        seg(nhi, ihi, x0, x1); far(x0, x1);
-        seg(ihi, whi, x0, x1); edge(x0, x1);
-        if (SHAPE == CS_VOIGT && qn > 0) { __syncwarp(); flush(); }
+            if (pass == 0 && xb_ < xc) qn = cold_near<SHAPE, R>(w, st, c0, xb_, xc, qn);
+        }
+        if (xd < n) cold_edge<SHAPE, R>(w, st, c0, xd, n);
+        if (SHAPE == CS_VOIGT && qn > 0) { cold_flush<SHAPE, R>(w, st, c0, qn); qn = 0; }
         // stage s is free again: refill it with chunk c + LS_STAGES
         __syncwarp();
         if (lane == 0 && c + LS_STAGES < nchunk) {
@@ -504,12 +544,13 @@ __global__ void __launch_bounds__(LS_THREADS, 2) line_sum_kernel(LineSumArgs a)
             issue(c + LS_STAGES);
         }
     }
+    __syncwarp();
 #pragma unroll
     for (int r = 0; r < R; r++) {
         int64_t i = tile0 + 32 * r + lane;
         if (i < a.nnu) {
             size_t o = (size_t)lev * a.nnu + i;
-            double v = lp.scale * (SHAPE == CS_VOIGT ? acc[r] + cacc[32 * r + lane] : acc[r]);
+            double v = lp.scale * (acc[r] + w.cacc[32 * r + lane]);
             a.out[o] = a.accumulate ? a.out[o] + v : v;
         }
     }
