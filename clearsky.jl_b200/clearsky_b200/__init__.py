@@ -18,4 +18,5 @@ from .line_shapes import (PHCO2, PHCO2_b200_inplace, DeviceLines, device_lines, 
 from .molparam import MOLPARAM, TMAX, TMIN
 from .par import SpectralLines, readpar
 from .quadrature import lobattonodes, streamnodes
+from .rcm import RCM
 from .util import AtmosphericProfile, chebygrid, pressuregrid, trapz

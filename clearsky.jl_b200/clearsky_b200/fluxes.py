@@ -37,22 +37,30 @@ def formprofile(P, x):
     return AtmosphericProfile(P, x)
 
 
+def _vec(f, *args):
+    """evaluate a profile callable on arrays when it supports them, element by element otherwise"""
+    shape = np.shape(args[0])
+    try:
+        out = np.asarray(f(*args), dtype=np.float64)
+        if out.shape == shape:
+            return out
+        if out.shape == ():
+            return np.full(shape, float(out))
+    except Exception:
+        pass
+    flat = [np.ravel(a) for a in args]
+    return np.array([float(f(*xs)) for xs in zip(*flat)], dtype=np.float64).reshape(shape)
+
+
 def lobattoevaluations(P, fT, fμ, nlobatto):
     """core/discretized.jl:11-30 -> T, μ [nlobatto, np-1] (returned as C arrays [np-1, nlobatto], i.e. the same
     memory order as Julia's column-major [nlobatto, np-1]) plus the node pressures"""
     x, _ = lobattonodes(nlobatto)
-    npl = len(P)
-    T = np.empty((npl - 1, nlobatto))
-    μ = np.empty((npl - 1, nlobatto))
-    Pn = np.empty((npl - 1, nlobatto))
-    for j in range(npl - 1):
-        ΔP = P[j + 1] - P[j]
-        for i in range(nlobatto):
-            Pi = P[j] + ΔP * x[i]
-            Ti = float(fT(Pi))
-            T[j, i] = Ti
-            μ[j, i] = float(fμ(Ti, Pi))
-            Pn[j, i] = Pi
+    P = np.asarray(P, dtype=np.float64)
+    ΔP = P[1:] - P[:-1]
+    Pn = P[:-1, None] + ΔP[:, None] * x[None, :]
+    T = _vec(fT, Pn)
+    μ = _vec(fμ, T, Pn)
     return T, μ, Pn
 
 
@@ -79,7 +87,13 @@ def _prepare(P, T, μ, absorbers, nlobatto):
     fT, fμ = formprofile(P, T), formprofile(P, μ)
     Tl, μl, Pn = lobattoevaluations(P, fT, fμ, nlobatto)
     Tn, Pq = _unique_nodes(P, Tl, Pn, nlobatto)
-    ws = SigmaWorkspace(ν, len(Tn))
+    # one device workspace per (absorber, node count), reused across calls (the RCM loop calls this every step)
+    cache = A.__dict__.setdefault("_ws_cache", {})
+    ws = cache.get(len(Tn))
+    if ws is None:
+        ws = cache[len(Tn)] = SigmaWorkspace(ν, len(Tn))
+    else:
+        ws.zero()
     A.sigma_nodes(ws, Tn, Pq)
     return A, ν, nν, P, fT, μl, ws
 
@@ -122,7 +136,7 @@ def monochromaticfluxes_(Mup, Mdn, τ, core, P, g, T, μ, fS, fa, *absorbers, θ
     nstream, nlobatto = core.nstream, core.nlobatto
     assert np.all(np.diff(P) >= 0), "pressure coordinates must be in ascending order (sorted)"
     A, ν, nν, P, fT, μl, ws = _prepare(P, T, μ, absorbers, nlobatto)
-    Tlev = f64(np.array([float(fT(p)) for p in P]))
+    Tlev = f64(_vec(fT, P))
     A.checkpressures(P[-1], P[0])
     checkstreams(nstream)
     checkazimuth(θs)

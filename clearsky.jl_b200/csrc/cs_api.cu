@@ -296,11 +296,25 @@ extern "C" int32_t cs_sigma_create(cs_ctx* ctx, int64_t nnu, const double* nu, i
     s->h_nu.assign(nu, nu + nnu);
     s->nu = nullptr;
     s->sig = nullptr;
+    s->w = nullptr;
     int32_t rc = upload(&s->nu, nu, (size_t)nnu, ctx->stream);
     if (rc) { delete s; return rc; }
+    {
+        // w_j = (dnu_{j-1} + dnu_j)/2: trapz(nu, y) = sum_j w_j y_j with every interval counted once
+        std::vector<double> hw((size_t)nnu);
+        for (int64_t j = 0; j < nnu; j++) {
+            double dl = j > 0 ? nu[j] - nu[j - 1] : 0.0;
+            double dr = j + 1 < nnu ? nu[j + 1] - nu[j] : 0.0;
+            hw[(size_t)j] = (dl + dr) / 2;
+        }
+        rc = upload(&s->w, hw.data(), (size_t)nnu, ctx->stream);
+        if (rc) { cs_free(s->nu, ctx->stream); delete s; return rc; }
+        CS_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
     cudaError_t e = cs_malloc((void**)&s->sig, sizeof(double) * (size_t)nnu * nnode, ctx->stream);
     if (e != cudaSuccess) {
         cs_free(s->nu, ctx->stream);
+        cs_free(s->w, ctx->stream);
         delete s;
         cs_set_error("cudaMalloc(sigma workspace %zu bytes): %s", sizeof(double) * (size_t)nnu * nnode, cudaGetErrorString(e));
         return CS_ERR_NOMEM;
@@ -325,6 +339,7 @@ extern "C" int32_t cs_sigma_free(cs_sigma* s)
     if (!s) return CS_OK;
     cudaSetDevice(s->ctx->device);
     if (s->own_nu) cs_free(s->nu, s->ctx->stream);
+    cs_free(s->w, s->ctx->stream);
     cs_free(s->sig, s->ctx->stream);
     delete s;
     return CS_OK;

@@ -118,6 +118,7 @@ struct cs_sigma {
     int64_t nnu, nnode;
     double* nu;      // device [nnu]
     double* sig;     // device [nnode][nnu], nu fastest
+    double* w;       // device [nnu] trapezoid weights of nu (util.jl:26-33 rewritten per point)
     std::vector<double> h_nu;
     bool own_nu;
 };

@@ -174,14 +174,17 @@ __global__ void __launch_bounds__(RT_THREADS) rt_kernel(RtArgs a)
     }
 }
 
-// K7 second stage: fixed-order sum over CTAs; F[0..np) = up, F[np..2np) = down
-__global__ void flux_reduce_kernel(const double* part, int nblocks, int n2, double* F)
+// K7 second stage: fixed-order sum over CTAs; F[0..np) = up, F[np..2np) = down.  One warp per output: lanes
+// stride over the CTAs in a fixed pattern and finish with a fixed shuffle tree -> run-to-run bit-stable.
+__global__ void __launch_bounds__(128) flux_reduce_kernel(const double* __restrict__ part, int nblocks, int n2, double* F)
 {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int t = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
     if (t >= n2) return;
     double s = 0.0;
-    for (int b = 0; b < nblocks; b++) s += part[(size_t)b * n2 + t];
-    F[t] = s;
+    for (int b = lane; b < nblocks; b += 32) s += part[(size_t)b * n2 + t];
+    s = warp_sum(s);
+    if (lane == 0) F[t] = s;
 }
 
 // total slant optical depth, d-depth (core/discretized.jl:92-134): no floor, tau += tau_i*m per layer
@@ -267,19 +270,8 @@ int32_t fluxes_impl(cs_sigma* s, int64_t np, const double* P, int32_t nlob, cons
     small.insert(small.end(), m, m + nstream);
     small.insert(small.end(), W, W + nstream);
 
-    // trapezoid weights (util.jl:26-33 rewritten per point): w_j = (dnu_{j-1} + dnu_j)/2
-    std::vector<double> hw;
+    // trapezoid weights: the workspace's own (computed at creation) unless the caller supplies global ones
     const double* wsrc = nu_weights;
-    if (!wsrc) {
-        hw.resize((size_t)nnu);
-        const double* x = s->h_nu.data();
-        for (int64_t j = 0; j < nnu; j++) {
-            double dl = j > 0 ? x[j] - x[j - 1] : 0.0;
-            double dr = j + 1 < nnu ? x[j + 1] - x[j] : 0.0;
-            hw[(size_t)j] = (dl + dr) / 2;
-        }
-        wsrc = hw.data();
-    }
     const int nblocks = (int)((nnu + RT_THREADS - 1) / RT_THREADS);
     size_t off_small = 0;
     size_t off_w = ((small.size() * sizeof(double) + 255) / 256) * 256;
@@ -290,7 +282,7 @@ int32_t fluxes_impl(cs_sigma* s, int64_t np, const double* P, int32_t nlob, cons
     CS_TRY(ctx->s_misc.reserve(total));
     char* base = ctx->s_misc.as<char>();
     CS_CUDA(cudaMemcpyAsync(base + off_small, small.data(), small.size() * sizeof(double), cudaMemcpyHostToDevice, st));
-    CS_CUDA(cudaMemcpyAsync(base + off_w, wsrc, sizeof(double) * (size_t)nnu, cudaMemcpyHostToDevice, st));
+    if (wsrc) CS_CUDA(cudaMemcpyAsync(base + off_w, wsrc, sizeof(double) * (size_t)nnu, cudaMemcpyHostToDevice, st));
     if (fS) CS_CUDA(cudaMemcpyAsync(base + off_fS, fS, sizeof(double) * (size_t)nnu, cudaMemcpyHostToDevice, st));
     if (fa) CS_CUDA(cudaMemcpyAsync(base + off_fa, fa, sizeof(double) * (size_t)nnu, cudaMemcpyHostToDevice, st));
     CS_TRY(ctx->s_tau.reserve(sizeof(double) * (size_t)L * nnu));
@@ -301,7 +293,7 @@ int32_t fluxes_impl(cs_sigma* s, int64_t np, const double* P, int32_t nlob, cons
     if (Mdn) CS_TRY(ctx->s_out2.reserve(sizeof(double) * (size_t)np * nnu));
 
     RtArgs a;
-    a.sig = s->sig; a.nu = s->nu; a.w = (const double*)(base + off_w);
+    a.sig = s->sig; a.nu = s->nu; a.w = wsrc ? (const double*)(base + off_w) : s->w;
     a.fS = fS ? (const double*)(base + off_fS) : nullptr;
     a.fa = fa ? (const double*)(base + off_fa) : nullptr;
     a.small = (const double*)(base + off_small);
@@ -329,7 +321,7 @@ int32_t fluxes_impl(cs_sigma* s, int64_t np, const double* P, int32_t nlob, cons
     }
     CS_CUDA(cudaEventRecord(ctx->ev1, st));
     double* dF = d_F ? d_F : (double*)(base + off_F);
-    flux_reduce_kernel<<<(2 * (int)np + 127) / 128, 128, 0, st>>>(a.part, nblocks, 2 * (int)np, dF);
+    flux_reduce_kernel<<<(2 * (int)np + 3) / 4, 128, 0, st>>>(a.part, nblocks, 2 * (int)np, dF);
     CS_CUDA(cudaGetLastError());
     cs_count_launch(ctx);
     CS_CUDA(cudaEventRecord(ctx->ev2, st));

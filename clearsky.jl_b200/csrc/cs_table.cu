@@ -89,29 +89,40 @@ __global__ void __launch_bounds__(128) cheb_pass_kernel(const double* in, double
 }
 
 // ---- K4: table evaluation at a block of LB levels.  basis[l][k] = T_i(xi_T(l)) * T_j(xi_P(l)).
+// Each thread owns one wavenumber and LB level accumulators in registers; the coefficient axis is streamed in
+// chunks of KC with the matching basis slab in shared memory (small footprint -> full occupancy).  Every
+// coefficient is read ceil(nlev/LB) times, so LB = 32 keeps a 101-level sweep of a 50 x 50 table near its FP64
+// floor instead of its HBM floor.
 // mode 0: out[l][nu] = exp(.)           (rawsigma, gases.jl:85,256)
 // mode 1: out[l][nu] += C[l]*exp(.)     (Gas functor, gases.jl:278)
+constexpr int TE_KC = 64;
 template <int LB>
-__global__ void __launch_bounds__(128) table_eval_kernel(const double* coef, int64_t nnu, int nk, const double* basis,
-                                                         const double* C, int nlev, double* out, int mode)
+__global__ void __launch_bounds__(128) table_eval_kernel(const double* __restrict__ coef, int64_t nnu, int nk,
+                                                         const double* __restrict__ basis, const double* __restrict__ C,
+                                                         int nlev, double* out, int mode)
 {
-    extern __shared__ double sb[];   // [nk][LB]
+    __shared__ __align__(16) double sb[TE_KC * LB];   // [k][l]
     const int l0 = blockIdx.y * LB;
-    for (int t = threadIdx.x; t < nk * LB; t += blockDim.x) {
-        int k = t / LB, l = t % LB;
-        sb[t] = (l0 + l < nlev) ? basis[(size_t)(l0 + l) * nk + k] : 0.0;
-    }
-    __syncthreads();
-    int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= nnu) return;
+    const int64_t vraw = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t v = vraw < nnu ? vraw : nnu - 1;
     double acc[LB];
 #pragma unroll
     for (int l = 0; l < LB; l++) acc[l] = 0.0;
-    for (int k = 0; k < nk; k++) {
-        double a = coef[(size_t)k * nnu + v];
+    for (int k0 = 0; k0 < nk; k0 += TE_KC) {
+        const int kc = min(TE_KC, nk - k0);
+        __syncthreads();
+        for (int t = threadIdx.x; t < kc * LB; t += blockDim.x) {
+            int k = t / LB, l = t % LB;
+            sb[t] = (l0 + l < nlev) ? basis[(size_t)(l0 + l) * nk + k0 + k] : 0.0;
+        }
+        __syncthreads();
+        for (int k = 0; k < kc; k++) {
+            double a = coef[(size_t)(k0 + k) * nnu + v];
 #pragma unroll
-        for (int l = 0; l < LB; l++) acc[l] = fma(a, sb[k * LB + l], acc[l]);
+            for (int l = 0; l < LB; l++) acc[l] = fma(a, sb[k * LB + l], acc[l]);
+        }
     }
+    if (vraw >= nnu) return;
 #pragma unroll
     for (int l = 0; l < LB; l++) {
         if (l0 + l < nlev) {
@@ -340,23 +351,14 @@ int32_t eval_table(cs_table* tb, int64_t nlev, const double* T, const double* P,
     CS_CUDA(cudaMemcpyAsync(base, basis.data(), basis.size() * sizeof(double), cudaMemcpyHostToDevice, st));
     if (C) CS_CUDA(cudaMemcpyAsync(base + offC, C, sizeof(double) * (size_t)nlev, cudaMemcpyHostToDevice, st));
     CS_CUDA(cudaEventRecord(ctx->ev0, st));
-    // levels per CTA limited by shared memory (nk*LB doubles)
-    int LB = 8;
-    while (LB > 1 && (size_t)nk * LB * sizeof(double) > 200 * 1024) LB >>= 1;
-    size_t smem = (size_t)nk * LB * sizeof(double);
+    const int LB = nlev > 12 ? 32 : 8;
     dim3 grid((unsigned)((tb->nnu + 127) / 128), (unsigned)((nlev + LB - 1) / LB));
-#define CS_LAUNCH_EVAL(LBV)                                                                                         \
-    do {                                                                                                            \
-        if (smem > 48 * 1024)                                                                                       \
-            CS_CUDA(cudaFuncSetAttribute(table_eval_kernel<LBV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        table_eval_kernel<LBV><<<grid, 128, smem, st>>>(tb->coef, tb->nnu, nk, (const double*)base,                \
-                                                        (const double*)(base + offC), (int)nlev, d_out, mode);      \
-    } while (0)
-    if (LB == 8) CS_LAUNCH_EVAL(8);
-    else if (LB == 4) CS_LAUNCH_EVAL(4);
-    else if (LB == 2) CS_LAUNCH_EVAL(2);
-    else CS_LAUNCH_EVAL(1);
-#undef CS_LAUNCH_EVAL
+    if (LB == 32)
+        table_eval_kernel<32><<<grid, 128, 0, st>>>(tb->coef, tb->nnu, nk, (const double*)base, (const double*)(base + offC),
+                                                    (int)nlev, d_out, mode);
+    else
+        table_eval_kernel<8><<<grid, 128, 0, st>>>(tb->coef, tb->nnu, nk, (const double*)base, (const double*)(base + offC),
+                                                   (int)nlev, d_out, mode);
     CS_CUDA(cudaGetLastError());
     cs_count_launch(ctx);
     CS_CUDA(cudaEventRecord(ctx->ev1, st));

@@ -320,3 +320,44 @@ def test_flux_errors(cs, co2):
         cs.fluxes(P, 9.8, Γ, 0.029, None, None, gas, θs=2.0)       # checkazimuth (fluxes.jl:4-6)
     with pytest.raises(AssertionError):
         cs.Gas(co2, 1.5, ν, cs.AtmosphericDomain((150, 300), 4, (10, 1e5), 4))   # gases.jl:124
+
+
+def test_rcm_heating_and_step(cs, orc, co2):
+    """RCM heating!/step! (radiative_convective.jl:109-151) on the GPU vs the same host arithmetic driven by the
+    oracle's fluxes: AcceleratedAbsorber frozen at the initial edge temperatures, radmul = 2"""
+    ν = np.linspace(50.0, 2000.0, 500)
+    Pe = cs.pressuregrid(50.0, 1e5, 11)
+    Γ = cs.DryAdiabat(288.0, 1e5, 1040.0, 0.029, Ptropo=1.5e4)
+    Te = Γ(Pe)
+    Ω = cs.AtmosphericDomain((120, 320), 8, (20, 1.1e5), 12)
+    gas = cs.Gas(co2, 400e-6, ν, Ω)
+    fS = lambda x: 0.3 * np.exp(-((x - 1200.0) / 500.0) ** 2)
+    rcm = cs.RCM(Pe, Te, 9.8, 0.029, fS, 0.25, 1040.0, 1e7, gas, radmul=2)
+    assert len(rcm.Pr) == 21 and np.all(np.diff(rcm.Pr) > 0)
+    # oracle-driven twin
+    blk, _ = orc.bake(orc.VOIGT, co2, ν, Ω.T, Ω.P, np.full((Ω.nP, Ω.nT), 400e-6), 25.0, nthreads=0)
+    σe = orc.gas_nodes(orc.table_fit(blk), Ω.T, Ω.P, Te, Pe, np.full(len(Pe), 400e-6))
+    lnσ = np.maximum(np.log(σe), np.log(np.finfo(float).tiny))
+    σr = orc.accel_nodes(np.log(Pe), lnσ, rcm.Pr)
+    m, W = cs.streamnodes(5)
+    x, w = cs.lobattonodes(2)
+    P, T = rcm.P.copy(), rcm.T.copy()
+
+    def heating(T):
+        fT = cs.AtmosphericProfile(P, T)
+        Tlev = fT(rcm.Pr)
+        f = orc.fluxes(ν, rcm.Pr, 2, w, np.full((len(rcm.Pr) - 1, 2), 0.029), Tlev, σr, 9.8, fS(ν), np.full(len(ν), 0.25),
+                       0.841, 5, m, W, nthreads=0, full=False)
+        R = -cs.AtmosphericProfile(rcm.Pr, f["Fnet"])(Pe)
+        H = np.empty(len(Pe))
+        H[:-1] = (9.8 / 1040.0) * (R[:-1] - R[1:]) / (Pe[1:] - Pe[:-1])
+        H[-1] = R[-1] / 1e7
+        return H
+
+    for _ in range(3):
+        Href = heating(T)
+        rcm.step_(3600.0)
+        T = T + 3600.0 * Href
+        scale = np.max(np.abs(Href))
+        assert np.max(np.abs(rcm.H - Href)) < 1e-8 * scale
+        assert np.max(np.abs(rcm.T - T)) < 1e-9 * np.max(T)
