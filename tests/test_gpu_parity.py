@@ -361,3 +361,77 @@ def test_rcm_heating_and_step(cs, orc, co2):
         scale = np.max(np.abs(Href))
         assert np.max(np.abs(rcm.H - Href)) < 1e-8 * scale
         assert np.max(np.abs(rcm.T - T)) < 1e-9 * np.max(T)
+
+
+def test_full_size_properties_c2(cs):
+    """BASELINE configs[1] at FULL size (500k lines, 300k ν, 101 levels): size-independent properties.
+    (1) additivity over a partition of the line list, (2) ν-sharding invariance of the spectrally integrated fluxes
+    with global trapezoid weights (the multi-GPU decomposition), (3) OLR within physical bounds."""
+    import bench
+    from clearsky_b200._lib import check, f64, lib, ptr
+    wl = bench.make_workload(cs, "c2")
+    ν, P, T = wl["ν"], wl["P"], wl["T"]
+    nlev = len(P)
+    (co2, Cc), (h2o, Ch) = wl["gases"]
+    ws = cs.SigmaWorkspace(ν, nlev)
+    Tn, Pn = f64(T), f64(P)
+
+    def add(sl, C):
+        dl = cs.DeviceLines(sl)
+        check(lib().cs_sigma_add_lines(ws.h, dl.h, 2, ptr(Tn), ptr(Pn), ptr(f64(np.full(nlev, C))), 25.0))
+
+    def sub(sl, mask):
+        return cs.SpectralLines(sl.name, sl.formula, int(mask.sum()), sl.M, sl.I[mask], sl.μ[mask], sl.A[mask], sl.ν[mask],
+                                sl.S[mask], sl.γa[mask], sl.γs[mask], sl.Epp[mask], sl.na[mask])
+
+    add(co2, Cc)
+    full = ws.read()
+    ws.zero()
+    m = np.zeros(co2.N, dtype=bool)
+    m[::3] = True
+    add(sub(co2, m), Cc)
+    add(sub(co2, ~m), Cc)
+    part = ws.read()
+    assert relerr(part, full, 1e-300) < 1e-12
+    del part
+    # full Σ and fluxes
+    add(h2o, Ch)
+    m_, W = cs.streamnodes(5)
+    x, w = cs.lobattonodes(2)
+    μn = f64(np.full((nlev - 1, 2), 0.029))
+    Fu, Fd, Fn = np.empty(nlev), np.empty(nlev), np.empty(nlev)
+    check(lib().cs_fluxes(ws.h, nlev, ptr(Pn), 2, ptr(f64(w)), ptr(μn), ptr(Tn), 9.8, None, None, 0.841, 5, ptr(f64(m_)),
+                          ptr(f64(W)), None, None, None, None, ptr(Fu), ptr(Fd), ptr(Fn)))
+    σT4 = 5.67037442e-8 * 288.0 ** 4
+    assert 0 < Fu[0] < Fu[-1] < σT4 and np.all(np.diff(Fd) >= -1e-9) and Fd[0] == 0.0
+    # ν-sharded evaluation: 3 contiguous slices balanced by evaluations, global weights, partial sums added
+    σ = ws.read()
+    cnt = bench.per_point_counts(ν, co2.ν, 25.0) + bench.per_point_counts(ν, h2o.ν, 25.0)
+    e = bench.balanced_slices(cnt, 3)
+    wg = bench.trapz_weights(ν)
+    tot = np.zeros(2 * nlev)
+    for a, b in zip(e, e[1:]):
+        wsl = cs.SigmaWorkspace(ν[a:b], nlev)
+        wsl.add_host(np.ascontiguousarray(σ[:, a:b]))
+        fu, fd, fn = np.empty(nlev), np.empty(nlev), np.empty(nlev)
+        check(lib().cs_fluxes(wsl.h, nlev, ptr(Pn), 2, ptr(f64(w)), ptr(μn), ptr(Tn), 9.8, None, None, 0.841, 5,
+                              ptr(f64(m_)), ptr(f64(W)), ptr(f64(wg[a:b])), None, None, None, ptr(fu), ptr(fd), ptr(fn)))
+        tot += np.concatenate([fu, fd])
+    assert relerr(tot[:nlev], Fu) < 1e-12 and relerr(tot[nlev + 1:], Fd[1:]) < 1e-12
+
+
+def test_table_export_import_roundtrip(cs, co2):
+    """cs_table_block -> cs_table_from_block reproduces the table (persistence path)"""
+    import ctypes as C
+    from clearsky_b200._lib import check, f64, lib, ptr
+    ν, P, Γ = c1_problem(cs, nν=400)
+    Ω = cs.AtmosphericDomain((140, 300), 9, (5, 1.1e5), 11)
+    gas = cs.Gas(co2, 400e-6, ν, Ω, keep_block=True)
+    blk = gas.σblock()
+    h = C.c_void_p()
+    check(lib().cs_table_from_block(gas.ctx.h, len(ν), Ω.nT, ptr(f64(Ω.T)), Ω.nP, ptr(f64(Ω.P)), ptr(f64(blk)), C.byref(h)))
+    T = Γ(P)
+    out = np.empty((len(P), len(ν)))
+    check(lib().cs_table_eval(h, len(P), ptr(f64(T)), ptr(f64(P)), ptr(out)))
+    lib().cs_table_free(h)
+    assert relerr(out, gas.rawσ(T, P), 1e-300) < 1e-13
