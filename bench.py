@@ -85,6 +85,14 @@ def per_point_counts(ν, νl, cut):
     return (hi - lo).astype(np.int64)
 
 
+def slice_cost(ν, gases, cut, kappa=5.6e-5):
+    """per-ν cost model for balancing ν slices: evaluations, inflated by the near-centre work that grows with ν
+    (Doppler widths are proportional to ν, so the share of near-centre lines per tile is too).  kappa was calibrated
+    on the measured per-slice kernel times of the 8-way split (profiles/r1_slice_balance.txt)."""
+    counts = sum(per_point_counts(ν, sl.ν, cut) for sl, _ in gases)
+    return counts * (1.0 + kappa * ν)
+
+
 def trapz_weights(ν):
     """per-point weights of trapz(ν, ·) (util.jl:26-33): every interval counted once across ν slices"""
     d = np.diff(ν)
@@ -250,7 +258,7 @@ def run_ours(args):
 
     # ---- ν sharding: contiguous slices balanced by evaluations, global trapezoid weights
     counts = sum(per_point_counts(ν, sl.ν, cut) for sl, _ in wl["gases"])
-    edges = balanced_slices(counts, world)
+    edges = balanced_slices(slice_cost(ν, wl["gases"], cut), world)
     i0, i1 = edges[rank], edges[rank + 1]
     νs = np.ascontiguousarray(ν[i0:i1])
     wts = np.ascontiguousarray(trapz_weights(ν)[i0:i1])

@@ -181,7 +181,8 @@ struct LineSumArgs {
     double* out;            // [nlev][nnu]
     int accumulate;         // 0: out = scale*sigma (surf! overwrites), 1: out += scale*sigma
     int64_t ntiles;
-    const int64_t* ranges;  // [ntiles][6], see tile_ranges_kernel
+    int nr;                 // entries per tile in ranges (6, or LS_NR for PHCO2)
+    const int64_t* ranges;  // [ntiles][nr], see tile_ranges_kernel
 };
 
 // Voigt evaluation of one (line, point) that is not safely in the far wing: decides the region exactly like
@@ -267,14 +268,15 @@ __device__ __forceinline__ double eval_checked(const double4 rc, double dnu, con
 //   [wlo,whi): lines within the cut-off of SOME point of the tile (exact FP64 rule of line_shapes.jl:10)
 //   [ilo,ihi): lines within the cut-off of ALL points (no per-point predicate needed)
 //   [nlo,nhi): lines whose centre is within cn*nul of the tile: the far-wing form may not apply there
+constexpr int LS_NR = 18;   // entries per tile (6 general + 12 PHCO2 chi-class boundaries)
 __global__ void tile_ranges_kernel(const double* __restrict__ nu, int64_t nnu, const double* __restrict__ nul,
-                                   int64_t nl, double cut, double cn, int tile_pts, int64_t ntiles,
+                                   int64_t nl, double cut, double cn, int tile_pts, int64_t ntiles, int nr,
                                    int64_t* __restrict__ ranges)
 {
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= ntiles * 6) return;
-    int64_t tile = t / 6;
-    int k = (int)(t % 6);
+    if (t >= ntiles * nr) return;
+    int64_t tile = t / nr;
+    int k = (int)(t % nr);
     int64_t i0 = tile * tile_pts, i1 = min(i0 + (int64_t)tile_pts, nnu);
     const double tmin = nu[i0], tmax = nu[i1 - 1];
     int64_t v;
@@ -284,7 +286,22 @@ __global__ void tile_ranges_kernel(const double* __restrict__ nu, int64_t nnu, c
     case 2: v = first_false(nul, 0, nl, [=](double x) { return (tmax - x) > cut; }); break;
     case 3: v = first_false(nul, 0, nl, [=](double x) { return !((x - tmin) > cut); }); break;
     case 4: v = first_false(nul, 0, nl, [=](double x) { return x * (1.0 + cn) < tmin; }); break;
-    default: v = first_false(nul, 0, nl, [=](double x) { return !(x * (1.0 - cn) > tmax); }); break;
+    case 5: v = first_false(nul, 0, nl, [=](double x) { return !(x * (1.0 - cn) > tmax); }); break;
+    // PHCO2 chi classes (line_shapes.jl:467-481, strict '<' at 3, 30, 120), decided for ALL points of the tile with
+    // the same FP subtraction chi itself uses.  Lines below the tile: |dnu| = nu_p - x in [tmin - x, tmax - x].
+    case 6: v = first_false(nul, 0, nl, [=](double x) { return (tmin - x) >= 120.0; }); break;      // end of ">=120 for all"
+    case 7: v = first_false(nul, 0, nl, [=](double x) { return !((tmax - x) < 120.0); }); break;    // start of "<120 for all"
+    case 8: v = first_false(nul, 0, nl, [=](double x) { return (tmin - x) >= 30.0; }); break;
+    case 9: v = first_false(nul, 0, nl, [=](double x) { return !((tmax - x) < 30.0); }); break;
+    case 10: v = first_false(nul, 0, nl, [=](double x) { return (tmin - x) >= 3.0; }); break;
+    case 11: v = first_false(nul, 0, nl, [=](double x) { return !((tmax - x) < 3.0); }); break;      // start of "<3 for all"
+    // lines above the tile: |dnu| = x - nu_p in [x - tmax, x - tmin]
+    case 12: v = first_false(nul, 0, nl, [=](double x) { return (x - tmin) < 3.0; }); break;         // end of "<3 for all"
+    case 13: v = first_false(nul, 0, nl, [=](double x) { return !((x - tmax) >= 3.0); }); break;     // start of ">=3 for all"
+    case 14: v = first_false(nul, 0, nl, [=](double x) { return (x - tmin) < 30.0; }); break;
+    case 15: v = first_false(nul, 0, nl, [=](double x) { return !((x - tmax) >= 30.0); }); break;
+    case 16: v = first_false(nul, 0, nl, [=](double x) { return (x - tmin) < 120.0; }); break;
+    default: v = first_false(nul, 0, nl, [=](double x) { return !((x - tmax) >= 120.0); }); break;
     }
     ranges[t] = v;
 }
@@ -293,6 +310,14 @@ __global__ void tile_ranges_kernel(const double* __restrict__ nu, int64_t nnu, c
 // and accumulate into the warp's shared-memory accumulators (each lane only touches its own R slots, except for
 // the deferred pass which uses shared atomics), so that the register allocation and instruction schedule of the
 // hot far-wing loop are not polluted by them.
+// per-warp shared memory behind the ring: nutile[TILE], cacc[TILE], queue[LS_QCAP]; PHCO2 adds the chi tables
+// Etab[6][TILE] (3 classes x 2 sides), the per-chunk line factors Fp[LS_CHUNK] and the 18 segment borders
+template <int SHAPE, int R> __host__ __device__ constexpr size_t ls_extra_bytes()
+{
+    return (size_t)2 * 32 * R * sizeof(double) + LS_QCAP * sizeof(uint32_t) +
+           (SHAPE == CS_PHCO2 ? (size_t)6 * 32 * R * sizeof(double) + LS_CHUNK * sizeof(double) + 18 * sizeof(int64_t) : 0);
+}
+
 struct WarpCold {
     const double* nutile;      // [32*R] wavenumbers of this warp's tile (shared memory)
     double* cacc;              // [32*R] accumulators of the cold paths (shared memory)
@@ -400,6 +425,27 @@ __device__ __noinline__ int cold_near(const WarpCold& w, const double4* st, int6
     return qn;
 }
 
+// PHCO2 lines that straddle a chi-class border for this tile: far-wing form with chi evaluated per point
+template <int R>
+__device__ __noinline__ void cold_phco2_generic(const WarpCold& w, const double4* st, int g0, int g1)
+{
+    const int lane = w.lane;
+    double nup[R], acc[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) { nup[r] = w.nutile[32 * r + lane]; acc[r] = 0.0; }
+    for (int j = g0; j < g1; j++) {
+        double4 rc = st[j];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            double dnu = nup[r] - rc.x;
+            double ge = chi_phco2(fabs(dnu), w.B1, w.B2) * rc.y;
+            acc[r] = fma(rc.z * ge, cs_rcp(fma(dnu, dnu, ge * ge)), acc[r]);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < R; r++) w.cacc[32 * r + lane] += acc[r];
+}
+
 // K2.  Work unit = one warp = (tile of 32*R consecutive wavenumbers, level).  Each warp streams the records of
 // ITS OWN line window through a private shared-memory ring fed by TMA bulk copies (one elected lane issues
 // cp.async.bulk, completion on a per-stage mbarrier), so warps never wait for each other.  The 8 warps of a CTA
@@ -419,7 +465,7 @@ __global__ void __launch_bounds__(LS_THREADS, 16 / LS_WARPS) line_sum_kernel(Lin
     const LevelParams lp = a.lev[lev];
     double4* ring = reinterpret_cast<double4*>(smem_raw) + (size_t)warp * LS_STAGES * LS_CHUNK;
     // per-warp extras behind the rings: copy of the tile's wavenumbers, cold-path accumulators, deferred queue
-    constexpr size_t EXTRA = (size_t)2 * TILE * sizeof(double) + LS_QCAP * sizeof(uint32_t);
+    constexpr size_t EXTRA = ls_extra_bytes<SHAPE, R>();
     unsigned char* xb = smem_raw + (size_t)LS_WARPS * LS_STAGES * LS_CHUNK * sizeof(double4) + (size_t)warp * EXTRA;
     WarpCold w;
     w.nutile = reinterpret_cast<double*>(xb);
@@ -435,7 +481,7 @@ __global__ void __launch_bounds__(LS_THREADS, 16 / LS_WARPS) line_sum_kernel(Lin
     }
     __syncwarp();
 
-    const int64_t* rg = a.ranges + tile * 6;
+    const int64_t* rg = a.ranges + tile * a.nr;
     const int64_t wlo = rg[0], whi = rg[1];
     int64_t ilo = rg[2], ihi = rg[3], nlo = rg[4], nhi = rg[5];
     if (ilo >= ihi) { ilo = whi; ihi = whi; }        // cut-off window narrower than the tile: every line is an edge line
@@ -471,6 +517,38 @@ __global__ void __launch_bounds__(LS_THREADS, 16 / LS_WARPS) line_sum_kernel(Lin
     }
     __syncwarp();
     int qn = 0;   // entries in the deferred queue (warp-uniform)
+    // ---- PHCO2: chi(|dnu|) = exp(-c0 - B (|dnu| - a)) factorises, for a line whose chi class is the same for all
+    // points of the tile, into a per-point factor E = exp(-+B (nu - nu0)) and a per-line factor
+    // F = exp(-c0 - B (+-(nu0 - nul) - a)): one multiplication per evaluation instead of one exp.
+    double* Etab = reinterpret_cast<double*>(w.queue + LS_QCAP);
+    double* Fp = Etab + 6 * TILE;
+    int64_t* bnd = reinterpret_cast<int64_t*>(Fp + LS_CHUNK);
+    const double nu0 = w.nutile[0];
+    if (SHAPE == CS_PHCO2) {
+        const double Bc[3] = {lp.B1, lp.B2, 0.0232};
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            double dx = nup[r] - nu0;
+#pragma unroll
+            for (int cc = 0; cc < 3; cc++) {
+                Etab[(2 * cc + 0) * TILE + 32 * r + lane] = exp(-Bc[cc] * dx);   // line below the point
+                Etab[(2 * cc + 1) * TILE + 32 * r + lane] = exp(Bc[cc] * dx);    // line above the point
+            }
+        }
+        if (lane == 0) {
+            // segment borders in line order:
+            // E | F4- | G | F3- | G | F2- | G | plain | near | plain | G | F2+ | G | F3+ | G | F4+ | E
+            int64_t b[18];
+            b[0] = wlo; b[1] = ilo;
+            for (int k = 0; k < 6; k++) b[2 + k] = min(max(rg[6 + k], ilo), nlo);    // never intrude into the near range
+            b[8] = nlo; b[9] = nhi;
+            for (int k = 0; k < 6; k++) b[10 + k] = max(min(rg[12 + k], ihi), nhi);
+            b[16] = ihi; b[17] = whi;
+            for (int k = 1; k < 18; k++) b[k] = max(b[k], b[k - 1]);
+            for (int k = 0; k < 18; k++) bnd[k] = b[k];
+        }
+        __syncwarp();
+    }
 
     for (int c = 0; c < nchunk; c++) {
         const int s = c % LS_STAGES;
@@ -483,6 +561,87 @@ __global__ void __launch_bounds__(LS_THREADS, 16 / LS_WARPS) line_sum_kernel(Lin
         const int n = (int)(c1 - c0);
         const int xa = (int)(min(max(ilo, c0), c1) - c0), xb_ = (int)(min(max(nlo, c0), c1) - c0);
         const int xc = (int)(min(max(nhi, c0), c1) - c0), xd = (int)(min(max(ihi, c0), c1) - c0);
+        if (SHAPE == CS_PHCO2) {
+            // per-line chi factors of this chunk (lines in one of the six factorised segments)
+            for (int jj = lane; jj < n; jj += 32) {
+                const int64_t jg = c0 + jj;
+                int cls = -1, up = 0;
+                if (jg >= bnd[1] && jg < bnd[2]) cls = 2;
+                else if (jg >= bnd[3] && jg < bnd[4]) cls = 1;
+                else if (jg >= bnd[5] && jg < bnd[6]) cls = 0;
+                else if (jg >= bnd[11] && jg < bnd[12]) { cls = 0; up = 1; }
+                else if (jg >= bnd[13] && jg < bnd[14]) { cls = 1; up = 1; }
+                else if (jg >= bnd[15] && jg < bnd[16]) { cls = 2; up = 1; }
+                if (cls >= 0) {
+                    double4 rc = st[jj];
+                    double B = cls == 0 ? lp.B1 : (cls == 1 ? lp.B2 : 0.0232);
+                    double c0c = cls == 0 ? 0.0 : (cls == 1 ? lp.B1 * 27.0 : lp.B1 * 27.0 + lp.B2 * 90.0);
+                    double aa = cls == 0 ? 3.0 : (cls == 1 ? 30.0 : 120.0);
+                    double d = up ? (rc.x - nu0) - aa : (nu0 - rc.x) - aa;
+                    Fp[jj] = exp(-c0c - B * d) * rc.y;      // chi's line factor times gamma
+                }
+            }
+            __syncwarp();
+#pragma unroll 1
+            for (int sgm = 0; sgm < 17; sgm++) {
+                const int x0 = (int)(min(max(bnd[sgm], c0), c1) - c0), x1 = (int)(min(max(bnd[sgm + 1], c0), c1) - c0);
+                if (x0 >= x1) continue;
+                if (sgm == 0 || sgm == 16) { cold_edge<SHAPE, R>(w, st, c0, x0, x1); continue; }
+                if (sgm == 8) { qn = cold_near<SHAPE, R>(w, st, c0, x0, x1, qn); continue; }
+                if (sgm == 7 || sgm == 9) {
+                    // |dnu| < 3 for every point: chi = 1, plain far-wing Voigt with gamma from the record
+                    int j = x0;
+                    for (; j + 1 < x1; j += 2) {
+                        double4 ra = st[j], rb = st[j + 1];
+                        double ga2 = ra.y * ra.y, gb2 = rb.y * rb.y, ka = ra.z * ra.y, kb = rb.z * rb.y;
+#pragma unroll
+                        for (int r = 0; r < R; r++) {
+                            double da = nup[r] - ra.x, db = nup[r] - rb.x;
+                            double qa = fma(da, da, ga2), qb = fma(db, db, gb2);
+                            acc[r] = fma(fma(kb, qa, ka * qb), cs_rcp(qa * qb), acc[r]);
+                        }
+                    }
+                    for (; j < x1; j++) {
+                        double4 rc = st[j];
+#pragma unroll
+                        for (int r = 0; r < R; r++) {
+                            double dnu = nup[r] - rc.x;
+                            acc[r] = fma(rc.z * rc.y, cs_rcp(fma(dnu, dnu, rc.y * rc.y)), acc[r]);
+                        }
+                    }
+                    continue;
+                }
+                if ((sgm & 1) == 0) { cold_phco2_generic<R>(w, st, x0, x1); continue; }   // straddles a chi border
+                // factorised chi: sgm 1,3,5 = classes 2,1,0 below; 11,13,15 = classes 0,1,2 above
+                const int tab = sgm < 8 ? 2 * ((5 - sgm) / 2) : 2 * ((sgm - 11) / 2) + 1;
+                double E[R];
+#pragma unroll
+                for (int r = 0; r < R; r++) E[r] = Etab[tab * TILE + 32 * r + lane];
+                int j = x0;
+                for (; j + 1 < x1; j += 2) {
+                    double4 ra = st[j], rb = st[j + 1];
+                    double fa = Fp[j], fb = Fp[j + 1];
+#pragma unroll
+                    for (int r = 0; r < R; r++) {
+                        double da = nup[r] - ra.x, db = nup[r] - rb.x;
+                        double gea = E[r] * fa, geb = E[r] * fb;
+                        double qa = fma(da, da, gea * gea), qb = fma(db, db, geb * geb);
+                        double num = fma(rb.z * geb, qa, (ra.z * gea) * qb);
+                        acc[r] = fma(num, cs_rcp(qa * qb), acc[r]);
+                    }
+                }
+                for (; j < x1; j++) {
+                    double4 rc = st[j];
+                    double f = Fp[j];
+#pragma unroll
+                    for (int r = 0; r < R; r++) {
+                        double dnu = nup[r] - rc.x;
+                        double ge = E[r] * f;
+                        acc[r] = fma(rc.z * ge, cs_rcp(fma(dnu, dnu, ge * ge)), acc[r]);
+                    }
+                }
+            }
+        } else {
         if (xa > 0) cold_edge<SHAPE, R>(w, st, c0, 0, xa);
 #pragma unroll 1
         for (int pass = 0; pass < 2; pass++) {
@@ -537,6 +696,7 @@ __global__ void __launch_bounds__(LS_THREADS, 16 / LS_WARPS) line_sum_kernel(Lin
         }
         if (xd < n) cold_edge<SHAPE, R>(w, st, c0, xd, n);
         if (SHAPE == CS_VOIGT && qn > 0) { cold_flush<SHAPE, R>(w, st, c0, qn); qn = 0; }
+        }
         // stage s is free again: refill it with chunk c + LS_STAGES
         __syncwarp();
         if (lane == 0 && c + LS_STAGES < nchunk) {
@@ -561,12 +721,13 @@ template <int SHAPE, int R> int32_t launch_line_sum(cs_ctx* ctx, LineSumArgs a, 
     constexpr int TILE = 32 * R;
     cudaStream_t st = ctx->stream;
     a.ntiles = (a.nnu + TILE - 1) / TILE;
-    CS_TRY(ctx->s_w.reserve(sizeof(int64_t) * 6 * (size_t)a.ntiles));
+    a.nr = (SHAPE == CS_PHCO2) ? LS_NR : 6;
+    CS_TRY(ctx->s_w.reserve(sizeof(int64_t) * a.nr * (size_t)a.ntiles));
     a.ranges = ctx->s_w.as<int64_t>();
-    tile_ranges_kernel<<<(unsigned)((a.ntiles * 6 + 127) / 128), 128, 0, st>>>(a.nu, a.nnu, a.nul, a.nl, a.cut, cn, TILE,
-                                                                               a.ntiles, ctx->s_w.as<int64_t>());
+    tile_ranges_kernel<<<(unsigned)((a.ntiles * a.nr + 127) / 128), 128, 0, st>>>(a.nu, a.nnu, a.nul, a.nl, a.cut, cn, TILE,
+                                                                                  a.ntiles, a.nr, ctx->s_w.as<int64_t>());
     CS_CUDA(cudaGetLastError());
-    size_t smem = (size_t)LS_WARPS * (LS_STAGES * LS_CHUNK * sizeof(double4) + 2 * TILE * sizeof(double) + LS_QCAP * sizeof(uint32_t));
+    size_t smem = (size_t)LS_WARPS * (LS_STAGES * LS_CHUNK * sizeof(double4) + ls_extra_bytes<SHAPE, R>());
     static bool attr_set = false;
     if (!attr_set) {
         CS_CUDA(cudaFuncSetAttribute(line_sum_kernel<SHAPE, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -435,3 +435,20 @@ def test_table_export_import_roundtrip(cs, co2):
     check(lib().cs_table_eval(h, len(P), ptr(f64(T)), ptr(f64(P)), ptr(out)))
     lib().cs_table_free(h)
     assert relerr(out, gas.rawσ(T, P), 1e-300) < 1e-13
+
+
+def test_phco2_all_chi_classes(cs, orc):
+    """PHCO2 with the default 500 cm^-1 cut-off on a fine grid: every chi class (|dnu| < 3, < 30, < 120, >= 120),
+    lines straddling the class borders, both sides of the tile, several temperatures (B1, B2 depend on T)"""
+    sl = synthetic_lines(cs, 6000, seed=23, νmax=1300.0)
+    ν = 640.0 + 0.01 * np.arange(2500)
+    T = np.array([140.0, 220.0, 300.0])
+    P = np.array([2e2, 2e4, 2e5])
+    got = cs.xsec("PHCO2", ν, sl, T, P, P, 500.0)
+    ref = orc.xsec(orc.PHCO2, sl, ν, T, P, P, 500.0, nthreads=0)
+    assert relerr(got, ref, 1e-290) < XSEC_TOL
+    # irregular grid with a tile wider than 3 cm^-1 (no plain class) and one wider than 27 (no class at all)
+    ν2 = np.unique(np.concatenate([np.linspace(300, 300.9, 100), np.linspace(301, 330, 120), np.linspace(331, 400, 30)]))
+    got = cs.xsec("PHCO2", ν2, sl, T, P, 0.5 * P, 500.0)
+    ref = orc.xsec(orc.PHCO2, sl, ν2, T, P, 0.5 * P, 500.0, nthreads=0)
+    assert relerr(got, ref, 1e-290) < XSEC_TOL
