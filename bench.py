@@ -69,37 +69,25 @@ def make_workload(cs, name):
                 nstream=5, nlob=2, nlayer=nlayer)
 
 
-def balanced_slices(counts, n):
-    """contiguous index slices with ~equal sums of `counts` (per-ν evaluation counts)"""
-    c = np.concatenate(([0], np.cumsum(counts, dtype=np.float64)))
-    edges = [int(np.searchsorted(c, c[-1] * k / n)) for k in range(n + 1)]
-    edges[0], edges[-1] = 0, len(counts)
-    for k in range(1, n + 1):
-        edges[k] = max(edges[k], edges[k - 1])
-    return edges
+def balanced_slices(cost, n):
+    from clearsky_b200 import sharding
+    return sharding.balanced_slices(cost, n)
 
 
 def per_point_counts(ν, νl, cut):
-    lo = np.searchsorted(νl, ν - cut, side="left")
-    hi = np.searchsorted(νl, ν + cut, side="right")
-    return (hi - lo).astype(np.int64)
+    from clearsky_b200 import sharding
+    return sharding.per_point_counts(ν, νl, cut)
 
 
-def slice_cost(ν, gases, cut, kappa=5.6e-5):
-    """per-ν cost model for balancing ν slices: evaluations, inflated by the near-centre work that grows with ν
-    (Doppler widths are proportional to ν, so the share of near-centre lines per tile is too).  kappa was calibrated
-    on the measured per-slice kernel times of the 8-way split (profiles/r1_slice_balance.txt)."""
-    counts = sum(per_point_counts(ν, sl.ν, cut) for sl, _ in gases)
-    return counts * (1.0 + kappa * ν)
+def slice_cost(ν, gases, cut):
+    """cost model used to balance the ν slices (clearsky_b200/sharding.py)"""
+    from clearsky_b200 import sharding
+    return sharding.slice_cost(ν, [sl.ν for sl, _ in gases], cut)
 
 
 def trapz_weights(ν):
-    """per-point weights of trapz(ν, ·) (util.jl:26-33): every interval counted once across ν slices"""
-    d = np.diff(ν)
-    w = np.zeros(len(ν))
-    w[:-1] += d / 2
-    w[1:] += d / 2
-    return w
+    from clearsky_b200 import sharding
+    return sharding.trapz_weights(ν)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -19,4 +19,5 @@ from .molparam import MOLPARAM, TMAX, TMIN
 from .par import SpectralLines, readpar
 from .quadrature import lobattonodes, streamnodes
 from .rcm import RCM
+from .sharding import DeviceGroup, ShardedLineByLine, sharded_fluxes
 from .util import AtmosphericProfile, chebygrid, pressuregrid, trapz

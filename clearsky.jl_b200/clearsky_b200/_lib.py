@@ -64,6 +64,13 @@ SIGNATURES = {
     "cs_fluxes_device": [_vp, C.c_int64, _dp, C.c_int32, _dp, _dp, _dp, C.c_double, _dp, _dp, C.c_double,
                          C.c_int32, _dp, _dp, _dp, _vp],
     "cs_opticaldepth": [_vp, C.c_int64, _dp, C.c_int32, _dp, _dp, C.c_double, C.c_double, _dp],
+    "cs_group_create": [C.c_int32, C.POINTER(C.c_int32), C.POINTER(_vp)],
+    "cs_group_free": [_vp],
+    "cs_group_size": [_vp, C.POINTER(C.c_int32)],
+    "cs_group_ctx": [_vp, C.c_int32, C.POINTER(_vp)],
+    "cs_group_buffer": [_vp, C.c_int32, C.c_int64, C.POINTER(_vp)],
+    "cs_group_allreduce_sum": [_vp, C.c_int64],
+    "cs_group_read": [_vp, C.c_int32, C.c_int64, _dp],
 }
 
 _lib = None
@@ -123,9 +130,12 @@ def i64ptr(a):
 class Context:
     """one CUDA device + stream (cs_ctx)"""
 
-    def __init__(self, device=0, stream=None):
+    def __init__(self, device=0, stream=None, borrowed=None):
         self.h = _vp()
-        if stream is None:
+        self._borrowed = borrowed is not None
+        if borrowed is not None:
+            self.h = borrowed          # owned by a cs_group
+        elif stream is None:
             check(lib().cs_ctx_create(int(device), C.byref(self.h)))
         else:
             check(lib().cs_ctx_create_on_stream(int(device), _vp(int(stream)), C.byref(self.h)))
@@ -150,9 +160,9 @@ class Context:
         return v.value
 
     def close(self):
-        if self.h:
+        if self.h and not self._borrowed:
             lib().cs_ctx_free(self.h)
-            self.h = _vp()
+        self.h = _vp()
 
     def __del__(self):
         try:

@@ -1,0 +1,189 @@
+"""ν-sharded multi-GPU evaluation: contiguous wavenumber slices balanced by cost, lines within
+slice ± cut-off only, global trapezoid weights (every interval counted exactly once, no halo), and ONE all-reduce of
+the 2·np spectrally integrated fluxes.
+
+Two host models use the same slicing:
+  * one process per GPU under torchrun (bench.py): partial fluxes go straight into a torch tensor via
+    cs_fluxes_device and torch.distributed (NCCL) reduces them;
+  * one process driving all GPUs (`DeviceGroup` + `sharded_fluxes` below, what the Julia wrapper would do with one
+    task per device): cs_group_* owns the contexts and the NCCL communicator.
+"""
+import ctypes as C
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+
+from . import _lib
+from ._lib import check, f64, lib, ptr
+from .absorbers import SigmaWorkspace
+from .core import Discretized
+from .fluxes import _unique_nodes, _vec, checkazimuth, formprofile, lobattoevaluations
+from .gases import LineGas
+from .par import SpectralLines
+from .quadrature import lobattonodes, streamnodes
+
+
+def per_point_counts(ν, νl, cut):
+    """number of lines within ± cut of every wavenumber (νl sorted)"""
+    lo = np.searchsorted(νl, ν - cut, side="left")
+    hi = np.searchsorted(νl, ν + cut, side="right")
+    return (hi - lo).astype(np.int64)
+
+
+def slice_cost(ν, line_lists, cut, kappa=5.6e-5):
+    """per-ν cost model for balancing slices: evaluations, inflated by the near-centre work that grows with ν
+    (Doppler widths are proportional to ν, so the share of near-centre lines per tile is too).  kappa was calibrated
+    on the measured per-slice kernel times of the 8-way split (profiles/r1_slice_balance.txt)."""
+    counts = sum(per_point_counts(ν, νl, cut) for νl in line_lists)
+    return counts * (1.0 + kappa * ν)
+
+
+def balanced_slices(cost, n):
+    """n contiguous index slices with ~equal sums of `cost` -> n+1 edges"""
+    c = np.concatenate(([0], np.cumsum(cost, dtype=np.float64)))
+    edges = [int(np.searchsorted(c, c[-1] * k / n)) for k in range(n + 1)]
+    edges[0], edges[-1] = 0, len(cost)
+    for k in range(1, n + 1):
+        edges[k] = max(edges[k], edges[k - 1])
+    return edges
+
+
+def trapz_weights(ν):
+    """per-point weights of trapz(ν, ·) (util.jl:26-33): w_j = (Δν_{j-1} + Δν_j)/2"""
+    d = np.diff(ν)
+    w = np.zeros(len(ν))
+    w[:-1] += d / 2
+    w[1:] += d / 2
+    return w
+
+
+def slice_lines(sl, νlo, νhi, cut):
+    """every line a slice can see (the per-point inclusive rule decides inside the kernel)"""
+    keep = (sl.ν >= νlo - cut - 1e-9) & (sl.ν <= νhi + cut + 1e-9)
+    if not keep.any():
+        keep[np.argmin(np.abs(sl.ν - νlo))] = True      # keep one (out-of-window) line: an upload cannot be empty
+    return SpectralLines(sl.name, sl.formula, int(keep.sum()), sl.M, sl.I[keep], sl.μ[keep], sl.A[keep], sl.ν[keep],
+                         sl.S[keep], sl.γa[keep], sl.γs[keep], sl.Epp[keep], sl.na[keep])
+
+
+class DeviceGroup:
+    """cs_group: one context per device + a single-node NCCL communicator, all inside this process"""
+
+    def __init__(self, devices=None):
+        if devices is None:
+            devices = list(range(_lib.device_count()))
+        self.devices = list(devices)
+        arr = (C.c_int32 * len(self.devices))(*self.devices)
+        self.h = C.c_void_p()
+        check(lib().cs_group_create(len(self.devices), arr, C.byref(self.h)))
+        self.ctx = []
+        for i in range(len(self.devices)):
+            c = C.c_void_p()
+            check(lib().cs_group_ctx(self.h, i, C.byref(c)))
+            self.ctx.append(_lib.Context(self.devices[i], borrowed=c))
+        self.pool = ThreadPoolExecutor(max_workers=len(self.devices))
+
+    def __len__(self):
+        return len(self.devices)
+
+    def buffer(self, i, count):
+        p = C.c_void_p()
+        check(lib().cs_group_buffer(self.h, i, int(count), C.byref(p)))
+        return p
+
+    def allreduce_sum(self, count):
+        check(lib().cs_group_allreduce_sum(self.h, int(count)))
+
+    def read(self, i, count):
+        out = np.empty(int(count))
+        check(lib().cs_group_read(self.h, i, int(count), ptr(out)))
+        return out
+
+    def close(self):
+        if self.h:
+            self.pool.shutdown(wait=True)
+            for c in self.ctx:
+                c.h = C.c_void_p()
+            lib().cs_group_free(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class ShardedLineByLine:
+    """Exact line-by-line gases sharded over a DeviceGroup by contiguous ν slices.  Slicing, line uploads and the
+    per-device Σ workspaces are done once; every `fluxes` call is then K1/K2 + K6/K7 per device (one host thread
+    each) and one all-reduce.   gases: list of (SpectralLines, fC, shape, Δνcut)."""
+
+    def __init__(self, group, gases, ν):
+        self.group = group
+        self.ν = f64(np.asarray(ν, dtype=np.float64))
+        assert np.all(np.diff(self.ν) > 0), "wavenumbers must be unique and in ascending order"
+        self.gases = list(gases)
+        n = len(group)
+        cost = sum(slice_cost(self.ν, [sl.ν], cut) for sl, _, _, cut in self.gases)
+        self.edges = balanced_slices(cost, n)
+        self.wg = trapz_weights(self.ν)
+        self.parts = []
+        for i in range(n):
+            a, b = self.edges[i], self.edges[i + 1]
+            if b <= a:
+                self.parts.append(None)
+                continue
+            νs = np.ascontiguousarray(self.ν[a:b])
+            ctx = group.ctx[i]
+            lg = [LineGas(slice_lines(sl, νs[0], νs[-1], cut), fC, νs, shape, cut, ctx=ctx) for sl, fC, shape, cut in self.gases]
+            self.parts.append(dict(a=a, b=b, ν=νs, gases=lg, ws={}, w=np.ascontiguousarray(self.wg[a:b])))
+
+    def fluxes(self, P, g, T, μ, fS=None, fa=None, core=None, θs=0.841):
+        core = core or Discretized()
+        group, n = self.group, len(self.group)
+        P = f64(np.asarray(P, dtype=np.float64))
+        assert np.all(np.diff(P) >= 0), "pressure coordinates must be in ascending order (sorted)"
+        checkazimuth(θs)
+        fT, fμ = formprofile(P, T), formprofile(P, μ)
+        Tl, μl, Pn = lobattoevaluations(P, fT, fμ, core.nlobatto)
+        Tn, Pq = _unique_nodes(P, Tl, Pn, core.nlobatto)
+        Tn, Pq, μl = f64(Tn), f64(Pq), f64(μl)
+        Tlev = f64(_vec(fT, P))
+        m, W = (f64(x) for x in streamnodes(core.nstream))
+        wl = f64(lobattonodes(core.nlobatto)[1])
+        npl = len(P)
+        fSν = None if fS is None else f64(_vec(fS, self.ν) if callable(fS) else np.full(len(self.ν), float(fS)))
+        faν = None if fa is None else f64(_vec(fa, self.ν) if callable(fa) else np.full(len(self.ν), float(fa)))
+
+        def run(i):
+            part = self.parts[i]
+            buf = group.buffer(i, 2 * npl)
+            ctx = group.ctx[i]
+            if part is None:     # empty slice: contribute zeros
+                z = SigmaWorkspace(self.ν[:1], len(Tn), ctx)
+                check(lib().cs_fluxes_device(z.h, npl, ptr(P), core.nlobatto, ptr(wl), ptr(μl), ptr(Tlev), float(g), None, None,
+                                             float(θs), core.nstream, ptr(m), ptr(W), ptr(np.zeros(1)), buf))
+                return
+            a, b = part["a"], part["b"]
+            ws = part["ws"].get(len(Tn))
+            if ws is None:
+                ws = part["ws"][len(Tn)] = SigmaWorkspace(part["ν"], len(Tn), ctx)
+            else:
+                ws.zero()
+            for lg in part["gases"]:
+                lg.add_to(ws, Tn, Pq)
+            check(lib().cs_fluxes_device(ws.h, npl, ptr(P), core.nlobatto, ptr(wl), ptr(μl), ptr(Tlev), float(g),
+                                         ptr(np.ascontiguousarray(fSν[a:b])) if fSν is not None else None,
+                                         ptr(np.ascontiguousarray(faν[a:b])) if faν is not None else None,
+                                         float(θs), core.nstream, ptr(m), ptr(W), ptr(part["w"]), buf))
+
+        list(group.pool.map(run, range(n)))      # one host thread per device; ctypes releases the GIL inside the calls
+        group.allreduce_sum(2 * npl)
+        F = group.read(0, 2 * npl)
+        return F[:npl].copy(), F[npl:].copy(), F[:npl] - F[npl:]
+
+
+def sharded_fluxes(group, P, g, T, μ, fS, fa, gases, ν, core=None, θs=0.841):
+    """one-shot form of ShardedLineByLine(group, gases, ν).fluxes(...) -> (F⁺, F⁻, Fnet)"""
+    return ShardedLineByLine(group, gases, ν).fluxes(P, g, T, μ, fS, fa, core=core, θs=θs)

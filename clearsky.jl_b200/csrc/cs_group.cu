@@ -1,0 +1,161 @@
+// cs_group.cu -- single-process multi-GPU plumbing: one context per device + one NCCL all-reduce.
+//
+// The path shards by contiguous wavenumber slices (every nu is independent through K2..K6); the only cross-device
+// step is the sum of the 2*np spectrally integrated fluxes.  NCCL is loaded with dlopen so that the library has no
+// link-time dependency on it (a host process such as PyTorch may bring its own libnccl.so.2).
+#include "cs_internal.cuh"
+#include <dlfcn.h>
+
+namespace {
+
+typedef struct ncclComm* ncclComm_t;
+typedef int ncclResult_t;
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+constexpr int NCCL_DOUBLE = 8;   // ncclFloat64
+constexpr int NCCL_SUM = 0;
+
+int32_t load_nccl(NcclApi& api)
+{
+    if (api.lib) return CS_OK;
+    const char* names[] = {getenv("CLEARSKY_B200_NCCL"), "libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+        if (!n) continue;
+        api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (api.lib) break;
+    }
+    CS_REQUIRE(api.lib, CS_ERR_CUDA, "cannot dlopen libnccl.so.2 (set CLEARSKY_B200_NCCL): %s", dlerror());
+#define CS_SYM(field, sym)                                                             \
+    *(void**)(&api.field) = dlsym(api.lib, sym);                                       \
+    CS_REQUIRE(api.field, CS_ERR_CUDA, "symbol %s missing from NCCL", sym)
+    CS_SYM(CommInitAll, "ncclCommInitAll");
+    CS_SYM(CommDestroy, "ncclCommDestroy");
+    CS_SYM(GroupStart, "ncclGroupStart");
+    CS_SYM(GroupEnd, "ncclGroupEnd");
+    CS_SYM(AllReduce, "ncclAllReduce");
+    CS_SYM(GetErrorString, "ncclGetErrorString");
+#undef CS_SYM
+    return CS_OK;
+}
+
+}  // namespace
+
+struct cs_group {
+    std::vector<cs_ctx*> ctx;
+    std::vector<int> dev;
+    std::vector<DevBuf> buf;
+    std::vector<ncclComm_t> comm;
+    NcclApi nccl;
+    std::mutex mtx;
+};
+
+extern "C" int32_t cs_group_create(int32_t ndev, const int32_t* devices, cs_group** out)
+{
+    CS_REQUIRE(out && devices && ndev >= 1, CS_ERR_ARG, "bad group arguments");
+    *out = nullptr;
+    cs_group* g = new cs_group();
+    for (int i = 0; i < ndev; i++) {
+        cs_ctx* c = nullptr;
+        int32_t rc = cs_ctx_create(devices[i], &c);
+        if (rc) {
+            cs_group_free(g);
+            return rc;
+        }
+        g->ctx.push_back(c);
+        g->dev.push_back(devices[i]);
+    }
+    g->buf.resize((size_t)ndev);
+    if (ndev > 1) {
+        int32_t rc = load_nccl(g->nccl);
+        if (rc) { cs_group_free(g); return rc; }
+        g->comm.resize((size_t)ndev, nullptr);
+        ncclResult_t r = g->nccl.CommInitAll(g->comm.data(), ndev, g->dev.data());
+        if (r != 0) {
+            cs_set_error("ncclCommInitAll: %s", g->nccl.GetErrorString(r));
+            g->comm.clear();
+            cs_group_free(g);
+            return CS_ERR_CUDA;
+        }
+    }
+    *out = g;
+    return CS_OK;
+}
+
+extern "C" int32_t cs_group_free(cs_group* g)
+{
+    if (!g) return CS_OK;
+    for (size_t i = 0; i < g->comm.size(); i++)
+        if (g->comm[i]) g->nccl.CommDestroy(g->comm[i]);
+    for (size_t i = 0; i < g->ctx.size(); i++) {
+        cudaSetDevice(g->dev[i]);
+        if (i < g->buf.size()) g->buf[i].release();
+        cs_ctx_free(g->ctx[i]);
+    }
+    delete g;
+    return CS_OK;
+}
+
+extern "C" int32_t cs_group_size(cs_group* g, int32_t* n)
+{
+    CS_REQUIRE(g && n, CS_ERR_ARG, "null argument");
+    *n = (int32_t)g->ctx.size();
+    return CS_OK;
+}
+
+extern "C" int32_t cs_group_ctx(cs_group* g, int32_t i, cs_ctx** c)
+{
+    CS_REQUIRE(g && c && i >= 0 && i < (int32_t)g->ctx.size(), CS_ERR_ARG, "bad group member index");
+    *c = g->ctx[(size_t)i];
+    return CS_OK;
+}
+
+extern "C" int32_t cs_group_buffer(cs_group* g, int32_t i, int64_t count, double** d_ptr)
+{
+    CS_REQUIRE(g && d_ptr && count > 0 && i >= 0 && i < (int32_t)g->ctx.size(), CS_ERR_ARG, "bad group buffer request");
+    std::lock_guard<std::mutex> lk(g->mtx);
+    CS_CUDA(cudaSetDevice(g->dev[(size_t)i]));
+    CS_TRY(g->buf[(size_t)i].reserve(sizeof(double) * (size_t)count));
+    *d_ptr = g->buf[(size_t)i].as<double>();
+    return CS_OK;
+}
+
+extern "C" int32_t cs_group_allreduce_sum(cs_group* g, int64_t count)
+{
+    CS_REQUIRE(g && count > 0, CS_ERR_ARG, "bad all-reduce arguments");
+    const int n = (int)g->ctx.size();
+    for (int i = 0; i < n; i++)
+        CS_REQUIRE(g->buf[(size_t)i].cap >= sizeof(double) * (size_t)count, CS_ERR_ARG, "group buffer %d smaller than %lld doubles", i, (long long)count);
+    if (n == 1) return cs_ctx_synchronize(g->ctx[0]);
+    std::lock_guard<std::mutex> lk(g->mtx);
+    ncclResult_t r = g->nccl.GroupStart();
+    for (int i = 0; i < n && r == 0; i++) {
+        double* p = g->buf[(size_t)i].as<double>();
+        r = g->nccl.AllReduce(p, p, (size_t)count, NCCL_DOUBLE, NCCL_SUM, g->comm[(size_t)i], g->ctx[(size_t)i]->stream);
+    }
+    ncclResult_t r2 = g->nccl.GroupEnd();
+    if (r == 0) r = r2;
+    CS_REQUIRE(r == 0, CS_ERR_CUDA, "ncclAllReduce: %s", g->nccl.GetErrorString(r));
+    for (int i = 0; i < n; i++) {
+        CS_CUDA(cudaSetDevice(g->dev[(size_t)i]));
+        CS_CUDA(cudaStreamSynchronize(g->ctx[(size_t)i]->stream));
+    }
+    return CS_OK;
+}
+
+extern "C" int32_t cs_group_read(cs_group* g, int32_t i, int64_t count, double* host)
+{
+    CS_REQUIRE(g && host && count > 0 && i >= 0 && i < (int32_t)g->ctx.size(), CS_ERR_ARG, "bad group read");
+    CS_REQUIRE(g->buf[(size_t)i].cap >= sizeof(double) * (size_t)count, CS_ERR_ARG, "group buffer smaller than the read");
+    CS_CUDA(cudaSetDevice(g->dev[(size_t)i]));
+    cudaStream_t st = g->ctx[(size_t)i]->stream;
+    CS_CUDA(cudaMemcpyAsync(host, g->buf[(size_t)i].p, sizeof(double) * (size_t)count, cudaMemcpyDeviceToHost, st));
+    CS_CUDA(cudaStreamSynchronize(st));
+    return CS_OK;
+}

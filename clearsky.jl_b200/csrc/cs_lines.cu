@@ -728,11 +728,8 @@ template <int SHAPE, int R> int32_t launch_line_sum(cs_ctx* ctx, LineSumArgs a, 
                                                                                   a.ntiles, a.nr, ctx->s_w.as<int64_t>());
     CS_CUDA(cudaGetLastError());
     size_t smem = (size_t)LS_WARPS * (LS_STAGES * LS_CHUNK * sizeof(double4) + ls_extra_bytes<SHAPE, R>());
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (smem > 48 * 1024)   // per device: not cached, several contexts may live on different GPUs
         CS_CUDA(cudaFuncSetAttribute(line_sum_kernel<SHAPE, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
     dim3 grid((unsigned)((a.ntiles + LS_WARPS - 1) / LS_WARPS), (unsigned)nlev);
     line_sum_kernel<SHAPE, R><<<grid, LS_THREADS, smem, st>>>(a);
     CS_CUDA(cudaGetLastError());

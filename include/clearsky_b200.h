@@ -174,6 +174,23 @@ int32_t cs_fluxes_device(cs_sigma* sig, int64_t np, const double* P, int32_t nlo
 int32_t cs_opticaldepth(cs_sigma* sig, int64_t np, const double* P, int32_t nlob, const double* wlob,
                         const double* mu, double g, double theta, double* tau_total);
 
+/* ---- single-process multi-GPU: nu-sharded runs from ONE host process --------------------
+ * A group owns one context per device and a single-node NCCL communicator (libnccl.so.2 is dlopen'ed on first use).
+ * The host shards nu contiguously, drives each device's cs_* calls from its own thread (every call only blocks its
+ * caller), lets each device leave its partial fluxes in its group buffer (cs_fluxes_device with the pointer from
+ * cs_group_buffer and GLOBAL trapezoid weights), and then issues the path's only collective: one all-reduce. */
+typedef struct cs_group cs_group;
+int32_t cs_group_create(int32_t ndev, const int32_t* devices, cs_group** out);
+int32_t cs_group_free(cs_group* grp);
+int32_t cs_group_size(cs_group* grp, int32_t* ndev);
+int32_t cs_group_ctx(cs_group* grp, int32_t i, cs_ctx** ctx);
+/* device buffer of `count` doubles owned by the group on device i (grown on demand, contents preserved per call) */
+int32_t cs_group_buffer(cs_group* grp, int32_t i, int64_t count, double** d_ptr);
+/* in-place sum over all devices of the first `count` doubles of every group buffer (ncclAllReduce over NVLink) */
+int32_t cs_group_allreduce_sum(cs_group* grp, int64_t count);
+/* copy the first `count` doubles of device i's group buffer to the host */
+int32_t cs_group_read(cs_group* grp, int32_t i, int64_t count, double* host);
+
 #ifdef __cplusplus
 }
 #endif

@@ -452,3 +452,25 @@ def test_phco2_all_chi_classes(cs, orc):
     got = cs.xsec("PHCO2", ν2, sl, T, P, 0.5 * P, 500.0)
     ref = orc.xsec(orc.PHCO2, sl, ν2, T, P, 0.5 * P, 500.0, nthreads=0)
     assert relerr(got, ref, 1e-290) < XSEC_TOL
+
+
+def test_single_process_device_group(cs, orc, co2):
+    """cs_group: ν-sharded fluxes from ONE process over all visible GPUs (NCCL all-reduce inside the library);
+    with one GPU the group degenerates to a single slice.  Result must equal the unsharded run to 1e-12."""
+    ν = np.linspace(500.0, 900.0, 4001)
+    P = cs.pressuregrid(10.0, 1e5, 16)
+    Γ = cs.DryAdiabat(288.0, 1e5, 1040.0, 0.029, Ptropo=1e4)
+    ndev = cs.device_count()
+    grp = cs.DeviceGroup(list(range(ndev)))
+    fS = lambda x: 0.2 + 0 * x
+    Fup, Fdn, Fnet = cs.sharded_fluxes(grp, P, 9.8, Γ, 0.029, fS, 0.3, [(co2, 400e-6, "voigt", 25.0)], ν)
+    gas = cs.LineGas(co2, 400e-6, ν, "voigt", 25.0)
+    F = cs.radiate(P, 9.8, Γ, 0.029, fS, 0.3, gas)
+    assert relerr(Fup, F.Fup) < 1e-12 and relerr(Fdn, F.Fdn) < 1e-12
+    # emulate a 3-way split on whatever devices exist (contexts may share a device)
+    grp3 = cs.DeviceGroup([i % ndev for i in range(3)]) if ndev >= 3 else None
+    if grp3 is not None:
+        Fup3, Fdn3, _ = cs.sharded_fluxes(grp3, P, 9.8, Γ, 0.029, fS, 0.3, [(co2, 400e-6, "voigt", 25.0)], ν)
+        assert relerr(Fup3, F.Fup) < 1e-12
+        grp3.close()
+    grp.close()
