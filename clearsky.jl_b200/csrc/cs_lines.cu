@@ -351,19 +351,20 @@ __device__ __noinline__ void cold_edge(const WarpCold& w, const double4* st, int
     for (int r = 0; r < R; r++) { nup[r] = w.nutile[32 * r + lane]; acc[r] = 0.0; }
     int j = e0;
     if ((SHAPE == CS_VOIGT || SHAPE == CS_LORENTZ) && w.edge_is_far) {
-        // far-wing pairs with the predicate folded into the numerators; a 32-point slice that is outside both
-        // windows is skipped warp-wide
-        for (; j + 1 < e1; j += 2) {
-            double4 ra = st[j], rb = st[j + 1];
+        // far-wing form with the inclusive predicate folded into the numerators (K -> 0 outside the window): no vote,
+        // no branch, so the R chains of a lane interleave exactly like in the hot loop
+        for (; j + 3 < e1; j += 4) {
+            double4 ra = st[j], rb = st[j + 1], rc = st[j + 2], rd = st[j + 3];
 #pragma unroll
             for (int r = 0; r < R; r++) {
-                double da = nup[r] - ra.x, db = nup[r] - rb.x;
-                bool ia = !(fabs(da) > cut), ib = !(fabs(db) > cut);
-                if (!__any_sync(0xffffffffu, ia | ib)) continue;
+                double da = nup[r] - ra.x, db = nup[r] - rb.x, dc = nup[r] - rc.x, dd = nup[r] - rd.x;
+                double ka = (fabs(da) > cut) ? 0.0 : ra.z, kb = (fabs(db) > cut) ? 0.0 : rb.z;
+                double kc = (fabs(dc) > cut) ? 0.0 : rc.z, kd = (fabs(dd) > cut) ? 0.0 : rd.z;
                 double qa = fma(da, da, ra.y), qb = fma(db, db, rb.y);
-                double num = (ia ? ra.z : 0.0) * qb;
-                num = fma(ib ? rb.z : 0.0, qa, num);
-                acc[r] = fma(num, cs_rcp(qa * qb), acc[r]);
+                double qc = fma(dc, dc, rc.y), qd = fma(dd, dd, rd.y);
+                double n1 = fma(kb, qa, ka * qb), d1 = qa * qb;
+                double n2 = fma(kd, qc, kc * qd), d2 = qc * qd;
+                acc[r] = fma(fma(n2, d1, n1 * d2), cs_rcp(d1 * d2), acc[r]);
             }
         }
         for (; j < e1; j++) {
@@ -371,8 +372,7 @@ __device__ __noinline__ void cold_edge(const WarpCold& w, const double4* st, int
 #pragma unroll
             for (int r = 0; r < R; r++) {
                 double dnu = nup[r] - rc.x;
-                bool in = !(fabs(dnu) > cut);
-                acc[r] = fma(in ? rc.z : 0.0, cs_rcp(fma(dnu, dnu, rc.y)), acc[r]);
+                acc[r] = fma((fabs(dnu) > cut) ? 0.0 : rc.z, cs_rcp(fma(dnu, dnu, rc.y)), acc[r]);
             }
         }
     } else {
@@ -403,17 +403,24 @@ __device__ __noinline__ int cold_near(const WarpCold& w, const double4* st, int6
         double4 rc = st[j];
         if (SHAPE == CS_VOIGT) {
             if (qn > LS_QCAP - 32 * R) { cold_flush<SHAPE, R>(w, st, c0, qn); qn = 0; }
+            // all R evaluations first (independent chains), then the deferral bookkeeping without divergent branches:
+            // (line, point) pairs that need the general routine are compacted in (line, slice, lane) order
+            bool need[R];
+            unsigned m[R];
 #pragma unroll
             for (int r = 0; r < R; r++) {
-                bool need;
-                double v = voigt_12(rc, nup[r] - rc.x, need);
-                acc[r] += need ? 0.0 : v;
-                unsigned m = __ballot_sync(0xffffffffu, need);
-                if (m) {   // defer: compact (line, point) into the queue, order fixed by (line, slice, lane)
-                    if (need) w.queue[qn + __popc(m & lt_mask)] = ((uint32_t)j << 8) | (uint32_t)(32 * r + lane);
-                    qn += __popc(m);
-                }
+                double v = voigt_12(rc, nup[r] - rc.x, need[r]);
+                acc[r] += need[r] ? 0.0 : v;
             }
+#pragma unroll
+            for (int r = 0; r < R; r++) m[r] = __ballot_sync(0xffffffffu, need[r]);
+            int off = qn;
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                if (need[r]) w.queue[off + __popc(m[r] & lt_mask)] = ((uint32_t)j << 8) | (uint32_t)(32 * r + lane);
+                off += __popc(m[r]);
+            }
+            qn = off;
         } else {
 #pragma unroll
             for (int r = 0; r < R; r++) acc[r] += eval_checked<SHAPE>(rc, nup[r] - rc.x, w.slow_lev, c0 + j, w.B1, w.B2);
