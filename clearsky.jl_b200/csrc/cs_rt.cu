@@ -26,7 +26,7 @@ struct RtArgs {
     const double* w;       // [nnu] trapezoid weights
     const double* fS;      // [nnu] or null (== 0)
     const double* fa;      // [nnu] or null (== 0)
-    const double* small;   // packed: P[np], mu[nlob*(np-1)], wl[nlob], kT[np], m[ns], W[ns]
+    const double* small;   // packed: P[np], mu[nlob*(np-1)], wl[nlob], 1/(kT)[np], m[ns], W[ns], 1/m[ns]
     int64_t nnu;
     int np, nlob, ns;
     double Cg, cos_s;
@@ -45,10 +45,12 @@ __device__ __forceinline__ double warp_sum(double v)
     return v;
 }
 
-// layerplanck (core/discretized.jl:85)
-__device__ __forceinline__ double layerplanck(double B1, double B2, double tau, double t)
+// layerplanck (core/discretized.jl:85): B2 (1-t) - (B1-B2) t + (1-t)(B1-B2)/tau, with 1/tau supplied by the caller
+// (one reciprocal per layer shared by all streams: 1/(tau m_k) = (1/tau)(1/m_k); differences are at the 1e-16 level)
+__device__ __forceinline__ double layerplanck(double B1, double B2, double rtau, double t)
 {
-    return B2 * (1.0 - t) - (B1 - B2) * t + (1.0 - t) * (B1 - B2) / tau;
+    double omt = 1.0 - t, dB = B1 - B2;
+    return fma(omt * dB, rtau, fma(B2, omt, -dB * t));
 }
 
 template <int NS>
@@ -58,13 +60,14 @@ __global__ void __launch_bounds__(RT_THREADS) rt_kernel(RtArgs a)
     const int np = a.np, L = np - 1, nlob = a.nlob;
     const int ns = (NS > 0) ? NS : a.ns;
     // shared layout: small arrays, then per-warp partial sums [2][np][RT_WARPS]
-    const int nsmall = np + nlob * L + nlob + np + 2 * ns;
+    const int nsmall = np + nlob * L + nlob + np + 3 * ns;
     double* sP = sm;
     double* smu = sP + np;
     double* swl = smu + nlob * L;
     double* skT = swl + nlob;
     double* sm_m = skT + np;
     double* sW = sm_m + ns;
+    double* srm = sW + ns;      // 1/m_k
     double* red = sm + nsmall;
     for (int t = threadIdx.x; t < nsmall; t += RT_THREADS) sm[t] = a.small[t];
     for (int t = threadIdx.x; t < 2 * np * RT_WARPS; t += RT_THREADS) red[t] = 0.0;
@@ -83,6 +86,7 @@ __global__ void __launch_bounds__(RT_THREADS) rt_kernel(RtArgs a)
     const double pref = 2 * CS_H * (CS_C * CS_C) * (num * num * num);
     const double Cg = a.Cg;
     const double c = a.cos_s;
+    const double rc = 1.0 / c;
 
     constexpr int NSMAX = (NS > 0) ? NS : CS_MAX_STREAMS;
     double I[NSMAX];
@@ -91,7 +95,7 @@ __global__ void __launch_bounds__(RT_THREADS) rt_kernel(RtArgs a)
 
     // ---- downward: optical depth of each layer on the fly, diffuse streams, stellar beam
     double beta1 = Cg * (a.sig[j] / smu[0]);
-    double Bprev = 100.0 * pref / (exp(hcn / skT[0]) - 1.0);
+    double Bprev = 100.0 * pref / (exp(hcn * skT[0]) - 1.0);
     a.B_s[j] = Bprev;
     double beam = c * (a.fS ? a.fS[j] : 0.0);
     double Mdn = beam;                                   // M-[1] = c*fS(nu)   (discretized.jl:299)
@@ -114,20 +118,21 @@ __global__ void __launch_bounds__(RT_THREADS) rt_kernel(RtArgs a)
         double tau = fmax(ti, 1e-6);                     // floor on the vertical depth (discretized.jl:174)
         a.tau_s[(size_t)i * nnu + j] = tau;
         if (a.tau_out && live) a.tau_out[(size_t)L * j + i] = tau;
-        double Bnext = 100.0 * pref / (exp(hcn / skT[i + 1]) - 1.0);
+        double Bnext = 100.0 * pref / (exp(hcn * skT[i + 1]) - 1.0);
         a.B_s[(size_t)(i + 1) * nnu + j] = Bnext;
         double Msum = 0.0;
+        const double rtau = cs_rcp(tau);
 #pragma unroll
         for (int k = 0; k < NSMAX; k++) {
             if (k < ns) {
                 double tk = tau * sm_m[k];
                 double tr = exp(-tk);
-                double Be = layerplanck(Bprev, Bnext, tk, tr);
+                double Be = layerplanck(Bprev, Bnext, rtau * srm[k], tr);
                 I[k] = I[k] * tr + Be;
                 Msum += sW[k] * I[k];
             }
         }
-        beam *= exp(-tau / c);                           // discretized.jl:302
+        beam *= exp(-tau * rc);                          // discretized.jl:302
         Mdn = Msum + beam;
         if (a.Mdn_out && live) a.Mdn_out[(size_t)np * j + i + 1] = Mdn;
         double r = warp_sum(wj * Mdn);
@@ -150,12 +155,13 @@ __global__ void __launch_bounds__(RT_THREADS) rt_kernel(RtArgs a)
         double tau = a.tau_s[(size_t)i * nnu + j];
         double B2 = a.B_s[(size_t)i * nnu + j];
         double Msum = 0.0;
+        const double rtau = cs_rcp(tau);
 #pragma unroll
         for (int k = 0; k < NSMAX; k++) {
             if (k < ns) {
                 double tk = tau * sm_m[k];
                 double tr = exp(-tk);
-                double Be = layerplanck(B1, B2, tk, tr);
+                double Be = layerplanck(B1, B2, rtau * srm[k], tr);
                 I[k] = I[k] * tr + Be;
                 Msum += sW[k] * I[k];
             }
@@ -262,13 +268,14 @@ int32_t fluxes_impl(cs_sigma* s, int64_t np, const double* P, int32_t nlob, cons
 
     // pack the small per-level arrays
     std::vector<double> small;
-    small.reserve((size_t)(2 * np + nlob * L + nlob + 2 * nstream));
+    small.reserve((size_t)(2 * np + nlob * L + nlob + 3 * nstream));
     small.insert(small.end(), P, P + np);
     small.insert(small.end(), mu, mu + (size_t)nlob * L);
     small.insert(small.end(), wlob, wlob + nlob);
-    for (int64_t i = 0; i < np; i++) small.push_back(CS_KB * Tlev[i]);
+    for (int64_t i = 0; i < np; i++) small.push_back(1.0 / (CS_KB * Tlev[i]));   // x = h c nu / (k T) as a product
     small.insert(small.end(), m, m + nstream);
     small.insert(small.end(), W, W + nstream);
+    for (int k = 0; k < nstream; k++) small.push_back(1.0 / m[k]);
 
     // trapezoid weights: the workspace's own (computed at creation) unless the caller supplies global ones
     const double* wsrc = nu_weights;
