@@ -252,19 +252,17 @@ static __device__ __noinline__ double cs_faddeyeva985(double x, double y)
     return cdiv(num, den).re;
 }
 
-// fast reciprocal with full double accuracy for normal, finite, positive arguments:
-// MUFU.RCP64H seed + one cubic and one quadratic Newton step (the sequence nvcc emits for 1.0/x,
-// minus the exponent-range fix-up the callers do not need).
+// fast reciprocal for normal, finite, positive arguments: MUFU.RCP64H seed (measured max relative error 9.9e-7 =
+// 2^-19.9 on B200, tools/micro/rcp_accuracy.cu) + ONE cubic Newton step r(1 + e + e^2), e = 1 - a r, which leaves
+// e^3 ~ 1e-18 < 2^-53: the result is within 1 ulp of 1/a (measured max 2.2e-16).  nvcc's own 1.0/x adds a second,
+// quadratic step and an exponent-range fix-up for correct rounding; a 1e-9 parity budget does not need them.
 __device__ __forceinline__ double cs_rcp(double a)
 {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
     double e = fma(-a, r, 1.0);
     e = fma(e, e, e);
-    r = fma(r, e, r);
-    e = fma(-a, r, 1.0);
-    r = fma(r, e, r);
-    return r;
+    return fma(r, e, r);
 }
 
 // internal entry points implemented across the .cu files
