@@ -14,7 +14,8 @@ from .fluxes import (fluxes, monochromaticfluxes, monochromaticfluxes_, netfluxe
                      transmittance)
 from .gases import AtmosphericDomain, Gas, GrayGas, LineGas, SemiGrayGas
 from .line_shapes import (PHCO2, PHCO2_b200_inplace, DeviceLines, device_lines, doppler, doppler_b200_inplace,
-                          lorentz, lorentz_b200_inplace, voigt, voigt_b200_inplace, xsec)
+                          lorentz, lorentz_b200_inplace, scaleintensity, voigt, voigt_b200_inplace, xsec, αdoppler,
+                          γlorentz)
 from .molparam import MOLPARAM, TMAX, TMIN
 from .par import SpectralLines, readpar
 from .quadrature import lobattonodes, streamnodes

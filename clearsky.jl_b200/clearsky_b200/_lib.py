@@ -35,6 +35,7 @@ SIGNATURES = {
     "cs_lines_upload": [_vp, C.c_int64, _dp, _dp, _dp, _dp, _dp, _dp, _dp, C.POINTER(C.c_int16), C.c_int32,
                         C.POINTER(C.c_int32), _dp, C.POINTER(C.c_uint8), C.POINTER(_vp)],
     "cs_lines_free": [_vp],
+    "cs_line_params": [_vp, C.c_double, C.c_double, C.c_double, _dp, _dp, _dp],
     "cs_xsec": [_vp, C.c_int32, C.c_int64, _dp, C.c_int64, _dp, _dp, _dp, C.c_double, _dp],
     "cs_count_evals": [_vp, C.c_int64, _dp, C.c_double, _i64p],
     "cs_bake": [_vp, C.c_int32, C.c_int64, _dp, C.c_int32, _dp, C.c_int32, _dp, _dp, C.c_double, C.c_int32,

@@ -119,6 +119,12 @@ class UnifiedAbsorber(AbstractAbsorber):
                     extra[m] += v
             ws.add_host(extra)
 
+    def __call__(self, T, P):
+        """(U::UnifiedAbsorber)(T, P): Σ for every wavenumber at one (T, P) (absorbers.jl:97-99)"""
+        ws = SigmaWorkspace(self.ν, 1)
+        self.sigma_nodes(ws, np.array([float(T)]), np.array([float(P)]))
+        return ws.read()[0]
+
     def checkpressures(self, Ps, Pt):
         """absorbers.jl:237-246"""
         assert Ps > Pt, "Pₛ must be greater than Pₜ"

@@ -104,6 +104,33 @@ class CIATables:
             self._dev[id(ctx)] = (h, ctx)
         return self._dev[id(ctx)][0]
 
+    def cia(self, ν, T, Pa, P1, P2, ctx=None):
+        """cia(ν, x::CIATables, T, Pₐ, P₁, P₂): cross-sections [cm²/molecule] for a vector of wavenumbers
+        (collision_induced_absorption.jl:318-323), evaluated on the GPU"""
+        ν = f64(np.atleast_1d(ν))
+        ctx = ctx or _lib.default_context()
+        h = C.c_void_p()
+        check(lib().cs_sigma_create(ctx.h, len(ν), ptr(ν), 1, C.byref(h)))
+        try:
+            one = lambda v: f64(np.array([float(v)]))
+            check(lib().cs_sigma_add_cia(h, self.handle(ctx), ptr(one(T)), ptr(one(Pa)), ptr(one(P1 / Pa)), ptr(one(P2 / Pa))))
+            out = np.empty((1, len(ν)))
+            check(lib().cs_sigma_read(h, ptr(out)))
+        finally:
+            lib().cs_sigma_free(h)
+        return out[0]
+
+    def __call__(self, ν, T):
+        """(tables::CIATables)(ν, T): absorption coefficient k [cm⁵/molecule²] (collision_induced_absorption.jl:251-276),
+        recovered from the cross-section at unit partial pressures"""
+        from . import constants as K
+        Pa = K.A
+        ρ = (Pa / K.A) * (K.T0 / T)
+        ρa = 1e-6 * Pa / (K.k * T)
+        σ = self.cia(ν, T, Pa, Pa, Pa)
+        k = σ * ρa / (K.Lo2 * ρ * ρ)
+        return float(k[0]) if np.ndim(ν) == 0 else k
+
     def __del__(self):
         try:
             for h, _ in self._dev.values():

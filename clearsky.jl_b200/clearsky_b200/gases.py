@@ -89,9 +89,13 @@ class Gas(AbstractGas):
         g.fC = fC
         return g
 
-    def rawσ(self, T, P):
-        """rawσ(g, T, P): cross-sections of all wavenumbers, without the concentration (gases.jl:263).
-        T, P may be vectors (nodes) -> array [nnode, nν]."""
+    def rawσ(self, *args):
+        """rawσ(g, T, P): cross-sections of all wavenumbers, without the concentration (gases.jl:263); T, P may be
+        vectors (nodes) -> array [nnode, nν].  rawσ(g, i, T, P): single wavenumber index i (0-based) (gases.jl:256)."""
+        if len(args) == 3:
+            i, T, P = args
+            return self.rawσ(T, P)[..., int(i)]
+        T, P = args
         scalar = np.ndim(T) == 0
         T, P = f64(np.atleast_1d(T)), f64(np.atleast_1d(P))
         out = np.empty((len(T), len(self.ν)))
@@ -104,8 +108,12 @@ class Gas(AbstractGas):
             return self.fC(T, P)
         return np.array([self.fC(t, p) for t, p in zip(T, P)], dtype=np.float64)
 
-    def __call__(self, T, P):
-        """(g::Gas)(T, P) = concentration * rawσ (gases.jl:281)"""
+    def __call__(self, *args):
+        """(g::Gas)(T, P) = concentration * rawσ (gases.jl:281); (g::Gas)(i, T, P) for one wavenumber index (gases.jl:278)"""
+        if len(args) == 3:
+            i, T, P = args
+            return self(T, P)[..., int(i)]
+        T, P = args
         c = self.concentration(T, P)
         r = self.rawσ(T, P)
         return c * r if np.ndim(T) == 0 else np.asarray(c)[:, None] * r

@@ -100,3 +100,27 @@ doppler_b200_inplace, doppler = _make("doppler", CS_DOPPLER)
 lorentz_b200_inplace, lorentz = _make("lorentz", CS_LORENTZ)
 voigt_b200_inplace, voigt = _make("voigt", CS_VOIGT)
 PHCO2_b200_inplace, PHCO2 = _make("PHCO2", CS_PHCO2)
+
+
+def _line_params(sl, T, P, Pp, which, ctx=None):
+    dl = device_lines(sl, ctx)
+    out = np.empty(dl.N)
+    args = [None, None, None]
+    args[which] = ptr(out)
+    check(lib().cs_line_params(dl.h, float(T), float(P), float(Pp), *args))
+    return out
+
+
+def scaleintensity(sl, T, ctx=None):
+    """scaleintensity(sl, :, T): temperature-scaled intensity of every line (line_shapes.jl:107-132), on the GPU"""
+    return _line_params(sl, T, 1.0, 0.0, 0, ctx)
+
+
+def αdoppler(sl, T, ctx=None):
+    """αdoppler(sl, :, T) (line_shapes.jl:144-148)"""
+    return _line_params(sl, T, 1.0, 0.0, 1, ctx)
+
+
+def γlorentz(sl, T, P, Pp, ctx=None):
+    """γlorentz(sl, :, T, P, Pₚ) (line_shapes.jl:255-261)"""
+    return _line_params(sl, T, P, Pp, 2, ctx)

@@ -744,7 +744,61 @@ template <int SHAPE, int R> int32_t launch_line_sum(cs_ctx* ctx, LineSumArgs a, 
     return CS_OK;
 }
 
+// per-line S(T), alpha(T), gamma(T,P,Pp) in the reference's operation order (same code path as prep_kernel)
+__global__ void __launch_bounds__(256) line_params_kernel(PrepArgs a, double* S_T, double* alpha, double* gamma)
+{
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= a.nl) return;
+    const LevelParams lp = a.lev[0];
+    const double T = lp.T, nul = a.nu[j];
+    const double c2 = 100.0 * CS_H * CS_C / CS_KB;
+    double ea = -c2 * a.Epp[j], eb = -c2 * nul;
+    double n = exp(ea / T) * (1 - exp(eb / T));
+    double d = exp(ea / CS_TREF) * (1 - exp(eb / CS_TREF));
+    int is = a.iso[j] - 1;
+    const double* ch = a.cheb + (size_t)is * CS_MAXCHEB;
+    double tau = 2 * (T - CS_TMIN) / (CS_TMAX - CS_TMIN) - 1;
+    double c1 = 1.0, c2c = tau, y = ch[0] + ch[1] * c2c;
+    for (int q = 2; q < a.ncheb[is]; q++) {
+        double c3 = 2 * tau * c2c - c1;
+        y += ch[q] * c3;
+        c1 = c2c;
+        c2c = c3;
+    }
+    if (S_T) S_T[j] = a.S[j] * (1.0 / y) * (n / d);
+    if (alpha) alpha[j] = (nul / CS_C) * sqrt(2.0 * CS_R * T / a.mu[j]);
+    if (gamma) gamma[j] = (pow(CS_TREF / T, a.na[j])) * (a.ga[j] * (lp.P - lp.Pp) + a.gs[j] * lp.Pp) / CS_ATM;
+}
+
 }  // namespace
+
+extern "C" int32_t cs_line_params(cs_lines* L, double T, double P, double Pp, double* S_T, double* alpha, double* gamma)
+{
+    CS_REQUIRE(L, CS_ERR_ARG, "null argument");
+    CS_REQUIRE(T >= CS_TMIN && T <= CS_TMAX, CS_ERR_DOMAIN, "temperature outside of Qref/Q interpolation range [%g, %g]: T = %g",
+               CS_TMIN, CS_TMAX, T);
+    cs_ctx* ctx = L->ctx;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mtx);
+    CS_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    LevelParams lp = {T, P, Pp, 1.0, 0, 0, 0, 0};
+    CS_TRY(ctx->s_lev.reserve(sizeof(LevelParams)));
+    CS_TRY(ctx->s_misc.reserve(sizeof(double) * 3 * (size_t)L->n));
+    CS_CUDA(cudaMemcpyAsync(ctx->s_lev.p, &lp, sizeof(lp), cudaMemcpyHostToDevice, st));
+    PrepArgs pa;
+    pa.nu = L->nu; pa.S = L->S; pa.ga = L->ga; pa.gs = L->gs; pa.Epp = L->Epp; pa.na = L->na; pa.mu = L->mu;
+    pa.iso = L->iso; pa.ncheb = L->ncheb; pa.cheb = L->cheb; pa.j0 = 0; pa.nl = L->n;
+    pa.lev = ctx->s_lev.as<LevelParams>(); pa.nlev = 1; pa.rec = nullptr; pa.slow = nullptr; pa.shape = CS_VOIGT;
+    double* d = ctx->s_misc.as<double>();
+    line_params_kernel<<<(unsigned)((L->n + 255) / 256), 256, 0, st>>>(pa, d, d + L->n, d + 2 * L->n);
+    CS_CUDA(cudaGetLastError());
+    cs_count_launch(ctx);
+    if (S_T) CS_CUDA(cudaMemcpyAsync(S_T, d, sizeof(double) * (size_t)L->n, cudaMemcpyDeviceToHost, st));
+    if (alpha) CS_CUDA(cudaMemcpyAsync(alpha, d + L->n, sizeof(double) * (size_t)L->n, cudaMemcpyDeviceToHost, st));
+    if (gamma) CS_CUDA(cudaMemcpyAsync(gamma, d + 2 * L->n, sizeof(double) * (size_t)L->n, cudaMemcpyDeviceToHost, st));
+    CS_CUDA(cudaStreamSynchronize(st));
+    return CS_OK;
+}
 
 // ------------------------------------------------------------------------------------------------
 // host orchestration shared by cs_xsec, cs_bake and cs_sigma_add_lines

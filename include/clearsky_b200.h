@@ -83,6 +83,10 @@ int32_t cs_lines_upload(cs_ctx* ctx, int64_t n, const double* nu, const double* 
                         const uint8_t* hascheb, cs_lines** out);
 int32_t cs_lines_free(cs_lines* lines);
 
+/* vector forms of scaleintensity(sl, i, T) (line_shapes.jl:125-132), alpha-doppler(sl, i, T) (:146-148) and
+ * gamma-lorentz(sl, i, T, P, Pp) (:259-261) for ALL lines at one (T, P, Pp): outputs [n] each (NULL = skip) */
+int32_t cs_line_params(cs_lines* lines, double T, double P, double Pp, double* S_T, double* alpha, double* gamma);
+
 /* S1: shape!(sigma, nu, sl, T, P, Pp, cut), batched over nlev (T,P,Pp) nodes
  * (line_shapes.jl:200-211, 313-324, 412-424, 527-540; surf! :53-87).  sigma is [nlev][nnu] and is
  * OVERWRITTEN like surf! does.  nu strictly ascending (assert :59); T in [25,1000] (assert :29). */

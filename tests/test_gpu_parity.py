@@ -474,3 +474,33 @@ def test_single_process_device_group(cs, orc, co2):
         assert relerr(Fup3, F.Fup) < 1e-12
         grp3.close()
     grp.close()
+
+
+def test_line_params_and_functors(cs, orc, co2):
+    """vector forms of scaleintensity / αdoppler / γlorentz (line_shapes.jl:125-132,146-148,259-261), the Gas and
+    UnifiedAbsorber functors (gases.jl:256-281, absorbers.jl:97-99) and the CIATables functor / cia()"""
+    import ctypes as C
+    T, P, Pp = 233.0, 4e4, 16.0
+    S, α, γ = cs.scaleintensity(co2, T), cs.αdoppler(co2, T), cs.γlorentz(co2, T, P, Pp)
+    niso, ncheb, cheb, has = co2.cheb_table()
+    idx = np.arange(0, co2.N, 37)
+    Sref = np.array([orc.scalar("orc_scaleintensity", co2.S[j], co2.ν[j], co2.Epp[j], T, C.c_int(int(ncheb[co2.I[j] - 1])),
+                                np.ascontiguousarray(cheb[co2.I[j] - 1]).ctypes.data_as(C.POINTER(C.c_double))) for j in idx])
+    αref = np.array([orc.scalar("orc_alpha_doppler", co2.ν[j], co2.μ[j], T) for j in idx])
+    γref = np.array([orc.scalar("orc_gamma_lorentz", co2.γa[j], co2.γs[j], co2.na[j], T, P, Pp) for j in idx])
+    assert relerr(S[idx], Sref, 1e-300) < 1e-12 and relerr(α[idx], αref) < 1e-14 and relerr(γ[idx], γref) < 1e-13
+    ν = np.linspace(600.0, 750.0, 301)
+    Ω = cs.AtmosphericDomain((150, 300), 6, (10, 1e5), 8)
+    gas = cs.Gas(co2, 400e-6, ν, Ω)
+    r = gas.rawσ(250.0, 2e4)
+    assert gas.rawσ(17, 250.0, 2e4) == r[17] and abs(gas(17, 250.0, 2e4) - 400e-6 * r[17]) < 1e-40
+    gray = cs.GrayGas(1e-27, ν)
+    U = cs.UnifiedAbsorber(gas, gray)
+    assert relerr(U(250.0, 2e4), 400e-6 * r + 1e-27, 1e-300) < 1e-13
+    g2 = gas.reconcentrate(1e-3)
+    assert relerr(g2(250.0, 2e4), 1e-3 * r, 1e-300) < 1e-15
+    x = cs.CIATables(os.path.join(DATA, "CO2-CO2_2018.cia.gz"), extrapolate=True)
+    νc = np.linspace(5.0, 700.0, 97)
+    assert relerr(x(νc, 250.0), orc.cia_k(x, νc, np.full(len(νc), 250.0)), 1e-300) < 1e-12
+    σ = x.cia(νc, 250.0, 1e5, 9e4, 9e4)
+    assert relerr(σ, orc.cia_nodes(x, νc, [250.0], [1e5], [0.9], [0.9])[0], 1e-300) < 1e-12
