@@ -250,8 +250,8 @@ def run_ours(args):
     i0, i1 = edges[rank], edges[rank + 1]
     νs = np.ascontiguousarray(ν[i0:i1])
     wts = np.ascontiguousarray(trapz_weights(ν)[i0:i1])
-    total_evals = int(counts.sum()) * nlev
-    my_evals = int(counts[i0:i1].sum()) * nlev
+    # exact evaluation counts (iterations of surf!'s inner loop, line_shapes.jl:75-82) from the library's host counter
+    total_evals = my_evals = None
 
     def slice_lines(sl):
         # every line the slice can see: the per-point rule decides inside the kernel
@@ -268,6 +268,13 @@ def run_ours(args):
 
     # resident objects for the device-timed loop
     dls = [cs.DeviceLines(sl, ctx) for sl, _ in my_gases]
+    my_evals = sum(dl.count_evals(νs, cut) for dl in dls) * nlev
+    if world > 1:
+        t_ev = torch.tensor([float(my_evals)], dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_reduce(t_ev)
+        total_evals = int(round(t_ev.item()))
+    else:
+        total_evals = my_evals
     ws = cs.SigmaWorkspace(νs, nlev, ctx)
     Cs = [f64(np.full(nlev, C)) for _, C in my_gases]
     timers_acc = {"linesum": 0.0, "prep": 0.0, "rt": 0.0, "reduce": 0.0}

@@ -38,10 +38,23 @@ def readpar(filename, νmin=0, νmax=np.inf, Scut=0, I=(), maxlines=-1, progress
     lines = _readlines(filename)
     N = len(lines)
     par = {}
-    par["M"] = np.array([int(ln[0:2]) for ln in lines], dtype=np.int16)
-    par["I"] = np.array([ln[2] for ln in lines], dtype="U1")
-    for key, a, b in _COLS[2:]:
-        par[key] = np.array([float(ln[a:b]) for ln in lines], dtype=np.float64)
+    # fixed 160-column records: slice the columns of all records at once (numpy), parse per column
+    if N > 0 and all(len(ln) >= 160 for ln in lines[:1000:7]) and min(map(len, lines)) >= 67:
+        width = 67
+        raw = np.frombuffer("".join(ln[:width] for ln in lines).encode("ascii"), dtype=np.uint8).reshape(N, width)
+
+        def col(a, b, dtype):
+            return np.ascontiguousarray(raw[:, a:b]).view(f"S{b - a}").ravel().astype(dtype)
+
+        par["M"] = col(0, 2, np.int64).astype(np.int16)
+        par["I"] = col(2, 3, "U1")
+        for key, a, b in _COLS[2:]:
+            par[key] = col(a, b, np.float64)
+    else:
+        par["M"] = np.array([int(ln[0:2]) for ln in lines], dtype=np.int16)
+        par["I"] = np.array([ln[2] for ln in lines], dtype="U1")
+        for key, a, b in _COLS[2:]:
+            par[key] = np.array([float(ln[a:b]) for ln in lines], dtype=np.float64)
     if strings:
         for key, a, b in _STR_COLS:
             par[key] = np.array([ln[a:b] for ln in lines], dtype=object)
