@@ -11,16 +11,18 @@
 //   sigma[level][nu]                               output, nu fastest (= Julia sigma[:, node])
 //
 // K2 design (FP64 CUDA cores; the roofline that bounds it is the FP64 FMA pipe, not HBM):
-//   grid = (nu tiles, levels); CTA = 8 consumer warps + 1 producer warp.  A warp owns 32*R contiguous nu
-//   points (R per lane, lane-strided so loads/stores coalesce).  Lines are sorted, so the lines that can
-//   touch a tile form one contiguous index range; the producer streams that range through a 4-stage
-//   shared-memory ring with cp.async.bulk (TMA 1-D bulk copy) completing on mbarriers.  Each consumer warp
-//   knows -- from four binary searches done once -- which lines are inside the cut-off for ALL of its
-//   points (interior: no predicate), which are inside for SOME (edge: exact inclusive per-point predicate
-//   |nu - nul| <= cut, line_shapes.jl:10) and which for none (culled warp-wide, never touched).
+//   work unit = one warp = (tile of 32*R consecutive nu, one level); one warp per CTA, 16 CTAs per SM.  A lane owns
+//   R points strided by 32 (coalesced).  Lines are sorted, so the lines that can touch a tile form one contiguous
+//   index range; an elected lane streams that range through the warp's private 4-stage shared-memory ring with
+//   cp.async.bulk (TMA 1-D bulk copy) completing on per-stage mbarriers.  Binary searches done once per call
+//   (tile_ranges_kernel) classify every line of the window per tile: inside the cut-off for ALL points and provably
+//   in the far wing (hot loop: no test of any kind), inside for SOME points (edge: exact inclusive predicate
+//   |nu - nul| <= cut, line_shapes.jl:10, folded into the numerators), centre close to the tile (near: Faddeyeva
+//   region decided per evaluation), outside (never touched).
 //   Far-wing Voigt (|z|^2 >= 1.6e4, >99 % of evaluations) is algebraically the Lorentz profile
-//   S*gamma/(pi*(dnu^2+gamma^2)); two lines share one reciprocal:  K1/q1 + K2/q2 = (K1*q2+K2*q1)/(q1*q2).
-//   Evaluations that are not safely in the far wing take the general Algorithm-985 routine.
+//   S*gamma/(pi*(dnu^2+gamma^2)); four lines share one reciprocal: n1/d1 + n2/d2 = (n1 d2 + n2 d1)/(d1 d2), twice.
+//   Evaluations that need the general Algorithm-985 routine are compacted into a per-warp queue and evaluated with
+//   all lanes busy.  PHCO2 factorises chi into per-point and per-line exponentials (see the kernel).
 #include "cs_internal.cuh"
 #include <algorithm>
 #include <cstdlib>
@@ -130,10 +132,6 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 {
