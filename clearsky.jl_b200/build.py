@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "lib")
 OUT = os.path.join(LIB, "libclearsky_b200.so")
-SOURCES = ["cs_api.cu", "cs_lines.cu", "cs_table.cu", "cs_rt.cu", "cs_group.cu"]
+SOURCES = ["cs_api.cu", "cs_lines.cu", "cs_table.cu", "cs_rt.cu", "cs_group.cu", "cs_par.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-O3", "--fmad=true"] + os.environ.get("CS_NVCC_EXTRA", "").split()

@@ -17,7 +17,7 @@ from .line_shapes import (PHCO2, PHCO2_b200_inplace, DeviceLines, device_lines, 
                           lorentz, lorentz_b200_inplace, scaleintensity, voigt, voigt_b200_inplace, xsec, αdoppler,
                           γlorentz)
 from .molparam import MOLPARAM, TMAX, TMIN
-from .par import SpectralLines, readpar
+from .par import SpectralLines, parse_records_b200, readpar, readpar_b200, writepar
 from .quadrature import lobattonodes, streamnodes
 from .rcm import RCM
 from .sharding import DeviceGroup, ShardedLineByLine, sharded_fluxes

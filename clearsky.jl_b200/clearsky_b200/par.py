@@ -136,3 +136,88 @@ class SpectralLines:
             assert mp.ncheb[i] <= MAXCHEB
             cheb[i, : mp.ncheb[i]] = mp.cheb[i]
         return niso, ncheb, cheb, has
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU ingestion: same result as readpar, parse loop on the device
+def parse_records_b200(buf, ctx=None):
+    """parse the numeric columns of fixed-width .par records held in `buf` (bytes) with cs_par_parse.
+    Returns (dict of arrays in file order, flags) -- flags[i] != 0 marks a record with a malformed field."""
+    import ctypes as C
+
+    from . import _lib
+    from ._lib import check, lib, ptr
+    ctx = ctx or _lib.default_context()
+    nl = buf.find(b"\n")
+    reclen = nl + 1 if nl >= 0 else len(buf)
+    assert reclen >= 161 or (nl < 0 and reclen >= 160), "expected 160-column HITRAN records"
+    nrec = (len(buf) + reclen - 1) // reclen if len(buf) % reclen else len(buf) // reclen
+    if len(buf) % reclen and len(buf) - (nrec - 1) * reclen < 67:
+        nrec -= 1                       # trailing blank line
+    M, I = np.empty(nrec, np.int16), np.empty(nrec, np.int16)
+    cols = {k: np.empty(nrec) for k in ("ν", "S", "A", "γa", "γs", "Epp", "na", "δa")}
+    flags = np.empty(nrec, np.uint8)
+    i16 = lambda a: a.ctypes.data_as(C.POINTER(C.c_int16))
+    check(lib().cs_par_parse(ctx.h, len(buf), buf, reclen, nrec, i16(M), i16(I), *[ptr(cols[k]) for k in
+                             ("ν", "S", "A", "γa", "γs", "Epp", "na", "δa")], flags.ctypes.data_as(C.POINTER(C.c_uint8))))
+    par = {"M": M, "I": I}
+    par.update(cols)
+    return par, flags, reclen
+
+
+def readpar_b200(filename, νmin=0, νmax=np.inf, Scut=0, I=(), maxlines=-1, ctx=None):
+    """readpar (par.jl:91-193) with the parse loop on the GPU.  "I" is returned as the isotopologue character like
+    readpar does; every numeric column is bit-identical to the host parser."""
+    base = filename[:-3] if filename.endswith(".gz") else filename
+    assert base.endswith(".par"), "expected file with .par extension, downloaded from https://hitran.org/lbl/"
+    op = gzip.open if filename.endswith(".gz") else open
+    with op(filename, "rb") as f:
+        buf = f.read()
+    par, flags, reclen = parse_records_b200(buf, ctx)
+    if flags.any():
+        raise ValueError(f"{int(flags.sum())} malformed record(s) in {filename}, first at line {int(np.argmax(flags)) + 1}")
+    N = len(par["ν"])
+    inv = {v: k for k, v in ISOINDEX.items()}
+    par["I"] = np.array([inv[int(i)] for i in par["I"]], dtype="U1")
+    mask = np.ones(N, dtype=bool)
+    mask &= par["ν"] >= νmin
+    mask &= par["ν"] <= νmax
+    mask &= par["S"] >= Scut
+    if len(I) > 0:
+        Iset = set(I)
+        keep = np.array([(ch in Iset) or (ISOINDEX[ch] in Iset) for ch in par["I"]])
+        mask &= keep
+    assert mask.any(), "par information has been filtered to nothing!"
+    for key in par:
+        par[key] = par[key][mask]
+    if maxlines > 0 and N > maxlines:
+        idx = np.argsort(par["S"], kind="stable")[::-1][:maxlines]
+        for key in par:
+            par[key] = par[key][idx]
+    idx = np.argsort(par["ν"], kind="stable")
+    for key in par:
+        par[key] = par[key][idx]
+    return par
+
+
+def _fortran_f(x, w, d):
+    """Fw.d the way HITRAN files print it: drop the leading zero when the field is too narrow"""
+    s = f"{x:{w}.{d}f}"
+    if len(s) > w:
+        s = s.replace("0.", ".", 1) if s.lstrip("-").startswith("0.") else s
+    assert len(s) <= w, (x, w, d, s)
+    return s.rjust(w)
+
+
+def writepar(filename, sl, A=None, δa=None):
+    """write a SpectralLines object as 160-column HITRAN records (column map of par.jl:131-149), so that the same
+    synthetic line list can be fed to the reference's readpar.  Quantum-number columns are blank."""
+    inv = {v: k for k, v in ISOINDEX.items()}
+    op = gzip.open if filename.endswith(".gz") else open
+    with op(filename, "wt") as f:
+        for j in range(sl.N):
+            rec = (f"{sl.M:2d}{inv[int(sl.I[j])]}{sl.ν[j]:12.6f}{sl.S[j]:10.3E}{(A[j] if A is not None else 0.0):10.3E}"
+                   f"{_fortran_f(sl.γa[j], 5, 4)}{_fortran_f(sl.γs[j], 5, 3)}{sl.Epp[j]:10.4f}{sl.na[j]:4.2f}"
+                   f"{_fortran_f(δa[j] if δa is not None else 0.0, 8, 6)}")
+            assert len(rec) == 67, (len(rec), rec)
+            f.write(rec.ljust(160) + "\n")

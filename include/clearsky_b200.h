@@ -178,6 +178,17 @@ int32_t cs_fluxes_device(cs_sigma* sig, int64_t np, const double* P, int32_t nlo
 int32_t cs_opticaldepth(cs_sigma* sig, int64_t np, const double* P, int32_t nlob, const double* wlob,
                         const double* mu, double g, double theta, double* tau_total);
 
+/* ---- HITRAN .par ingestion on the GPU (the step BEFORE the path; readpar's parse loop, src/hitran/par.jl:127-152) ----
+ * text = the file's bytes, nrec fixed-width records of reclen bytes each (160 columns + line terminator), column map
+ * of par.jl:131-140.  Outputs (host, nrec each, FILE order -- filtering/sorting stay with the caller exactly like
+ * readpar's vector operations): M (molecule number), I (ISOINDEX of the isotopologue character, par.jl:6-13), nu, S, A,
+ * gamma_a, gamma_s, Epp, na, delta_a.  Decimal -> binary64 conversion is correctly rounded (bit-identical to
+ * parse(Float64, .)): exact one-operation path for |decimal exponent| <= 22, double-double otherwise; flags[i] != 0
+ * marks a record with a malformed field (the caller re-parses or rejects it). */
+int32_t cs_par_parse(cs_ctx* ctx, int64_t nbytes, const char* text, int32_t reclen, int64_t nrec, int16_t* M, int16_t* I,
+                     double* nu, double* S, double* A, double* gamma_a, double* gamma_s, double* Epp, double* na,
+                     double* delta_a, uint8_t* flags);
+
 /* ---- single-process multi-GPU: nu-sharded runs from ONE host process --------------------
  * A group owns one context per device and a single-node NCCL communicator (libnccl.so.2 is dlopen'ed on first use).
  * The host shards nu contiguously, drives each device's cs_* calls from its own thread (every call only blocks its
