@@ -313,6 +313,7 @@ int32_t fluxes_impl(cs_sigma* s, int64_t np, const double* P, int32_t nlob, cons
     a.Mdn_out = Mdn ? ctx->s_out2.as<double>() : nullptr;
     a.part = ctx->s_part.as<double>();
     size_t smem = sizeof(double) * (small.size() + (size_t)2 * np * RT_WARPS);
+    CS_REQUIRE(smem <= 200 * 1024, CS_ERR_ARG, "too many pressure levels for one flux call (%lld): per-CTA tables need %zu bytes", (long long)np, smem);
 
     CS_CUDA(cudaEventRecord(ctx->ev0, st));
     switch (nstream) {

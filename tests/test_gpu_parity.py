@@ -550,3 +550,62 @@ def test_par_ingestion_bit_exact(cs, tmp_path):
     for k in ("ν", "S", "γa", "γs", "Epp", "na"):
         assert np.array_equal(getattr(back, k), getattr(sl, k)), k
     assert np.array_equal(getattr(cs.SpectralLines.from_file(fn), "S"), sl.S)
+
+
+def test_extreme_cutoffs_and_sizes(cs, orc, co2):
+    """cut-off 0 (only exact coincidences count), a cut-off wider than the whole line list (every line is an interior
+    line for every tile), many levels in one call, a one-line list, many pressure levels in the flux solver"""
+    νl = co2.ν[(co2.ν > 660) & (co2.ν < 670)]
+    ν = np.unique(np.concatenate([np.linspace(660, 670, 500), νl[:40]]))
+    T, P = [250.0], [3e4]
+    for cut in (0.0, 1e-3, 1e6):
+        for shape, sid in (("voigt", 2), ("lorentz", 1), ("doppler", 0), ("PHCO2", 3)):
+            got = cs.xsec(shape, ν, co2, T, P, [12.0], cut)
+            ref = orc.xsec(sid, co2, ν, T, P, [12.0], cut)
+            assert relerr(got, ref, 1e-290) < XSEC_TOL, (cut, shape)
+    # 257 levels in one call
+    Pn = cs.pressuregrid(10.0, 1e5, 257)
+    Tn = np.linspace(150.0, 300.0, 257)
+    ν2 = np.linspace(600.0, 760.0, 333)
+    got = cs.xsec("voigt", ν2, co2, Tn, Pn, 400e-6 * Pn, 25.0)
+    ref = orc.xsec(orc.VOIGT, co2, ν2, Tn, Pn, 400e-6 * Pn, 25.0, nthreads=0)
+    assert relerr(got, ref, 1e-290) < XSEC_TOL
+    # one line
+    one = cs.SpectralLines(co2.name, co2.formula, 1, co2.M, co2.I[3000:3001], co2.μ[3000:3001], co2.A[3000:3001],
+                           co2.ν[3000:3001], co2.S[3000:3001], co2.γa[3000:3001], co2.γs[3000:3001], co2.Epp[3000:3001],
+                           co2.na[3000:3001])
+    ν3 = co2.ν[3000] + np.linspace(-30, 30, 1201)
+    assert relerr(cs.xsec("voigt", ν3, one, [200.0], [100.0], [0.04], 25.0),
+                  orc.xsec(orc.VOIGT, one, ν3, [200.0], [100.0], [0.04], 25.0), 1e-300) < XSEC_TOL
+    # 401 pressure levels through the flux solver
+    P4 = cs.pressuregrid(10.0, 1e5, 401)
+    Γ = cs.DryAdiabat(288.0, 1e5, 1040.0, 0.029, Ptropo=1e4)
+    gray = cs.GrayGas(3e-26, ν2)
+    Fup, Fdn = cs.fluxes(P4, 9.8, Γ, 0.029, None, None, gray)
+    m, W = cs.streamnodes(5)
+    x, w = cs.lobattonodes(2)
+    ref = orc.fluxes(ν2, P4, 2, w, np.full((400, 2), 0.029), Γ(P4), np.full((401, len(ν2)), 3e-26), 9.8, None, None, 0.841, 5, m, W,
+                     full=False)
+    assert relerr(Fup, ref["Fup"]) < FLUX_TOL and relerr(Fdn[1:], ref["Fdn"][1:]) < FLUX_TOL
+
+
+def test_bench_line_contract(cs):
+    """bench.py prints ONE JSON line with the keys the driver reads (small workload, N = 1)"""
+    import json
+    import subprocess
+    import sys
+    from conftest import ROOT
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--workload", "c2small", "--steps", "2", "--warmup", "3",
+                          "--cpu-evals", "2e8"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
+        assert k in d, k
+    assert d["dtype"] == "f64" and d["n_gpus"] == 1 and d["gpu_launches"] > 0 and d["value"] > 0
+    assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(d["roofline"])
+    assert set(("value", "unit", "cores", "kind", "sample")) <= set(d["cpu_baseline"])
+    assert set(("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")) <= set(d["e2e"]) and d["e2e"]["h2d_bytes_per_step"] > 0
+    assert "workload" in d["config"]
