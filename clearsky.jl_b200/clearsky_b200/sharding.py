@@ -119,7 +119,10 @@ class ShardedLineByLine:
     per-device Σ workspaces are done once; every `fluxes` call is then K1/K2 + K6/K7 per device (one host thread
     each) and one all-reduce.   gases: list of (SpectralLines, fC, shape, Δνcut)."""
 
-    def __init__(self, group, gases, ν):
+    def __init__(self, group, gases, ν, cia=()):
+        """cia: iterable of (CIATables, i, j) pairing the tables with gases[i] and gases[j]
+        (CIA functor, collision_induced_absorption.jl:431-465)"""
+        self.cia = list(cia)
         self.group = group
         self.ν = f64(np.asarray(ν, dtype=np.float64))
         assert np.all(np.diff(self.ν) > 0), "wavenumbers must be unique and in ascending order"
@@ -138,6 +141,11 @@ class ShardedLineByLine:
             ctx = group.ctx[i]
             lg = [LineGas(slice_lines(sl, νs[0], νs[-1], cut), fC, νs, shape, cut, ctx=ctx) for sl, fC, shape, cut in self.gases]
             self.parts.append(dict(a=a, b=b, ν=νs, gases=lg, ws={}, w=np.ascontiguousarray(self.wg[a:b])))
+        self._pairs = []
+        for x, i, j in self.cia:
+            assert self.gases[i][0].formula in x.formulae and self.gases[j][0].formula in x.formulae, \
+                f"gases do not match the {x.name} CIA tables"
+            self._pairs.append((x, i, j))
 
     def fluxes(self, P, g, T, μ, fS=None, fa=None, core=None, θs=0.841):
         core = core or Discretized()
@@ -173,6 +181,10 @@ class ShardedLineByLine:
                 ws.zero()
             for lg in part["gases"]:
                 lg.add_to(ws, Tn, Pq)
+            for x, gi, gj in self._pairs:
+                C1 = f64(part["gases"][gi].concentration(Tn, Pq))
+                C2 = f64(part["gases"][gj].concentration(Tn, Pq))
+                check(lib().cs_sigma_add_cia(ws.h, x.handle(ctx), ptr(Tn), ptr(Pq), ptr(C1), ptr(C2)))
             check(lib().cs_fluxes_device(ws.h, npl, ptr(P), core.nlobatto, ptr(wl), ptr(μl), ptr(Tlev), float(g),
                                          ptr(np.ascontiguousarray(fSν[a:b])) if fSν is not None else None,
                                          ptr(np.ascontiguousarray(faν[a:b])) if faν is not None else None,

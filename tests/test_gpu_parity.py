@@ -476,6 +476,27 @@ def test_single_process_device_group(cs, orc, co2):
     grp.close()
 
 
+def test_single_process_device_group_with_cia(cs, co2):
+    """config-3 flavour through cs_group: PHCO2 line gas + CO2-CO2 CIA on every slice; equals the unsharded run"""
+    ν = np.linspace(20.0, 1500.0, 3001)
+    P = cs.pressuregrid(10.0, 2e5, 12)
+    Γ = cs.DryAdiabat(250.0, 2e5, 770.0, 0.044, Ptropo=1e4)
+    x = cs.CIATables(os.path.join(DATA, "CO2-CO2_2018.cia.gz"), extrapolate=True)
+    ndev = cs.device_count()
+    grp = cs.DeviceGroup([i % ndev for i in range(3)])
+    sh = cs.ShardedLineByLine(grp, [(co2, 1.0, "PHCO2", 500.0)], ν, cia=[(x, 0, 0)])
+    Fup, Fdn, Fnet = sh.fluxes(P, 3.71, Γ, 0.044)
+    gas = cs.LineGas(co2, 1.0, ν, "PHCO2", 500.0)
+    F = cs.radiate(P, 3.71, Γ, 0.044, None, None, gas, cs.CIA(x, gas, gas))
+    assert relerr(Fup, F.Fup) < 1e-12 and relerr(Fdn[1:], F.Fdn[1:]) < 1e-12
+    nocia = cs.radiate(P, 3.71, Γ, 0.044, None, None, gas)
+    assert relerr(nocia.Fup[:1], F.Fup[:1]) > 1e-4          # the CIA term is not a no-op
+    with pytest.raises(AssertionError):
+        cs.ShardedLineByLine(grp, [(co2, 1.0, "PHCO2", 500.0)], ν,
+                             cia=[(cs.CIATables(os.path.join(DATA, "CO2-CH4_2018.cia.gz")), 0, 0)])
+    grp.close()
+
+
 def test_line_params_and_functors(cs, orc, co2):
     """vector forms of scaleintensity / αdoppler / γlorentz (line_shapes.jl:125-132,146-148,259-261), the Gas and
     UnifiedAbsorber functors (gases.jl:256-281, absorbers.jl:97-99) and the CIATables functor / cia()"""

@@ -45,6 +45,26 @@ def c3(small):
             "algorithmic_tflops": 16.0 * evals / (ls * 1e-3) / 1e12 if ls else None}
 
 
+def c3sharded(small):
+    """C3 nu-sharded over all visible GPUs from one process (cs_group + NCCL all-reduce)"""
+    n, nν = (20_000, 12_000) if small else (500_000, 300_000)
+    co2 = bench.synthetic_lines(cs, n, 20261019 + 1, 2, (0.06, 0.13))
+    ν = 0.01 * np.arange(1, nν + 1) * (300_000 / nν)
+    P = cs.pressuregrid(10.0, 2e5, 101)
+    Γ = cs.DryAdiabat(250.0, 2e5, 770.0, 0.044, Ptropo=1e4)
+    x = cs.CIATables(os.path.join(ROOT, "tests", "data", "CO2-CO2_2018.cia.gz"), extrapolate=True)
+    grp = cs.DeviceGroup()
+    sh = cs.ShardedLineByLine(grp, [(co2, 1.0, "PHCO2", 500.0)], ν, cia=[(x, 0, 0)])
+    evals = sum(p["gases"][0].evals_per_node() for p in sh.parts if p is not None) * len(P)
+    ts = []
+    for it in range(3):
+        t0 = time.perf_counter()
+        Fup, Fdn, Fnet = sh.fluxes(P, 3.71, Γ, 0.044)
+        ts.append(time.perf_counter() - t0)
+    return {"config": "c3-sharded", "n_gpus": len(grp), "lines": n, "n_nu": nν, "levels": len(P), "evals": evals,
+            "s_per_spectrum": min(ts[1:]), "evals_per_s": evals / min(ts[1:]), "olr": float(Fup[0])}
+
+
 def c4(small):
     """OpacityTable build: 50 T x 50 P x 1e6 nu for CO2 and H2O, then interpolated sweep at 101 levels"""
     n, nν, nT, nP = (20_000, 40_000, 12, 12) if small else (250_000, 1_000_000, 50, 50)
@@ -121,4 +141,4 @@ def par(small):
 if __name__ == "__main__":
     which = sys.argv[1]
     small = "--small" in sys.argv
-    print(json.dumps({"c3": c3, "c4": c4, "c5": c5, "par": par}[which](small)))
+    print(json.dumps({"c3": c3, "c3sharded": c3sharded, "c4": c4, "c5": c5, "par": par}[which](small)))
