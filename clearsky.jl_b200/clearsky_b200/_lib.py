@@ -10,6 +10,8 @@ import numpy as np
 
 CS_OK, CS_ERR_CUDA, CS_ERR_ARG, CS_ERR_NOMEM, CS_ERR_DOMAIN = 0, 1, 2, 3, 4
 CS_DOPPLER, CS_LORENTZ, CS_VOIGT, CS_PHCO2 = 0, 1, 2, 3
+CS_FARFIELD_DIRECT, CS_FARFIELD_EXPANSION = 0, 1
+FARFIELD_MODES = {"direct": CS_FARFIELD_DIRECT, "expansion": CS_FARFIELD_EXPANSION}
 CS_MAXCHEB = 16
 CS_NTIMERS = 8
 TIMER_NAMES = ("prep", "linesum", "table_fit", "table_eval", "cia", "rt", "reduce", "total")
@@ -31,6 +33,8 @@ SIGNATURES = {
     "cs_ctx_synchronize": [_vp],
     "cs_ctx_timers": [_vp, _dp],
     "cs_ctx_launches": [_vp, _i64p],
+    "cs_ctx_set_farfield": [_vp, C.c_int32],
+    "cs_ctx_get_farfield": [_vp, C.POINTER(C.c_int32)],
     "cs_fp64_peak": [_vp, C.c_int32, _dp],
     "cs_lines_upload": [_vp, C.c_int64, _dp, _dp, _dp, _dp, _dp, _dp, _dp, C.POINTER(C.c_int16), C.c_int32,
                         C.POINTER(C.c_int32), _dp, C.POINTER(C.c_uint8), C.POINTER(_vp)],
@@ -156,6 +160,16 @@ class Context:
 
     def synchronize(self):
         check(lib().cs_ctx_synchronize(self.h))
+
+    def set_farfield(self, mode):
+        """far-wing treatment of the Voigt / Lorentz line sum: "direct" (every pair, like surf!) or "expansion"
+        (local Taylor expansion of well-separated far-wing lines, truncation < 3e-11; see clearsky_b200.h)"""
+        check(lib().cs_ctx_set_farfield(self.h, FARFIELD_MODES[mode] if isinstance(mode, str) else int(mode)))
+
+    def get_farfield(self):
+        m = C.c_int32(0)
+        check(lib().cs_ctx_get_farfield(self.h, C.byref(m)))
+        return {v: k for k, v in FARFIELD_MODES.items()}[m.value]
 
     def fp64_peak(self, iters=20000):
         v = C.c_double(0)

@@ -1,5 +1,7 @@
 // cs_api.cu -- C ABI entry points: context, lines, cross-sections, sigma workspace.
 #include "cs_internal.cuh"
+#include <cstdlib>
+#include <cstring>
 #include <stdarg.h>
 #include <algorithm>
 #include <limits>
@@ -61,6 +63,8 @@ static int32_t ctx_create(int32_t device, void* stream, bool own, cs_ctx** out)
         c->stream = (cudaStream_t)stream;
     }
     c->own_stream = own;
+    if (const char* ff = getenv("CS_FARFIELD"))
+        c->farfield = (strcmp(ff, "expansion") == 0) ? CS_FARFIELD_EXPANSION : CS_FARFIELD_DIRECT;
     {
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -113,6 +117,22 @@ extern "C" int32_t cs_ctx_launches(cs_ctx* c, int64_t* n)
 {
     CS_REQUIRE(c && n, CS_ERR_ARG, "null argument");
     *n = c->launches;
+    return CS_OK;
+}
+
+extern "C" int32_t cs_ctx_set_farfield(cs_ctx* c, int32_t mode)
+{
+    CS_REQUIRE(c, CS_ERR_ARG, "null argument");
+    CS_REQUIRE(mode == CS_FARFIELD_DIRECT || mode == CS_FARFIELD_EXPANSION, CS_ERR_ARG, "unknown far-field mode %d", mode);
+    std::lock_guard<std::recursive_mutex> lk(c->mtx);
+    c->farfield = mode;
+    return CS_OK;
+}
+
+extern "C" int32_t cs_ctx_get_farfield(cs_ctx* c, int32_t* mode)
+{
+    CS_REQUIRE(c && mode, CS_ERR_ARG, "null argument");
+    *mode = c->farfield;
     return CS_OK;
 }
 

@@ -98,6 +98,7 @@ struct cs_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
     double last_kernel_ms[CS_NTIMERS] = {0};
     int64_t launches = 0;   // number of kernels of this library launched on this context
+    int32_t farfield = CS_FARFIELD_DIRECT;   // K2 far-wing treatment (cs_ctx_set_farfield)
 };
 
 struct cs_lines {

@@ -40,6 +40,8 @@ constexpr int LS_THREADS = LS_WARPS * 32;
 constexpr int LS_CHUNK = 64;                      // lines per shared-memory stage (2 KB), one ring per warp
 constexpr int LS_STAGES = 4;
 constexpr int LS_QCAP = 256;                      // per-warp queue of evaluations that need the general routine
+constexpr int MP_P = 20;                          // order of the far-field expansion
+constexpr double MP_THETA = 4.0;                  // separation (in half tile widths) beyond which lines are expanded
 
 struct LevelParams {
     double T, P, Pp, scale;
@@ -179,8 +181,9 @@ struct LineSumArgs {
     double* out;            // [nlev][nnu]
     int accumulate;         // 0: out = scale*sigma (surf! overwrites), 1: out += scale*sigma
     int64_t ntiles;
-    int nr;                 // entries per tile in ranges (6, or LS_NR for PHCO2)
+    int nr;                 // entries per tile in ranges (6, 8 with the far-field expansion, or LS_NR for PHCO2)
     const int64_t* ranges;  // [ntiles][nr], see tile_ranges_kernel
+    double mp_theta;        // > 0: far-field expansion for lines farther than mp_theta half tile widths (Voigt, Lorentz)
 };
 
 // Voigt evaluation of one (line, point) that is not safely in the far wing: decides the region exactly like
@@ -269,7 +272,7 @@ __device__ __forceinline__ double eval_checked(const double4 rc, double dnu, con
 constexpr int LS_NR = 18;   // entries per tile (6 general + 12 PHCO2 chi-class boundaries)
 __global__ void tile_ranges_kernel(const double* __restrict__ nu, int64_t nnu, const double* __restrict__ nul,
                                    int64_t nl, double cut, double cn, int tile_pts, int64_t ntiles, int nr,
-                                   int64_t* __restrict__ ranges)
+                                   double mp_theta, int64_t* __restrict__ ranges)
 {
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= ntiles * nr) return;
@@ -278,6 +281,14 @@ __global__ void tile_ranges_kernel(const double* __restrict__ nu, int64_t nnu, c
     int64_t i0 = tile * tile_pts, i1 = min(i0 + (int64_t)tile_pts, nnu);
     const double tmin = nu[i0], tmax = nu[i1 - 1];
     int64_t v;
+    if (nr == 8 && k >= 6) {
+        // far-field expansion borders: lines at least mp_theta half-widths away from the tile centre
+        const double cen = 0.5 * (tmin + tmax), D = mp_theta * (0.5 * (tmax - tmin));
+        if (k == 6) v = first_false(nul, 0, nl, [=](double x) { return x <= cen - D; });
+        else        v = first_false(nul, 0, nl, [=](double x) { return x < cen + D; });
+        ranges[t] = v;
+        return;
+    }
     switch (k) {
     case 0: v = first_false(nul, 0, nl, [=](double x) { return (tmin - x) > cut; }); break;
     case 1: v = first_false(nul, 0, nl, [=](double x) { return !((x - tmax) > cut); }); break;
@@ -460,6 +471,8 @@ __global__ void __launch_bounds__(LS_THREADS, 16 / LS_WARPS) line_sum_kernel(Lin
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[LS_WARPS][LS_STAGES];
+    __shared__ int64_t seg_tab[LS_WARPS][10];
+    __shared__ int seg_cnt[LS_WARPS][5];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int lev = blockIdx.y;
@@ -495,16 +508,45 @@ __global__ void __launch_bounds__(LS_THREADS, 16 / LS_WARPS) line_sum_kernel(Lin
     // edge lines are normally ~cut-off away from every point, i.e. far wing; only when the near-centre range
     // reaches into the edge classes (tiny cut-offs, very coarse grids) do they need the per-evaluation region test
     w.edge_is_far = (SHAPE == CS_LORENTZ) || (SHAPE == CS_VOIGT && nlo >= ilo && nhi <= ihi && ilo < ihi);
-    if (SHAPE == CS_LORENTZ) { nlo = ilo; nhi = ilo; }   // no near-centre branch
+    // far-field expansion (Voigt far wing and Lorentz only): lines [ilo,mlo) and [mhi,ihi) are summed through a local
+    // Taylor expansion about the tile centre instead of point by point
+    const bool mp = (SHAPE == CS_VOIGT || SHAPE == CS_LORENTZ) && a.mp_theta > 0.0 && a.nr >= 8;
+    int64_t mlo = ilo, mhi = ihi;
+    if (mp) { mlo = min(max(rg[6], ilo), ihi); mhi = min(max(rg[7], mlo), ihi); }
+    if (SHAPE == CS_LORENTZ) { nlo = mlo; nhi = mlo; }   // no near-centre branch (empty range at the start of the direct lines)
     nlo = min(max(nlo, ilo), ihi);
     nhi = min(max(nhi, nlo), ihi);
-    const int nchunk = (int)((whi - wlo + LS_CHUNK - 1) / LS_CHUNK);
+    if (mp) { mlo = min(mlo, nlo); mhi = max(mhi, nhi); }   // never expand lines of the near-centre range
+    // segments streamed through the ring, in this order; a chunk never spans two segments.
+    //   expansion: [ilo,mlo) [mhi,ihi)      direct: [wlo,ilo) [mlo,mhi) [ihi,whi)   (one direct segment [wlo,whi) without mp)
+    // (kept in shared memory: indexed dynamically by the chunk number, warp-uniform)
+    int64_t* slo = seg_tab[warp];
+    int64_t* shi = seg_tab[warp] + 5;
+    int* sch = seg_cnt[warp];
+    if (lane == 0) {
+        slo[0] = ilo; shi[0] = mp ? mlo : ilo;
+        slo[1] = mhi; shi[1] = mp ? ihi : mhi;
+        slo[2] = wlo; shi[2] = mp ? ilo : whi;
+        slo[3] = mlo; shi[3] = mp ? mhi : mlo;
+        slo[4] = ihi; shi[4] = mp ? whi : ihi;
+        for (int q = 0; q < 5; q++) sch[q] = (int)((shi[q] - slo[q] + LS_CHUNK - 1) / LS_CHUNK);
+    }
+    __syncwarp();
+    const int nchunkA = sch[0] + sch[1];
+    const int nchunk = nchunkA + sch[2] + sch[3] + sch[4];
     const double4* rec_lev = a.rec + (size_t)lev * a.nl;
+    auto chunk_bounds = [&](int c, int64_t& c0, int64_t& c1) {
+        int q = 0;
+        while (q < 4 && c >= sch[q]) { c -= sch[q]; q++; }
+        c0 = slo[q] + (int64_t)c * LS_CHUNK;
+        c1 = min(c0 + (int64_t)LS_CHUNK, shi[q]);
+    };
 
     auto issue = [&](int c) {   // lane 0 only
         int s = c % LS_STAGES;
-        int64_t c0 = wlo + (int64_t)c * LS_CHUNK;
-        uint32_t bytes = (uint32_t)min((int64_t)LS_CHUNK, whi - c0) * (uint32_t)sizeof(double4);
+        int64_t c0, c1;
+        chunk_bounds(c, c0, c1);
+        uint32_t bytes = (uint32_t)(c1 - c0) * (uint32_t)sizeof(double4);
         mbar_arrive_expect_tx(&full_bar[warp][s], bytes);
         tma_bulk_g2s(ring + (size_t)s * LS_CHUNK, rec_lev + c0, bytes, &full_bar[warp][s]);
     };
@@ -555,11 +597,72 @@ __global__ void __launch_bounds__(LS_THREADS, 16 / LS_WARPS) line_sum_kernel(Lin
         __syncwarp();
     }
 
-    for (int c = 0; c < nchunk; c++) {
+    // ---- phase A: far-field expansion.  For a line at u = nul - cen (|u| >= theta*h) and t = (nu - cen)/h in [-1,1]
+    //   K/((h t - u)^2 + g^2) = sum_k c_k t^k,  c_0 = K/q0,  c_1 = al c_0,  c_k = al c_{k-1} - be c_{k-2},
+    //   q0 = u^2 + g^2, al = 2 u h/q0, be = h^2/q0   (generating function of the Chebyshev polynomials U_k);
+    // |c_k| <= (k+1) theta^-k c_0, so MP_P = 20 terms at theta = 4 truncate below 3e-11 of each line's own value
+    // (all terms of the sum are positive, so that also bounds the relative error of the sum).  A lane sums the
+    // coefficients of every 32nd line (3 FP64 ops per coefficient), a butterfly reduces them over the warp, and every
+    // point then costs MP_P FMAs (Horner) instead of 5.25 FP64 ops per line.
+    if (mp && nchunkA > 0) {
+        const double cen = 0.5 * (w.nutile[0] + a.nu[min(tile0 + TILE, a.nnu) - 1]);
+        const double h = 0.5 * (a.nu[min(tile0 + TILE, a.nnu) - 1] - w.nutile[0]);
+        const double h2 = h * h, twoh = 2.0 * h;
+        double am[MP_P];
+#pragma unroll
+        for (int k = 0; k < MP_P; k++) am[k] = 0.0;
+        for (int c = 0; c < nchunkA; c++) {
+            const int s = c % LS_STAGES;
+            const uint32_t ph = (c / LS_STAGES) & 1;
+            int64_t c0, c1;
+            chunk_bounds(c, c0, c1);
+            mbar_wait(&full_bar[warp][s], ph);
+            const double4* st = ring + (size_t)s * LS_CHUNK;
+            const int n = (int)(c1 - c0);
+            for (int jj = lane; jj < n; jj += 32) {
+                const double4 rc = st[jj];
+                const double u = rc.x - cen;
+                const double r = cs_rcp(fma(u, u, rc.y));
+                const double al = (u * r) * twoh, be = r * h2;
+                double ck2 = rc.z * r;
+                double ck1 = al * ck2;
+                am[0] += ck2;
+                am[1] += ck1;
+#pragma unroll
+                for (int k = 2; k < MP_P; k++) {
+                    double ck = fma(al, ck1, -(be * ck2));
+                    am[k] += ck;
+                    ck2 = ck1;
+                    ck1 = ck;
+                }
+            }
+            __syncwarp();
+            if (lane == 0 && c + LS_STAGES < nchunk) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                issue(c + LS_STAGES);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < MP_P; k++) {
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) am[k] += __shfl_xor_sync(0xffffffffu, am[k], off);
+        }
+        const double ih = h > 0.0 ? 1.0 / h : 0.0;
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const double t = (nup[r] - cen) * ih;
+            double v = am[MP_P - 1];
+#pragma unroll
+            for (int k = MP_P - 2; k >= 0; k--) v = fma(v, t, am[k]);
+            acc[r] = v;
+        }
+    }
+
+    for (int c = nchunkA; c < nchunk; c++) {
         const int s = c % LS_STAGES;
         const uint32_t ph = (c / LS_STAGES) & 1;
-        const int64_t c0 = wlo + (int64_t)c * LS_CHUNK;
-        const int64_t c1 = min(c0 + (int64_t)LS_CHUNK, whi);
+        int64_t c0, c1;
+        chunk_bounds(c, c0, c1);
         mbar_wait(&full_bar[warp][s], ph);
         const double4* st = ring + (size_t)s * LS_CHUNK;
         // chunk-local boundaries of the five classes: [0,xa) edge | [xa,xb) far | [xb,xc) near | [xc,xd) far | [xd,n) edge
@@ -726,11 +829,13 @@ template <int SHAPE, int R> int32_t launch_line_sum(cs_ctx* ctx, LineSumArgs a, 
     constexpr int TILE = 32 * R;
     cudaStream_t st = ctx->stream;
     a.ntiles = (a.nnu + TILE - 1) / TILE;
-    a.nr = (SHAPE == CS_PHCO2) ? LS_NR : 6;
+    if (!(SHAPE == CS_VOIGT || SHAPE == CS_LORENTZ)) a.mp_theta = 0.0;
+    a.nr = (SHAPE == CS_PHCO2) ? LS_NR : (a.mp_theta > 0.0 ? 8 : 6);
     CS_TRY(ctx->s_w.reserve(sizeof(int64_t) * a.nr * (size_t)a.ntiles));
     a.ranges = ctx->s_w.as<int64_t>();
     tile_ranges_kernel<<<(unsigned)((a.ntiles * a.nr + 127) / 128), 128, 0, st>>>(a.nu, a.nnu, a.nul, a.nl, a.cut, cn, TILE,
-                                                                                  a.ntiles, a.nr, ctx->s_w.as<int64_t>());
+                                                                                  a.ntiles, a.nr, a.mp_theta,
+                                                                                  ctx->s_w.as<int64_t>());
     CS_CUDA(cudaGetLastError());
     size_t smem = (size_t)LS_WARPS * (LS_STAGES * LS_CHUNK * sizeof(double4) + ls_extra_bytes<SHAPE, R>());
     if (smem > 48 * 1024)   // per device: not cached, several contexts may live on different GPUs
@@ -885,6 +990,7 @@ int32_t cs_lines_accumulate(cs_lines* L, int32_t shape, int64_t nnu, const doubl
         la.nu = d_nu; la.nnu = nnu; la.nul = L->nu + j0; la.nl = nl;
         la.rec = pa.rec; la.slow = pa.slow; la.lev = pa.lev; la.cut = cut;
         la.out = d_out + (size_t)k0 * nnu; la.accumulate = accumulate;
+        la.mp_theta = ctx->farfield == CS_FARFIELD_EXPANSION ? MP_THETA : 0.0;
         double cn = 0.0;
         for (int64_t k = 0; k < kb; k++) cn = std::max(cn, hl[(size_t)k].cnear);
         switch (shape) {

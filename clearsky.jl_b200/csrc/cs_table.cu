@@ -88,47 +88,106 @@ __global__ void __launch_bounds__(128) cheb_pass_kernel(const double* in, double
     }
 }
 
-// ---- K4: table evaluation at a block of LB levels.  basis[l][k] = T_i(xi_T(l)) * T_j(xi_P(l)).
-// Each thread owns one wavenumber and LB level accumulators in registers; the coefficient axis is streamed in
-// chunks of KC with the matching basis slab in shared memory (small footprint -> full occupancy).  Every
-// coefficient is read ceil(nlev/LB) times, so LB = 32 keeps a 101-level sweep of a 50 x 50 table near its FP64
-// floor instead of its HBM floor.
+// ---- K4: table evaluation, out[l][nu] = exp( sum_j Tp_j(l) * sum_i coef[i + nT*j][nu] * Tt_i(l) ).
+// FP64-FMA bound (2*nT*nP flop per (nu, level)); the coefficient block is read from HBM ONCE per block of
+// up to 128 levels.  CTA = G warps that share 64 wavenumbers (a lane owns nu and nu+32: one shared-memory operand
+// feeds two FMAs); warp g owns levels [g*LB, (g+1)*LB) of the CTA's level block, so the G warps read the same
+// coefficient rows and hit L1.  The 1-D Chebyshev values Tt[i][l], Tp[j][l] of the block live in shared memory
+// ((nT+nP)*G*LB doubles); coefficients are prefetched U rows ahead in registers.  The inner sum over i runs in
+// tmp[], folded into acc[] once per j (nP extra FMAs per level: +1/nT).
 // mode 0: out[l][nu] = exp(.)           (rawsigma, gases.jl:85,256)
 // mode 1: out[l][nu] += C[l]*exp(.)     (Gas functor, gases.jl:278)
-constexpr int TE_KC = 64;
-template <int LB>
-__global__ void __launch_bounds__(128) table_eval_kernel(const double* __restrict__ coef, int64_t nnu, int nk,
-                                                         const double* __restrict__ basis, const double* __restrict__ C,
-                                                         int nlev, double* out, int mode)
+template <int LB, int U>
+__global__ void __launch_bounds__(LB == 8 ? 512 : 352) table_eval_kernel(const double* __restrict__ coef, int64_t nnu, int nT, int nP,
+                                                         const double* __restrict__ Tt, const double* __restrict__ Tp,
+                                                         const double* __restrict__ C, int nlev, int lpb, double* out,
+                                                         int mode)
 {
-    __shared__ __align__(16) double sb[TE_KC * LB];   // [k][l]
-    const int l0 = blockIdx.y * LB;
-    const int64_t vraw = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t v = vraw < nnu ? vraw : nnu - 1;
-    double acc[LB];
-#pragma unroll
-    for (int l = 0; l < LB; l++) acc[l] = 0.0;
-    for (int k0 = 0; k0 < nk; k0 += TE_KC) {
-        const int kc = min(TE_KC, nk - k0);
-        __syncthreads();
-        for (int t = threadIdx.x; t < kc * LB; t += blockDim.x) {
-            int k = t / LB, l = t % LB;
-            sb[t] = (l0 + l < nlev) ? basis[(size_t)(l0 + l) * nk + k0 + k] : 0.0;
-        }
-        __syncthreads();
-        for (int k = 0; k < kc; k++) {
-            double a = coef[(size_t)(k0 + k) * nnu + v];
-#pragma unroll
-            for (int l = 0; l < LB; l++) acc[l] = fma(a, sb[k * LB + l], acc[l]);
-        }
+    extern __shared__ __align__(16) double te_sm[];
+    const int G = blockDim.x >> 5, LC = G * LB;
+    double* sTt = te_sm;                 // [nT][LC]
+    double* sTp = te_sm + nT * LC;       // [nP][LC]
+    const int lb0 = blockIdx.y * lpb;    // first level of this CTA's block
+    const int lend = min(lb0 + lpb, nlev);
+    for (int t = threadIdx.x; t < nT * LC; t += blockDim.x) {
+        int i = t / LC, l = lb0 + t % LC;
+        sTt[t] = l < lend ? Tt[(size_t)l * nT + i] : 0.0;
     }
-    if (vraw >= nnu) return;
+    for (int t = threadIdx.x; t < nP * LC; t += blockDim.x) {
+        int j = t / LC, l = lb0 + t % LC;
+        sTp[t] = l < lend ? Tp[(size_t)l * nP + j] : 0.0;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t v0 = (int64_t)blockIdx.x * 64 + lane, v1 = v0 + 32;
+    const double* c0 = coef + (v0 < nnu ? v0 : nnu - 1);
+    const double* c1 = coef + (v1 < nnu ? v1 : nnu - 1);
+    const double* tt = sTt + warp * LB;
+    const double* tp = sTp + warp * LB;
+    const int nk = nT * nP;
+    double acc0[LB], acc1[LB], tmp0[LB], tmp1[LB];
+#pragma unroll
+    for (int l = 0; l < LB; l++) acc0[l] = acc1[l] = tmp0[l] = tmp1[l] = 0.0;
+    double a0[U], a1[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        a0[u] = u < nk ? c0[(size_t)u * nnu] : 0.0;
+        a1[u] = u < nk ? c1[(size_t)u * nnu] : 0.0;
+    }
+    int i = 0, j = 0;
+    for (int k0 = 0; k0 < nk; k0 += U) {
+        double b0[U], b1[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            int k = k0 + U + u;
+            b0[u] = k < nk ? c0[(size_t)k * nnu] : 0.0;
+            b1[u] = k < nk ? c1[(size_t)k * nnu] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (k0 + u < nk) {
+                const double2* t2 = reinterpret_cast<const double2*>(tt + i * LC);
+#pragma unroll
+                for (int l = 0; l < LB; l += 2) {
+                    double2 b = t2[l >> 1];
+                    tmp0[l] = fma(a0[u], b.x, tmp0[l]);
+                    tmp1[l] = fma(a1[u], b.x, tmp1[l]);
+                    tmp0[l + 1] = fma(a0[u], b.y, tmp0[l + 1]);
+                    tmp1[l + 1] = fma(a1[u], b.y, tmp1[l + 1]);
+                }
+                if (++i == nT) {
+                    const double2* p2 = reinterpret_cast<const double2*>(tp + j * LC);
+#pragma unroll
+                    for (int l = 0; l < LB; l += 2) {
+                        double2 b = p2[l >> 1];
+                        acc0[l] = fma(tmp0[l], b.x, acc0[l]);
+                        acc1[l] = fma(tmp1[l], b.x, acc1[l]);
+                        acc0[l + 1] = fma(tmp0[l + 1], b.y, acc0[l + 1]);
+                        acc1[l + 1] = fma(tmp1[l + 1], b.y, acc1[l + 1]);
+                        tmp0[l] = tmp1[l] = tmp0[l + 1] = tmp1[l + 1] = 0.0;
+                    }
+                    i = 0;
+                    j++;
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) { a0[u] = b0[u]; a1[u] = b1[u]; }
+    }
 #pragma unroll
     for (int l = 0; l < LB; l++) {
-        if (l0 + l < nlev) {
-            size_t o = (size_t)(l0 + l) * nnu + v;
-            double s = exp(acc[l]);
-            out[o] = mode ? out[o] + C[l0 + l] * s : s;
+        const int lev = lb0 + warp * LB + l;
+        if (lev < lend) {
+            if (v0 < nnu) {
+                size_t o = (size_t)lev * nnu + v0;
+                double s = exp(acc0[l]);
+                out[o] = mode ? out[o] + C[lev] * s : s;
+            }
+            if (v1 < nnu) {
+                size_t o = (size_t)lev * nnu + v1;
+                double s = exp(acc1[l]);
+                out[o] = mode ? out[o] + C[lev] * s : s;
+            }
         }
     }
 }
@@ -285,14 +344,14 @@ int32_t fit_table(cs_ctx* ctx, cs_table* tb, double* d_block)
     unsigned nb = (unsigned)((nnu + 255) / 256);
     table_log_kernel<<<nb, 256, 0, st>>>(d_block, nnu, nk, (unsigned long long*)(base + offc));
     CS_CUDA(cudaGetLastError());
-    // pass along T: block -> coef ; pass along ln P: coef -> block ; final copy back into coef
+    // pass along T in place (a thread reads its whole line of nT values before it writes any), then the pass along
+    // ln P from the block into coef: the block is read twice and written once, coef written once
     dim3 gA((unsigned)((nnu + 127) / 128), (unsigned)nP);
-    cheb_pass_kernel<<<gA, 128, sizeof(double) * nT * nT, st>>>(d_block, tb->coef, nnu, nT, nP, 0, (const double*)base);
+    cheb_pass_kernel<<<gA, 128, sizeof(double) * nT * nT, st>>>(d_block, d_block, nnu, nT, nP, 0, (const double*)base);
     CS_CUDA(cudaGetLastError());
     dim3 gB((unsigned)((nnu + 127) / 128), (unsigned)nT);
-    cheb_pass_kernel<<<gB, 128, sizeof(double) * nP * nP, st>>>(tb->coef, d_block, nnu, nT, nP, 1, (const double*)(base + offy));
+    cheb_pass_kernel<<<gB, 128, sizeof(double) * nP * nP, st>>>(d_block, tb->coef, nnu, nT, nP, 1, (const double*)(base + offy));
     CS_CUDA(cudaGetLastError());
-    CS_CUDA(cudaMemcpyAsync(tb->coef, d_block, sizeof(double) * (size_t)nk * nnu, cudaMemcpyDeviceToDevice, st));
     cs_count_launch(ctx, 3);
     CS_CUDA(cudaEventRecord(ctx->ev1, st));
     unsigned long long nz = 0;
@@ -326,10 +385,11 @@ int32_t eval_table(cs_table* tb, int64_t nlev, const double* T, const double* P,
 {
     cs_ctx* ctx = tb->ctx;
     cudaStream_t st = ctx->stream;
-    const int nT = tb->nT, nP = tb->nP, nk = nT * nP;
-    std::vector<double> basis((size_t)nlev * nk);
-    std::vector<double> ct((size_t)nT), cp((size_t)nP);
-    for (int64_t l = 0; l < nlev; l++) {
+    const int nT = tb->nT, nP = tb->nP;
+    std::vector<double> basis((size_t)nlev * (nT + nP));   // Tt[l][i] then Tp[l][j]
+    double* ct = basis.data();
+    double* cp = basis.data() + (size_t)nlev * nT;
+    for (int64_t l = 0; l < nlev; l++, ct += nT, cp += nP) {
         double lp = log(P[l]);
         // StrictBoundaries: out-of-domain coordinates are an error (gases.jl:85 via BichebyshevInterpolator)
         CS_REQUIRE(T[l] >= tb->Ta && T[l] <= tb->Tb, CS_ERR_DOMAIN,
@@ -339,26 +399,43 @@ int32_t eval_table(cs_table* tb, int64_t nlev, const double* T, const double* P,
         double xt = 2 * (T[l] - tb->Ta) / (tb->Tb - tb->Ta) - 1;
         double xp = 2 * (lp - tb->lnPa) / (tb->lnPb - tb->lnPa) - 1;
         ct[0] = 1; ct[1] = xt;
-        for (int k = 2; k < nT; k++) ct[(size_t)k] = 2 * xt * ct[(size_t)k - 1] - ct[(size_t)k - 2];
+        for (int k = 2; k < nT; k++) ct[k] = 2 * xt * ct[k - 1] - ct[k - 2];
         cp[0] = 1; cp[1] = xp;
-        for (int k = 2; k < nP; k++) cp[(size_t)k] = 2 * xp * cp[(size_t)k - 1] - cp[(size_t)k - 2];
-        for (int j = 0; j < nP; j++)
-            for (int i = 0; i < nT; i++) basis[(size_t)l * nk + i + (size_t)nT * j] = ct[(size_t)i] * cp[(size_t)j];
+        for (int k = 2; k < nP; k++) cp[k] = 2 * xp * cp[k - 1] - cp[k - 2];
     }
+    size_t offP = sizeof(double) * (size_t)nlev * nT;
     size_t offC = ((basis.size() * sizeof(double) + 255) / 256) * 256;
     CS_TRY(ctx->s_misc.reserve(offC + sizeof(double) * (size_t)nlev));
     char* base = ctx->s_misc.as<char>();
     CS_CUDA(cudaMemcpyAsync(base, basis.data(), basis.size() * sizeof(double), cudaMemcpyHostToDevice, st));
     if (C) CS_CUDA(cudaMemcpyAsync(base + offC, C, sizeof(double) * (size_t)nlev, cudaMemcpyHostToDevice, st));
     CS_CUDA(cudaEventRecord(ctx->ev0, st));
-    const int LB = nlev > 12 ? 32 : 8;
-    dim3 grid((unsigned)((tb->nnu + 127) / 128), (unsigned)((nlev + LB - 1) / LB));
-    if (LB == 32)
-        table_eval_kernel<32><<<grid, 128, 0, st>>>(tb->coef, tb->nnu, nk, (const double*)base, (const double*)(base + offC),
-                                                    (int)nlev, d_out, mode);
-    else
-        table_eval_kernel<8><<<grid, 128, 0, st>>>(tb->coef, tb->nnu, nk, (const double*)base, (const double*)(base + offC),
-                                                   (int)nlev, d_out, mode);
+    // level blocking: blocks of <= 128 levels (each re-reads the coefficients once); within a block G warps of LB
+    // levels each, LB from {8, 12} chosen for the least padding
+    const int nby = (int)((nlev + 127) / 128);
+    const int lpb = (int)((nlev + nby - 1) / nby);
+    int LB = 8, best = 1 << 30;
+    for (int cand : {8, 12}) {
+        int pad = ((lpb + cand - 1) / cand) * cand;
+        if (pad < best || (pad == best && cand > LB)) { best = pad; LB = cand; }
+    }
+    const int G = best / LB;
+    const size_t smem = sizeof(double) * (size_t)(nT + nP) * best;
+    dim3 grid((unsigned)((tb->nnu + 63) / 64), (unsigned)nby);
+    const double* dTt = (const double*)base;
+    const double* dTp = (const double*)(base + offP);
+    const double* dC = (const double*)(base + offC);
+#define CS_TE_LAUNCH(LBV)                                                                                             \
+    do {                                                                                                              \
+        if (smem > 48 * 1024)                                                                                         \
+            CS_CUDA(cudaFuncSetAttribute(table_eval_kernel<LBV, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                         (int)smem));                                                                 \
+        table_eval_kernel<LBV, 4><<<grid, 32 * G, smem, st>>>(tb->coef, tb->nnu, nT, nP, dTt, dTp, dC, (int)nlev, lpb, \
+                                                              d_out, mode);                                           \
+    } while (0)
+    if (LB == 8) CS_TE_LAUNCH(8);
+    else CS_TE_LAUNCH(12);
+#undef CS_TE_LAUNCH
     CS_CUDA(cudaGetLastError());
     cs_count_launch(ctx);
     CS_CUDA(cudaEventRecord(ctx->ev1, st));

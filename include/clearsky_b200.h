@@ -69,6 +69,20 @@ int32_t cs_ctx_synchronize(cs_ctx* ctx);
 /* timers[CS_NTIMERS] of the last compute call; launches = kernels launched so far on this context */
 int32_t cs_ctx_timers(cs_ctx* ctx, double* timers_ms);
 int32_t cs_ctx_launches(cs_ctx* ctx, int64_t* launches);
+/* Far-wing treatment of the windowed line sum (Voigt and Lorentz; PHCO2 and Doppler always sum directly).
+ *   CS_FARFIELD_DIRECT (default): every (nu, line) pair inside the cut-off is evaluated, as surf! does
+ *     (src/absorption/line_shapes.jl:53-87).
+ *   CS_FARFIELD_EXPANSION: lines that are inside the cut-off for ALL points of a 128-point tile, provably in the
+ *     far wing (where the reference's Voigt equals S*gamma/(pi*(dnu^2+gamma^2))) and at least 4 half tile widths
+ *     from the tile centre are summed through a 20-term local Taylor expansion about the tile centre; the
+ *     truncation error is below 3e-11 of each line's own contribution (all contributions are positive), i.e. two
+ *     orders inside the 1e-9 parity tolerance.  Everything else (cut-off edges, near lines, line centres) is
+ *     evaluated exactly as in the direct mode.
+ * The CS_FARFIELD environment variable ("direct" | "expansion") sets the default of new contexts. */
+#define CS_FARFIELD_DIRECT 0
+#define CS_FARFIELD_EXPANSION 1
+int32_t cs_ctx_set_farfield(cs_ctx* ctx, int32_t mode);
+int32_t cs_ctx_get_farfield(cs_ctx* ctx, int32_t* mode);
 /* sustained FP64 FMA rate of this device, measured with a register-resident DFMA loop [FLOP/s] */
 int32_t cs_fp64_peak(cs_ctx* ctx, int32_t iters, double* flops_per_s);
 

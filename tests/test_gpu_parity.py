@@ -54,6 +54,58 @@ def test_xsec_fine_grid_all_regions(cs, orc, name, sid, cut):
     assert relerr(got, ref, 1e-290) < XSEC_TOL
 
 
+@pytest.fixture
+def expansion(cs):
+    """switch the default context to the far-field expansion for one test"""
+    ctx = cs.default_context()
+    ctx.set_farfield("expansion")
+    assert ctx.get_farfield() == "expansion"
+    yield ctx
+    ctx.set_farfield("direct")
+
+
+@pytest.mark.parametrize("name,sid", [("lorentz", 1), ("voigt", 2)])
+def test_xsec_farfield_expansion(cs, orc, expansion, name, sid):
+    """CS_FARFIELD_EXPANSION: well-separated far-wing lines go through a 20-term local expansion; same parity bar
+    against the oracle (1e-9) and within 1e-10 of the direct mode, on uniform, ragged, gappy and irregular grids"""
+    sl = synthetic_lines(cs, 6000, seed=17, νmax=200.0)
+    rng = np.random.default_rng(5)
+    grids = [30.0 + 0.01 * np.arange(9000),                                    # 0.01 cm^-1, several tiles, ragged end
+             np.sort(rng.uniform(20.0, 180.0, 7001)),                           # irregular spacing
+             np.concatenate([np.linspace(40, 45, 777), np.linspace(120, 150, 2031)]),   # a gap inside a tile
+             30.0 + 2.5 * np.arange(60)]                                        # coarse: tiles wider than the cut-off
+    P = np.array([10.0, 5e3, 1e5, 5e5])
+    T = np.array([150.0, 230.0, 296.0, 320.0])
+    Pp = np.array([1e-3, 5.0, 5e4, 4e5])
+    for ν in grids:
+        got = cs.xsec(name, ν, sl, T, P, Pp, 25.0)
+        ref = orc.xsec(sid, sl, ν, T, P, Pp, 25.0, nthreads=0)
+        assert relerr(got, ref, 1e-290) < XSEC_TOL
+        expansion.set_farfield("direct")
+        direct = cs.xsec(name, ν, sl, T, P, Pp, 25.0)
+        expansion.set_farfield("expansion")
+        assert relerr(got, direct, 1e-290) < 1e-10
+    # tiny and huge cut-offs
+    for cut in (0.05, 1.0, 1e4):
+        ν = 60.0 + 0.01 * np.arange(3000)
+        got = cs.xsec(name, ν, sl, T[:2], P[:2], Pp[:2], cut)
+        ref = orc.xsec(sid, sl, ν, T[:2], P[:2], Pp[:2], cut, nthreads=0)
+        assert relerr(got, ref, 1e-290) < XSEC_TOL
+
+
+def test_fluxes_farfield_expansion(cs, orc, co2, expansion):
+    """C1 problem on a fine grid with the expansion on: fluxes within 1e-8 of the oracle and 1e-10 of the direct mode"""
+    ν = 600.0 + 0.01 * np.arange(12000)
+    P = cs.pressuregrid(10.0, 1e5, 21)
+    Γ = cs.DryAdiabat(288.0, 1e5, 1040.0, 0.029, Ptropo=1e4)
+    gas = cs.LineGas(co2, 400e-6, ν, "voigt", 25.0)
+    F = cs.radiate(P, 9.8, Γ, 0.029, None, None, gas)
+    expansion.set_farfield("direct")
+    Fd = cs.radiate(P, 9.8, Γ, 0.029, None, None, gas)
+    assert relerr(F.Fup, Fd.Fup) < 1e-10 and relerr(F.Fdn[1:], Fd.Fdn[1:]) < 1e-10
+    assert not np.array_equal(F.Mup, Fd.Mup)        # the expansion really was used
+
+
 def test_xsec_line_centres(cs, orc, co2):
     """evaluation points sitting exactly on / next to line centres at low pressure (Hui / Humlicek regions)"""
     νl = co2.ν[(co2.ν > 600) & (co2.ν < 760)][::7][:150]
@@ -483,7 +535,7 @@ def test_single_process_device_group_with_cia(cs, co2):
     Γ = cs.DryAdiabat(250.0, 2e5, 770.0, 0.044, Ptropo=1e4)
     x = cs.CIATables(os.path.join(DATA, "CO2-CO2_2018.cia.gz"), extrapolate=True)
     ndev = cs.device_count()
-    grp = cs.DeviceGroup([i % ndev for i in range(3)])
+    grp = cs.DeviceGroup(list(range(ndev)))      # NCCL needs distinct devices: one slice per visible GPU
     sh = cs.ShardedLineByLine(grp, [(co2, 1.0, "PHCO2", 500.0)], ν, cia=[(x, 0, 0)])
     Fup, Fdn, Fnet = sh.fluxes(P, 3.71, Γ, 0.044)
     gas = cs.LineGas(co2, 1.0, ν, "PHCO2", 500.0)
