@@ -19,6 +19,7 @@ from .line_shapes import (PHCO2, PHCO2_b200_inplace, DeviceLines, device_lines, 
 from .molparam import MOLPARAM, TMAX, TMIN
 from .par import SpectralLines, parse_records_b200, readpar, readpar_b200, writepar
 from .quadrature import lobattonodes, streamnodes
+from .radau import Radau, outgoing
 from .rcm import RCM
 from .sharding import DeviceGroup, ShardedLineByLine, sharded_fluxes
 from .util import AtmosphericProfile, chebygrid, pressuregrid, trapz

@@ -35,6 +35,7 @@ SIGNATURES = {
     "cs_ctx_launches": [_vp, _i64p],
     "cs_ctx_set_farfield": [_vp, C.c_int32],
     "cs_ctx_get_farfield": [_vp, C.POINTER(C.c_int32)],
+    "cs_ctx_set_tau_floor": [_vp, C.c_double],
     "cs_fp64_peak": [_vp, C.c_int32, _dp],
     "cs_lines_upload": [_vp, C.c_int64, _dp, _dp, _dp, _dp, _dp, _dp, _dp, C.POINTER(C.c_int16), C.c_int32,
                         C.POINTER(C.c_int32), _dp, C.POINTER(C.c_uint8), C.POINTER(_vp)],
@@ -165,6 +166,10 @@ class Context:
         """far-wing treatment of the Voigt / Lorentz line sum: "direct" (every pair, like surf!) or "expansion"
         (local Taylor expansion of well-separated far-wing lines, truncation < 3e-11; see clearsky_b200.h)"""
         check(lib().cs_ctx_set_farfield(self.h, FARFIELD_MODES[mode] if isinstance(mode, str) else int(mode)))
+
+    def set_tau_floor(self, τmin):
+        """floor on the vertical layer optical depth in the flux kernel (reference: 1e-6, discretized.jl:174)"""
+        check(lib().cs_ctx_set_tau_floor(self.h, float(τmin)))
 
     def get_farfield(self):
         m = C.c_int32(0)

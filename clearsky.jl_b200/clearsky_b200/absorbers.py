@@ -39,10 +39,15 @@ class SigmaWorkspace:
         check(lib().cs_sigma_read(self.h, ptr(out)))
         return out
 
+    def close(self):
+        # a workspace that outlives its context (a closed DeviceGroup) must not touch the freed cs_ctx
+        if self.h and self.ctx.h:
+            lib().cs_sigma_free(self.h)
+        self.h = C.c_void_p()
+
     def __del__(self):
         try:
-            if self.h:
-                lib().cs_sigma_free(self.h)
+            self.close()
         except Exception:
             pass
 
@@ -177,7 +182,7 @@ class AcceleratedAbsorber(AbstractAbsorber):
 
     def __del__(self):
         try:
-            if self.h:
+            if self.h and self._ws.ctx.h:
                 lib().cs_accel_free(self.h)
         except Exception:
             pass

@@ -133,8 +133,9 @@ class CIATables:
 
     def __del__(self):
         try:
-            for h, _ in self._dev.values():
-                lib().cs_cia_free(h)
+            for h, ctx in self._dev.values():
+                if ctx.h:
+                    lib().cs_cia_free(h)
         except Exception:
             pass
 

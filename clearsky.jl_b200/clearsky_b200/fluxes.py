@@ -98,8 +98,16 @@ def _prepare(P, T, μ, absorbers, nlobatto):
     return A, ν, nν, P, fT, μl, ws
 
 
-def opticaldepth(P, g, T, μ, θ, *absorbers, nlobatto=4):
-    """opticaldepth(P::Vector, g, T, μ, θ, absorbers...; nlobatto=4) -- fluxes.jl:68-97"""
+def opticaldepth(P, *args, **kwargs):
+    """opticaldepth(P::Vector, g, T, μ, θ, absorbers...; nlobatto=4)    -- fluxes.jl:68-97 (Discretized core)
+    opticaldepth(P₁::Real, P₂::Real, g, 𝒻T, 𝒻μ, θ, absorbers...; tol=1e-5) -- fluxes.jl:39-66 (Radau equivalent, radau.py)"""
+    if np.ndim(P) == 0:
+        from .radau import opticaldepth_between
+        return opticaldepth_between(P, *args, **kwargs)
+    return _opticaldepth_levels(P, *args, **kwargs)
+
+
+def _opticaldepth_levels(P, g, T, μ, θ, *absorbers, nlobatto=4):
     P = np.sort(np.asarray(P, dtype=np.float64))
     A, ν, nν, P, fT, μl, ws = _prepare(P, T, μ, absorbers, nlobatto)
     A.checkpressures(P[-1], P[0])
@@ -132,7 +140,11 @@ def _eval_spectral(f, ν):
 def monochromaticfluxes_(Mup, Mdn, τ, core, P, g, T, μ, fS, fa, *absorbers, θs=0.841, _F=None, ν_weights=None):
     """monochromaticfluxes!(M⁺, M⁻, τ, core::Discretized, P, g, T, μ, 𝒻S, 𝒻a, absorbers...; θₛ) -- fluxes.jl:238-279.
     Any of Mup/Mdn/τ may be None (not materialised).  Returns (F⁺, F⁻, Fnet) since the spectral integral is fused."""
-    assert isinstance(core, Discretized), "only the Discretized core runs on the B200 engine"
+    if not isinstance(core, Discretized):
+        from .radau import Radau, monochromaticfluxes_radau
+        assert isinstance(core, Radau), "core must be Discretized or Radau"
+        assert _F is None and ν_weights is None
+        return monochromaticfluxes_radau(Mup, Mdn, τ, core, P, g, T, μ, fS, fa, *absorbers, θs=θs)
     nstream, nlobatto = core.nstream, core.nlobatto
     assert np.all(np.diff(P) >= 0), "pressure coordinates must be in ascending order (sorted)"
     A, ν, nν, P, fT, μl, ws = _prepare(P, T, μ, absorbers, nlobatto)

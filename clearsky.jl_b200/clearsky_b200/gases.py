@@ -140,7 +140,7 @@ class Gas(AbstractGas):
 
     def __del__(self):
         try:
-            if getattr(self, "_parent", None) is None and self.h:
+            if getattr(self, "_parent", None) is None and self.h and self.ctx.h:
                 lib().cs_table_free(self.h)
         except Exception:
             pass

@@ -48,7 +48,7 @@ class DeviceLines:
 
     def __del__(self):
         try:
-            if self.h:
+            if self.h and self.ctx.h:
                 lib().cs_lines_free(self.h)
         except Exception:
             pass

@@ -143,7 +143,7 @@ class ShardedLineByLine:
             self.parts.append(dict(a=a, b=b, ν=νs, gases=lg, ws={}, w=np.ascontiguousarray(self.wg[a:b])))
         self._pairs = []
         for x, i, j in self.cia:
-            assert self.gases[i][0].formula in x.formulae and self.gases[j][0].formula in x.formulae, \
+            assert sorted((self.gases[i][0].formula, self.gases[j][0].formula)) == sorted(x.formulae), \
                 f"gases do not match the {x.name} CIA tables"
             self._pairs.append((x, i, j))
 

@@ -136,6 +136,15 @@ extern "C" int32_t cs_ctx_get_farfield(cs_ctx* c, int32_t* mode)
     return CS_OK;
 }
 
+extern "C" int32_t cs_ctx_set_tau_floor(cs_ctx* c, double tau_min)
+{
+    CS_REQUIRE(c, CS_ERR_ARG, "null argument");
+    CS_REQUIRE(tau_min > 0 && tau_min <= 1.0, CS_ERR_ARG, "tau floor must be in (0, 1] (got %g)", tau_min);
+    std::lock_guard<std::recursive_mutex> lk(c->mtx);
+    c->tau_floor = tau_min;
+    return CS_OK;
+}
+
 void cs_reset_timers(cs_ctx* c)
 {
     for (int i = 0; i < CS_NTIMERS; i++) c->last_kernel_ms[i] = 0.0;

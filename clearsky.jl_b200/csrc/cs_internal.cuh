@@ -99,6 +99,7 @@ struct cs_ctx {
     double last_kernel_ms[CS_NTIMERS] = {0};
     int64_t launches = 0;   // number of kernels of this library launched on this context
     int32_t farfield = CS_FARFIELD_DIRECT;   // K2 far-wing treatment (cs_ctx_set_farfield)
+    double tau_floor = 1e-6;                 // K6 floor on the vertical layer depth (cs_ctx_set_tau_floor)
 };
 
 struct cs_lines {
@@ -265,6 +266,47 @@ __device__ __forceinline__ double cs_rcp(double a)
     e = fma(e, e, e);
     return fma(r, e, r);
 }
+
+// ------------------------------------------------------------------------------------------------
+// mbarrier / TMA bulk-copy helpers (PTX)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
 
 // internal entry points implemented across the .cu files
 void cs_reset_timers(cs_ctx* c);

@@ -30,6 +30,7 @@ struct RtArgs {
     int64_t nnu;
     int np, nlob, ns;
     double Cg, cos_s;
+    double tau_floor;      // floor on the vertical layer depth (1e-6 in the reference, discretized.jl:174)
     double* tau_s;         // scratch [np-1][nnu]
     double* B_s;           // scratch [np][nnu]
     double* tau_out;       // optional, Julia tau[i,j] -> i + (np-1)*j
@@ -115,7 +116,7 @@ __global__ void __launch_bounds__(RT_THREADS) rt_kernel(RtArgs a)
         double bn = Cg * (a.sig[(size_t)((nlob - 1) * (i + 1)) * nnu + j] / smu[(nlob - 1) + nlob * i]);
         ti += (dP * swl[nlob - 1]) * bn;
         beta1 = bn;
-        double tau = fmax(ti, 1e-6);                     // floor on the vertical depth (discretized.jl:174)
+        double tau = fmax(ti, a.tau_floor);              // floor on the vertical depth (discretized.jl:174)
         a.tau_s[(size_t)i * nnu + j] = tau;
         if (a.tau_out && live) a.tau_out[(size_t)L * j + i] = tau;
         double Bnext = 100.0 * pref / (exp(hcn * skT[i + 1]) - 1.0);
@@ -307,6 +308,7 @@ int32_t fluxes_impl(cs_sigma* s, int64_t np, const double* P, int32_t nlob, cons
     a.nnu = nnu; a.np = (int)np; a.nlob = nlob; a.ns = nstream;
     a.Cg = 1e-4 * CS_NA / g;          // fluxes.jl:259
     a.cos_s = cos(theta_s);
+    a.tau_floor = ctx->tau_floor;
     a.tau_s = ctx->s_tau.as<double>(); a.B_s = ctx->s_planck.as<double>();
     a.tau_out = tau ? ctx->s_out0.as<double>() : nullptr;
     a.Mup_out = Mup ? ctx->s_out1.as<double>() : nullptr;
@@ -399,7 +401,11 @@ extern "C" int32_t cs_opticaldepth(cs_sigma* s, int64_t np, const double* P, int
     char* base = ctx->s_misc.as<char>();
     CS_CUDA(cudaMemcpyAsync(base, small.data(), small.size() * sizeof(double), cudaMemcpyHostToDevice, st));
     int nblocks = (int)((s->nnu + RT_THREADS - 1) / RT_THREADS);
-    depth_kernel<<<nblocks, RT_THREADS, small.size() * sizeof(double), st>>>(
+    const size_t dsm = small.size() * sizeof(double);
+    CS_REQUIRE(dsm <= 200 * 1024, CS_ERR_ARG, "too many pressure levels for one optical-depth call (%lld): per-CTA tables need %zu bytes",
+               (long long)np, dsm);
+    if (dsm > 48 * 1024) CS_CUDA(cudaFuncSetAttribute(depth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
+    depth_kernel<<<nblocks, RT_THREADS, dsm, st>>>(
         s->sig, (const double*)base, s->nnu, (int)np, nlob, 1e-4 * CS_NA / g, 1 / cos(theta), (double*)(base + off_out));
     CS_CUDA(cudaGetLastError());
     cs_count_launch(ctx);

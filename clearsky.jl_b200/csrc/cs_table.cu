@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 
 namespace {
 
@@ -187,6 +188,133 @@ __global__ void __launch_bounds__(LB == 8 ? 512 : 352) table_eval_kernel(const d
                 size_t o = (size_t)lev * nnu + v1;
                 double s = exp(acc1[l]);
                 out[o] = mode ? out[o] + C[lev] * s : s;
+            }
+        }
+    }
+}
+
+// ---- K4 as an FP64 tensor-core GEMM (the one dense contraction on the path):
+//   lnsigma[nu][l] = sum_k coef[k][nu] * basis[k][l],   basis[k = i + nT*j][l] = T_i(xi_T(l)) * T_j(xi_P(l)),
+// M = nnu, N = levels of one block (<= 128), K = nT*nP.  DMMA m8n8k4 (mma.sync, the only FP64 tensor-core form; tcgen05
+// has no f64 kind) takes one A and one B element per lane for 256 FMAs, so operand delivery from shared memory costs
+// 1/4 of the tensor time, whereas the FMA-pipe form above needs a broadcast shared-memory operand for every 2 FMAs
+// and is bound by the shared-memory pipe at 29 % of the FP64 peak.
+// CTA = 128 wavenumbers x <=128 levels: 16 consumer warps (4 along nu x 4 along levels, 32 x 32 each = 4 x 4 MMA tiles,
+// 32 accumulator doubles per lane) + 1 producer warp that streams K in slabs of 16 rows (coefficient rows of 1 KB,
+// basis rows of 1 KB) through a 4-stage shared-memory ring with cp.async.bulk and full/empty mbarriers.  Rows are
+// padded to 132 doubles in shared memory so that the fragment loads (4 rows x 8 columns per half warp) are
+// conflict-free.  Requires nnu even (16-byte aligned rows); otherwise table_eval_kernel runs.
+constexpr int GM_BM = 128, GM_BN = 128, GM_BK = 16, GM_STAGES = 4, GM_LD = 132;
+__global__ void __launch_bounds__(128) basis_kernel(const double* __restrict__ Tt, const double* __restrict__ Tp, int nT,
+                                                    int nP, int nlev, int lpb, double* __restrict__ basis)
+{
+    // basis[by][k][GM_BN], zero beyond the levels of the block
+    const int k = blockIdx.x, by = blockIdx.y, l = threadIdx.x;
+    const int i = k % nT, j = k / nT;
+    const int lev = by * lpb + l;
+    const bool ok = l < lpb && lev < nlev;
+    basis[((size_t)by * nT * nP + k) * GM_BN + l] = ok ? Tt[(size_t)lev * nT + i] * Tp[(size_t)lev * nP + j] : 0.0;
+}
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(32 * 17) table_eval_mma_kernel(const double* __restrict__ coef, int64_t nnu, int nk,
+                                                                 const double* __restrict__ basis,
+                                                                 const double* __restrict__ C, int nlev, int lpb,
+                                                                 double* out, int mode)
+{
+    extern __shared__ __align__(128) double gm_sm[];     // [GM_STAGES][2][GM_BK][GM_LD]
+    __shared__ __align__(8) uint64_t full_bar[GM_STAGES], empty_bar[GM_STAGES];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int lb0 = blockIdx.y * lpb;
+    const int nl = min(lpb, nlev - lb0);                  // levels of this block
+    const int nactive = 4 * ((nl + 31) / 32);             // consumer warps that own at least one level
+    const int64_t vbase = (int64_t)blockIdx.x * GM_BM;
+    const int nv = (int)min((int64_t)GM_BM, nnu - vbase);
+    const int nit = (nk + GM_BK - 1) / GM_BK;
+    const double* bas = basis + (size_t)blockIdx.y * nk * GM_BN;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < GM_STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], nactive); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 16) {
+        if (lane == 0) {
+            const uint32_t abytes = (uint32_t)nv * 8u, bbytes = (uint32_t)(((nl + 1) & ~1) * 8);
+            for (int it = 0; it < nit; it++) {
+                const int s = it % GM_STAGES;
+                if (it >= GM_STAGES) mbar_wait(&empty_bar[s], ((it / GM_STAGES) - 1) & 1);
+                const int rows = min(GM_BK, nk - it * GM_BK);
+                double* sA = gm_sm + (size_t)s * 2 * GM_BK * GM_LD;
+                double* sB = sA + GM_BK * GM_LD;
+                mbar_arrive_expect_tx(&full_bar[s], (abytes + bbytes) * (uint32_t)rows);
+                for (int u = 0; u < rows; u++) {
+                    const size_t k = (size_t)it * GM_BK + u;
+                    tma_bulk_g2s(sA + u * GM_LD, coef + k * nnu + vbase, abytes, &full_bar[s]);
+                    tma_bulk_g2s(sB + u * GM_LD, bas + k * GM_BN, bbytes, &full_bar[s]);
+                }
+            }
+        }
+        return;
+    }
+    if (warp >= nactive) return;
+    const int wm = warp & 3, wn = warp >> 2;
+    const int ntc = min(4, (nl - 32 * wn + 7) / 8);       // level tiles of this warp that hold a real level
+    const int fr = lane >> 2, fk = lane & 3;              // fragment row/column index, k index
+    double acc[4][4][2];
+#pragma unroll
+    for (int t = 0; t < 4; t++)
+#pragma unroll
+        for (int u = 0; u < 4; u++) acc[t][u][0] = acc[t][u][1] = 0.0;
+    for (int it = 0; it < nit; it++) {
+        const int s = it % GM_STAGES;
+        mbar_wait(&full_bar[s], (it / GM_STAGES) & 1);
+        const double* sA = gm_sm + (size_t)s * 2 * GM_BK * GM_LD + 32 * wm + fr;
+        const double* sB = gm_sm + (size_t)s * 2 * GM_BK * GM_LD + GM_BK * GM_LD + 32 * wn + fr;
+        const int rows = min(GM_BK, nk - it * GM_BK);
+#pragma unroll
+        for (int kk = 0; kk < GM_BK / 4; kk++) {
+            if (kk * 4 < rows) {
+                const int kr = kk * 4 + fk;
+                const bool kok = kr < rows;               // only the last slab can hold a partial group of four rows
+                double a[4], b[4];
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    double av = sA[kr * GM_LD + 8 * t], bv = sB[kr * GM_LD + 8 * t];
+                    a[t] = kok ? av : 0.0;
+                    b[t] = (kok && t < ntc) ? bv : 0.0;
+                }
+#pragma unroll
+                for (int t = 0; t < 4; t++)
+#pragma unroll
+                    for (int u = 0; u < 4; u++)
+                        if (u < ntc) dmma884(acc[t][u][0], acc[t][u][1], a[t], b[u]);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[s]);
+    }
+    // epilogue: lane holds D[row = lane/4][col = 2*(lane%4) + {0,1}] of every 8 x 8 tile
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+        const int64_t v = vbase + 32 * wm + 8 * t + fr;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+                const int l = 32 * wn + 8 * u + 2 * fk + c;
+                if (u < ntc && l < nl && v < nnu) {
+                    const int lev = lb0 + l;
+                    size_t o = (size_t)lev * nnu + v;
+                    double sg = exp(acc[t][u][c]);
+                    out[o] = mode ? out[o] + C[lev] * sg : sg;
+                }
             }
         }
     }
@@ -403,28 +531,42 @@ int32_t eval_table(cs_table* tb, int64_t nlev, const double* T, const double* P,
         cp[0] = 1; cp[1] = xp;
         for (int k = 2; k < nP; k++) cp[k] = 2 * xp * cp[k - 1] - cp[k - 2];
     }
-    size_t offP = sizeof(double) * (size_t)nlev * nT;
-    size_t offC = ((basis.size() * sizeof(double) + 255) / 256) * 256;
-    CS_TRY(ctx->s_misc.reserve(offC + sizeof(double) * (size_t)nlev));
+    // level blocking: blocks of <= 128 levels (each re-reads the coefficients once)
+    const int nk = nT * nP;
+    const int nby = (int)((nlev + 127) / 128);
+    const int lpb = (int)((nlev + nby - 1) / nby);
+    // the tensor-core kernel needs 16-byte aligned coefficient rows: nnu even (coef itself is 256-byte aligned)
+    const bool mma = (tb->nnu % 2 == 0) && getenv("CS_TABLE_EVAL_NO_MMA") == nullptr;
+    const size_t offP = sizeof(double) * (size_t)nlev * nT;
+    const size_t offC = ((basis.size() * sizeof(double) + 255) / 256) * 256;
+    const size_t offB = offC + ((sizeof(double) * (size_t)nlev + 255) / 256) * 256;
+    CS_TRY(ctx->s_misc.reserve(offB + (mma ? sizeof(double) * (size_t)nby * nk * GM_BN : 0)));
     char* base = ctx->s_misc.as<char>();
     CS_CUDA(cudaMemcpyAsync(base, basis.data(), basis.size() * sizeof(double), cudaMemcpyHostToDevice, st));
     if (C) CS_CUDA(cudaMemcpyAsync(base + offC, C, sizeof(double) * (size_t)nlev, cudaMemcpyHostToDevice, st));
     CS_CUDA(cudaEventRecord(ctx->ev0, st));
-    // level blocking: blocks of <= 128 levels (each re-reads the coefficients once); within a block G warps of LB
-    // levels each, LB from {8, 12} chosen for the least padding
-    const int nby = (int)((nlev + 127) / 128);
-    const int lpb = (int)((nlev + nby - 1) / nby);
-    int LB = 8, best = 1 << 30;
-    for (int cand : {8, 12}) {
-        int pad = ((lpb + cand - 1) / cand) * cand;
-        if (pad < best || (pad == best && cand > LB)) { best = pad; LB = cand; }
-    }
-    const int G = best / LB;
-    const size_t smem = sizeof(double) * (size_t)(nT + nP) * best;
-    dim3 grid((unsigned)((tb->nnu + 63) / 64), (unsigned)nby);
     const double* dTt = (const double*)base;
     const double* dTp = (const double*)(base + offP);
     const double* dC = (const double*)(base + offC);
+    if (mma) {
+        double* dB = (double*)(base + offB);
+        basis_kernel<<<dim3((unsigned)nk, (unsigned)nby), GM_BN, 0, st>>>(dTt, dTp, nT, nP, (int)nlev, lpb, dB);
+        CS_CUDA(cudaGetLastError());
+        const size_t sm2 = sizeof(double) * GM_STAGES * 2 * GM_BK * GM_LD;
+        CS_CUDA(cudaFuncSetAttribute(table_eval_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
+        dim3 g2((unsigned)((tb->nnu + GM_BM - 1) / GM_BM), (unsigned)nby);
+        table_eval_mma_kernel<<<g2, 32 * 17, sm2, st>>>(tb->coef, tb->nnu, nk, dB, dC, (int)nlev, lpb, d_out, mode);
+        cs_count_launch(ctx);
+    } else {
+        // FMA-pipe kernel: within a level block G warps of LB levels each, LB from {8, 12} chosen for the least padding
+        int LB = 8, best = 1 << 30;
+        for (int cand : {8, 12}) {
+            int pad = ((lpb + cand - 1) / cand) * cand;
+            if (pad < best || (pad == best && cand > LB)) { best = pad; LB = cand; }
+        }
+        const int G = best / LB;
+        const size_t smem = sizeof(double) * (size_t)(nT + nP) * best;
+        dim3 grid((unsigned)((tb->nnu + 63) / 64), (unsigned)nby);
 #define CS_TE_LAUNCH(LBV)                                                                                             \
     do {                                                                                                              \
         if (smem > 48 * 1024)                                                                                         \
@@ -433,8 +575,9 @@ int32_t eval_table(cs_table* tb, int64_t nlev, const double* T, const double* P,
         table_eval_kernel<LBV, 4><<<grid, 32 * G, smem, st>>>(tb->coef, tb->nnu, nT, nP, dTt, dTp, dC, (int)nlev, lpb, \
                                                               d_out, mode);                                           \
     } while (0)
-    if (LB == 8) CS_TE_LAUNCH(8);
-    else CS_TE_LAUNCH(12);
+        if (LB == 8) CS_TE_LAUNCH(8);
+        else CS_TE_LAUNCH(12);
+    }
 #undef CS_TE_LAUNCH
     CS_CUDA(cudaGetLastError());
     cs_count_launch(ctx);

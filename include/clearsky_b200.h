@@ -83,6 +83,10 @@ int32_t cs_ctx_launches(cs_ctx* ctx, int64_t* launches);
 #define CS_FARFIELD_EXPANSION 1
 int32_t cs_ctx_set_farfield(cs_ctx* ctx, int32_t mode);
 int32_t cs_ctx_get_farfield(cs_ctx* ctx, int32_t* mode);
+/* Floor applied to the vertical optical depth of every layer before the Schwarzschild sweep.  Default 1e-6 =
+ * the reference's tau_min (src/core/discretized.jl:174); the Radau-equivalent wrappers (many thin layers) lower it
+ * to 1e-9 so that the floor does not add opacity in spectral windows. */
+int32_t cs_ctx_set_tau_floor(cs_ctx* ctx, double tau_min);
 /* sustained FP64 FMA rate of this device, measured with a register-resident DFMA loop [FLOP/s] */
 int32_t cs_fp64_peak(cs_ctx* ctx, int32_t iters, double* flops_per_s);
 

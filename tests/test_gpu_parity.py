@@ -202,6 +202,26 @@ def test_bake_and_table(cs, orc, co2):
         gas.rawσ(np.array([250.0]), np.array([2e5]))
 
 
+@pytest.mark.parametrize("nν,nq", [(777, 3), (778, 150), (64, 101), (1301, 129)])
+def test_table_eval_variants(cs, orc, co2, nν, nq):
+    """K4 on both kernels (TMA-fed for even nν, register-prefetch for odd nν), ragged wavenumber tiles, level counts
+    around the 8/12-level groups and above the 128-level block; the Gas functor accumulates C·σ (gases.jl:278)"""
+    ν = np.linspace(600.0, 760.0, nν)
+    Ω = cs.AtmosphericDomain((150, 310), 9, (8, 1.05e5), 11)
+    gas = cs.Gas(co2, lambda T, P: 300e-6 + 1e-9 * T, ν, Ω, "voigt", 25.0, keep_block=True)
+    A = orc.table_fit(gas.σblock())
+    rng = np.random.default_rng(nq)
+    Tq = rng.uniform(151, 309, nq)
+    Pq = np.exp(rng.uniform(np.log(9), np.log(1e5), nq))
+    ref = orc.gas_nodes(A, Ω.T, Ω.P, Tq, Pq, np.ones(nq))
+    assert relerr(gas.rawσ(Tq, Pq), ref, 1e-290) < XSEC_TOL
+    ws = cs.SigmaWorkspace(ν, nq)
+    gas.add_to(ws, Tq, Pq)
+    gas.add_to(ws, Tq, Pq)
+    C = 300e-6 + 1e-9 * Tq
+    assert relerr(ws.read(), 2 * C[:, None] * ref, 1e-290) < XSEC_TOL
+
+
 def test_zero_mixing_repair(cs, orc):
     """a wavenumber whose σ underflows to 0 at some nodes only is zeroed at all nodes (gases.jl:131-142) and its
     table becomes log(floatmin) everywhere (gases.jl:77-79)"""
@@ -361,6 +381,63 @@ def test_opticaldepth(cs, orc, co2):
     x, w = cs.lobattonodes(4)
     ref = orc.opticaldepth(P, 4, w, μl, σ, 9.8, 0.3)
     assert relerr(τ, ref, 1e-300) < FLUX_TOL
+
+
+def test_radau_equivalents(cs, co2):
+    """Radau-core entry points on the GPU (fluxes.jl:39-66, 133-158, 160-192, 197-236): convergence to tol against
+    closed forms and against much finer Discretized solves (they are not 1e-8 parity targets, see radau.py)"""
+    from test_oracle_pins import _gray_analytic
+    from clearsky_b200 import constants as K
+    # opticaldepth(P1, P2, ...) for a gray gas is closed form: tau = 1e-4 Na sigma (P1 - P2) / (g mu cos(theta))
+    g, μ, cp, Ps, Ts = 10.0, 0.01, 1e3, 1e5, 300.0
+    ν = np.concatenate([np.linspace(1e-3, 10, 60)[:-1], np.linspace(10, 6000, 1500)])
+    Γ = cs.DryAdiabat(Ts, Ps, cp, μ)
+    gray = cs.GrayGas(1e-26, ν)
+    τ = cs.opticaldepth(Ps, 10.0, g, Γ, μ, 0.5, gray)
+    assert relerr(τ, np.full(len(ν), 1e-4 * K.Na * 1e-26 * (Ps - 10.0) / (g * μ * np.cos(0.5))), 1e-300) < 1e-12
+    assert np.allclose(cs.transmittance(Ps, 10.0, g, Γ, μ, 0.5, gray), np.exp(-τ))
+    # outgoing(Ps, ...) integrates to the analytic gray OLR (test/test_gray.jl)
+    m, W = cs.streamnodes(5)
+    for σ in (1e-27, 1e-25):
+        olr = cs.outgoing(Ps, g, Γ, μ, cs.GrayGas(σ, ν), Ptop=1e-2)
+        assert abs(cs.trapz(ν, olr) / _gray_analytic(σ, g, μ, cp, Ps, Ts, m, W) - 1) < 0.01
+    # real gas: table-based CO2 on the C1 atmosphere
+    ν = np.linspace(500.0, 800.0, 1201)
+    Γ = cs.DryAdiabat(288.0, 1e5, 1040.0, 0.029, Ptropo=1e4)
+    Ω = cs.AtmosphericDomain((140, 300), 10, (5, 1.1e5), 16)
+    gas = cs.Gas(co2, 400e-6, ν, Ω, "voigt", 25.0)
+    τ = cs.opticaldepth(1e5, 10.0, 9.8, Γ, 0.029, 0.0, gas, tol=1e-6)
+    Pf = np.exp(np.linspace(np.log(10.0), np.log(1e5), 1025))
+    assert relerr(τ, cs.opticaldepth(Pf, 9.8, Γ, 0.029, 0.0, gas, nlobatto=4), 1e-300) < 1e-5
+    olr = cs.outgoing(1e5, 9.8, Γ, 0.029, gas, Ptop=10.0, tol=1e-5)
+    ctx = cs.default_context()
+    ctx.set_tau_floor(1e-9)
+    try:    # independent reference: Richardson extrapolation of two fine Discretized solves
+        Mf, _ = cs.monochromaticfluxes(Pf, 9.8, Γ, 0.029, None, None, gas, core=cs.Discretized(5, 4))
+        Mc, _ = cs.monochromaticfluxes(Pf[::2], 9.8, Γ, 0.029, None, None, gas, core=cs.Discretized(5, 4))
+    finally:
+        ctx.set_tau_floor(1e-6)
+    ref = (4 * Mf[:, 0] - Mc[:, 0]) / 3
+    assert relerr(olr, ref, 1e-3 * ref.max()) < 5e-5
+    # outgoing(P::Vector) == M+ at the top level of the Discretized core with nlobatto = 3, no sun, black surface
+    P = cs.pressuregrid(10.0, 1e5, 31)
+    Mu, _ = cs.monochromaticfluxes(P, 9.8, Γ, 0.029, None, None, gas, core=cs.Discretized(5, 3))
+    assert np.array_equal(cs.outgoing(P[::-1], 9.8, Γ, 0.029, gas), Mu[:, 0])
+    # monochromaticfluxes!(…, core::Radau, …): levels of P from a refined solve; tau is NaN like the reference's
+    F = cs.FluxPack(len(P), len(ν))
+    cs.radiate_(F, cs.Radau(5, 1e-5), P, 9.8, Γ, 0.029, lambda x: 0.1 + 0 * x, 0.2, gas)
+    assert np.all(np.isnan(F.τ))
+    k = 32
+    lnP = np.log(P)
+    fine = np.concatenate([np.exp(lnP[:-1, None] + (lnP[1:] - lnP[:-1])[:, None] * (np.arange(k) / k)[None, :]).ravel(), P[-1:]])
+    fine[::k] = P
+    ctx.set_tau_floor(1e-9)
+    try:
+        Mu, Md = cs.monochromaticfluxes(fine, 9.8, Γ, 0.029, lambda x: 0.1 + 0 * x, 0.2, gas, core=cs.Discretized(5, 4))
+    finally:
+        ctx.set_tau_floor(1e-6)
+    assert relerr(F.Mup, Mu[:, ::k], 1e-3 * Mu.max()) < 5e-5 and relerr(F.Mdn, Md[:, ::k], 1e-3 * Md.max()) < 5e-5
+    assert abs(F.Fup[0] / cs.trapz(ν, Mu[:, 0]) - 1) < 5e-5
 
 
 def test_flux_errors(cs, co2):
@@ -539,7 +616,7 @@ def test_single_process_device_group_with_cia(cs, co2):
     sh = cs.ShardedLineByLine(grp, [(co2, 1.0, "PHCO2", 500.0)], ν, cia=[(x, 0, 0)])
     Fup, Fdn, Fnet = sh.fluxes(P, 3.71, Γ, 0.044)
     gas = cs.LineGas(co2, 1.0, ν, "PHCO2", 500.0)
-    F = cs.radiate(P, 3.71, Γ, 0.044, None, None, gas, cs.CIA(x, gas, gas))
+    F = cs.radiate(P, 3.71, Γ, 0.044, None, None, gas, cs.CIA(x, gas))
     assert relerr(Fup, F.Fup) < 1e-12 and relerr(Fdn[1:], F.Fdn[1:]) < 1e-12
     nocia = cs.radiate(P, 3.71, Γ, 0.044, None, None, gas)
     assert relerr(nocia.Fup[:1], F.Fup[:1]) > 1e-4          # the CIA term is not a no-op
