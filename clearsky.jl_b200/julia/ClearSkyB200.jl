@@ -16,6 +16,7 @@ using ClearSky: SpectralLines, AtmosphericDomain, AbstractGas, AbstractNumerical
                 checkazimuth, checkstreams, checkν
 
 export B200Discretized, B200Gas, B200LineGas, voigt_b200!, lorentz_b200!, doppler_b200!, PHCO2_b200!
+export farfield!, taufloor!, outgoing_b200, opticaldepth_b200
 
 const LIB = get(ENV, "CLEARSKY_B200_LIB", joinpath(@__DIR__, "..", "lib", "libclearsky_b200.so"))
 const MAXCHEB = 16
@@ -40,6 +41,13 @@ mutable struct Context
 end
 const CTX = Ref{Union{Nothing,Context}}(nothing)
 context() = (CTX[] === nothing && (CTX[] = Context()); CTX[])
+
+# far-wing treatment of the Voigt/Lorentz line sum: :direct (every pair, like surf!) or :expansion (20-term local
+# expansion of well-separated far-wing lines, truncation < 3e-11; include/clearsky_b200.h)
+farfield!(mode::Symbol) = check(ccall((:cs_ctx_set_farfield, LIB), Int32, (Ptr{Cvoid}, Int32), context().h,
+                                      mode === :expansion ? Int32(1) : Int32(0)))
+# floor on the vertical optical depth of a layer in the flux kernel (reference: 1e-6, src/core/discretized.jl:174)
+taufloor!(τmin::Real) = check(ccall((:cs_ctx_set_tau_floor, LIB), Int32, (Ptr{Cvoid}, Float64), context().h, τmin))
 
 # ---- SpectralLines on the device (cs_lines_upload <- src/hitran/par.jl:224-284) --------------------------
 mutable struct DeviceLines
@@ -210,6 +218,39 @@ function ClearSky.radiate!(F::FluxPack, core::B200Discretized, P::AbstractVector
     F⁺, F⁻, Fnet = fluxes_b200(core, P, g, T, μ, 𝒻S, 𝒻a, absorbers...; M⁺=F.M⁺, M⁻=F.M⁻, τ=F.τ, kwargs...)
     F.F⁺ .= F⁺; F.F⁻ .= F⁻; F.Fnet .= Fnet
     nothing
+end
+
+# ---- Radau-core equivalents (src/fluxes.jl:39-66, 133-158): same entry points on the Discretized GPU core, layers
+# equally spaced in ln P doubled until the Richardson estimate is below tol (see clearsky_b200/radau.py, the executed twin)
+function outgoing_b200(Pₛ::Real, g::Real, 𝒻T, 𝒻μ, absorbers...; Ptop::Real=1.0, nstream::Int=5, tol::Real=1e-5)
+    taufloor!(1e-9)
+    try
+        prev, n = nothing, 32
+        while true
+            P = exp.(range(log(Ptop), log(Pₛ), length=n + 1))
+            ν = first(a for a in absorbers if a isa AbstractGas).ν
+            M⁺, M⁻ = zeros(n + 1, length(ν)), zeros(n + 1, length(ν))
+            fluxes_b200(B200Discretized(nstream, 4), P, g, 𝒻T, 𝒻μ, x -> 0.0, x -> 0.0, absorbers...; M⁺=M⁺, M⁻=M⁻)
+            olr = M⁺[1, :]
+            if prev !== nothing
+                scale = max.(abs.(olr), 1e-3 * maximum(abs.(olr)))
+                (maximum(abs.(olr .- prev) ./ (3 .* scale)) < tol || 2n + 1 > 1025) && return (4 .* olr .- prev) ./ 3
+            end
+            prev, n = olr, 2n
+        end
+    finally
+        taufloor!(1e-6)
+    end
+end
+
+function opticaldepth_b200(P₁::Real, P₂::Real, g::Real, 𝒻T, 𝒻μ, θ::Real, absorbers...; tol::Real=1e-5)
+    P₁, P₂ = max(P₁, P₂), min(P₁, P₂)
+    prev, n = nothing, 16
+    while true
+        τ = ClearSky.opticaldepth(exp.(range(log(P₂), log(P₁), length=n + 1)), g, 𝒻T, 𝒻μ, θ, absorbers...; nlobatto=4)
+        prev !== nothing && (maximum(abs.(τ .- prev) ./ max.(abs.(τ), 1e-3 * maximum(abs.(τ)))) < tol || 2n + 1 > 1025) && return τ
+        prev, n = τ, 2n
+    end
 end
 
 end # module

@@ -616,7 +616,7 @@ def test_single_process_device_group_with_cia(cs, co2):
     sh = cs.ShardedLineByLine(grp, [(co2, 1.0, "PHCO2", 500.0)], ν, cia=[(x, 0, 0)])
     Fup, Fdn, Fnet = sh.fluxes(P, 3.71, Γ, 0.044)
     gas = cs.LineGas(co2, 1.0, ν, "PHCO2", 500.0)
-    F = cs.radiate(P, 3.71, Γ, 0.044, None, None, gas, cs.CIA(x, gas))
+    F = cs.radiate(P, 3.71, Γ, 0.044, None, None, gas, x)
     assert relerr(Fup, F.Fup) < 1e-12 and relerr(Fdn[1:], F.Fdn[1:]) < 1e-12
     nocia = cs.radiate(P, 3.71, Γ, 0.044, None, None, gas)
     assert relerr(nocia.Fup[:1], F.Fup[:1]) > 1e-4          # the CIA term is not a no-op
