@@ -223,21 +223,31 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                  : "d"(a), "d"(b));
 }
 
-__global__ void __launch_bounds__(32 * 17) table_eval_mma_kernel(const double* __restrict__ coef, int64_t nnu, int nk,
+// The same kernel serves the two separable passes of the table fit (K3): there the "levels" are the output Chebyshev
+// coefficients of one axis, blockIdx.y selects the other axis' index, rows are addressed through (row0, stride) pairs
+// and the epilogue stores the plain sum (mode 2).
+struct GemmRows {
+    int64_t a_row0_step, a_row_stride;   // A row k of block y: (y*a_row0_step + k*a_row_stride)
+    int64_t b_y_stride;                  // basis of block y starts at y*b_y_stride doubles
+    int64_t o_row0_step, o_row_stride;   // output column l of block y goes to row (y*o_row0_step + l*o_row_stride)
+};
+__global__ void __launch_bounds__(32 * 17, 1) table_eval_mma_kernel(const double* coef, int64_t nnu, int nk,
                                                                  const double* __restrict__ basis,
                                                                  const double* __restrict__ C, int nlev, int lpb,
-                                                                 double* out, int mode)
+                                                                 double* out, int mode, GemmRows gr)
 {
     extern __shared__ __align__(128) double gm_sm[];     // [GM_STAGES][2][GM_BK][GM_LD]
     __shared__ __align__(8) uint64_t full_bar[GM_STAGES], empty_bar[GM_STAGES];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int lb0 = blockIdx.y * lpb;
-    const int nl = min(lpb, nlev - lb0);                  // levels of this block
+    const int lb0 = mode == 2 ? 0 : blockIdx.y * lpb;
+    const int nl = min(lpb, nlev - lb0);                  // levels (output columns) of this block
     const int nactive = 4 * ((nl + 31) / 32);             // consumer warps that own at least one level
     const int64_t vbase = (int64_t)blockIdx.x * GM_BM;
     const int nv = (int)min((int64_t)GM_BM, nnu - vbase);
     const int nit = (nk + GM_BK - 1) / GM_BK;
-    const double* bas = basis + (size_t)blockIdx.y * nk * GM_BN;
+    const double* bas = basis + (size_t)blockIdx.y * gr.b_y_stride;
+    const double* arow = coef + (size_t)blockIdx.y * gr.a_row0_step * nnu + vbase;
+    const size_t astride = (size_t)gr.a_row_stride * nnu;
     if (threadIdx.x == 0) {
         for (int s = 0; s < GM_STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], nactive); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -256,7 +266,7 @@ __global__ void __launch_bounds__(32 * 17) table_eval_mma_kernel(const double* _
                 mbar_arrive_expect_tx(&full_bar[s], (abytes + bbytes) * (uint32_t)rows);
                 for (int u = 0; u < rows; u++) {
                     const size_t k = (size_t)it * GM_BK + u;
-                    tma_bulk_g2s(sA + u * GM_LD, coef + k * nnu + vbase, abytes, &full_bar[s]);
+                    tma_bulk_g2s(sA + u * GM_LD, arow + k * astride, abytes, &full_bar[s]);
                     tma_bulk_g2s(sB + u * GM_LD, bas + k * GM_BN, bbytes, &full_bar[s]);
                 }
             }
@@ -310,10 +320,14 @@ __global__ void __launch_bounds__(32 * 17) table_eval_mma_kernel(const double* _
             for (int c = 0; c < 2; c++) {
                 const int l = 32 * wn + 8 * u + 2 * fk + c;
                 if (u < ntc && l < nl && v < nnu) {
-                    const int lev = lb0 + l;
-                    size_t o = (size_t)lev * nnu + v;
-                    double sg = exp(acc[t][u][c]);
-                    out[o] = mode ? out[o] + C[lev] * sg : sg;
+                    if (mode == 2) {
+                        out[((size_t)blockIdx.y * gr.o_row0_step + (size_t)l * gr.o_row_stride) * nnu + v] = acc[t][u][c];
+                    } else {
+                        const int lev = lb0 + l;
+                        size_t o = (size_t)lev * nnu + v;
+                        double sg = exp(acc[t][u][c]);
+                        out[o] = mode ? out[o] + C[lev] * sg : sg;
+                    }
                 }
             }
         }
@@ -461,25 +475,52 @@ int32_t fit_table(cs_ctx* ctx, cs_table* tb, double* d_block)
     std::vector<double> Mx, My;
     cheb_matrix(nT, Mx);
     cheb_matrix(nP, My);
-    size_t offy = ((Mx.size() * sizeof(double) + 255) / 256) * 256;
-    size_t offc = offy + ((My.size() * sizeof(double) + 255) / 256) * 256;
-    CS_TRY(ctx->s_misc.reserve(offc + 64));
+    // transposed, zero-padded copies [q][GM_BN] for the tensor-core passes (B operand of the GEMM)
+    std::vector<double> MxT((size_t)nT * GM_BN, 0.0), MyT((size_t)nP * GM_BN, 0.0);
+    for (int o = 0; o < nT; o++)
+        for (int q = 0; q < nT; q++) MxT[(size_t)q * GM_BN + o] = Mx[(size_t)o * nT + q];
+    for (int o = 0; o < nP; o++)
+        for (int q = 0; q < nP; q++) MyT[(size_t)q * GM_BN + o] = My[(size_t)o * nP + q];
+    auto al = [](size_t b) { return ((b + 255) / 256) * 256; };
+    const size_t offy = al(Mx.size() * sizeof(double));
+    const size_t offc = offy + al(My.size() * sizeof(double));
+    const size_t offxt = offc + 256;
+    const size_t offyt = offxt + al(MxT.size() * sizeof(double));
+    CS_TRY(ctx->s_misc.reserve(offyt + al(MyT.size() * sizeof(double))));
     char* base = ctx->s_misc.as<char>();
     CS_CUDA(cudaMemcpyAsync(base, Mx.data(), Mx.size() * sizeof(double), cudaMemcpyHostToDevice, st));
     CS_CUDA(cudaMemcpyAsync(base + offy, My.data(), My.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    CS_CUDA(cudaMemcpyAsync(base + offxt, MxT.data(), MxT.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    CS_CUDA(cudaMemcpyAsync(base + offyt, MyT.data(), MyT.size() * sizeof(double), cudaMemcpyHostToDevice, st));
     CS_CUDA(cudaMemsetAsync(base + offc, 0, 8, st));
     CS_CUDA(cudaEventRecord(ctx->ev0, st));
     unsigned nb = (unsigned)((nnu + 255) / 256);
     table_log_kernel<<<nb, 256, 0, st>>>(d_block, nnu, nk, (unsigned long long*)(base + offc));
     CS_CUDA(cudaGetLastError());
-    // pass along T in place (a thread reads its whole line of nT values before it writes any), then the pass along
+    // pass along T in place (a thread / CTA reads its whole line of nT rows before it writes any), then the pass along
     // ln P from the block into coef: the block is read twice and written once, coef written once
-    dim3 gA((unsigned)((nnu + 127) / 128), (unsigned)nP);
-    cheb_pass_kernel<<<gA, 128, sizeof(double) * nT * nT, st>>>(d_block, d_block, nnu, nT, nP, 0, (const double*)base);
-    CS_CUDA(cudaGetLastError());
-    dim3 gB((unsigned)((nnu + 127) / 128), (unsigned)nT);
-    cheb_pass_kernel<<<gB, 128, sizeof(double) * nP * nP, st>>>(d_block, tb->coef, nnu, nT, nP, 1, (const double*)(base + offy));
-    CS_CUDA(cudaGetLastError());
+    if (nnu % 2 == 0 && getenv("CS_TABLE_EVAL_NO_MMA") == nullptr) {
+        // tensor-core passes: per (128-wavenumber tile, index of the other axis) an [128 x n] = [128 x n] . [n x n] product
+        const size_t sm2 = sizeof(double) * GM_STAGES * 2 * GM_BK * GM_LD;
+        CS_CUDA(cudaFuncSetAttribute(table_eval_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
+        const unsigned gx = (unsigned)((nnu + GM_BM - 1) / GM_BM);
+        GemmRows gT = {nT, 1, 0, nT, 1};          // block y = j: rows nT*j + q -> rows nT*j + o
+        table_eval_mma_kernel<<<dim3(gx, (unsigned)nP), 32 * 17, sm2, st>>>(d_block, nnu, nT, (const double*)(base + offxt),
+                                                                            nullptr, nT, nT, d_block, 2, gT);
+        CS_CUDA(cudaGetLastError());
+        GemmRows gP = {1, nT, 0, 1, nT};          // block y = i: rows i + nT*q -> rows i + nT*o
+        table_eval_mma_kernel<<<dim3(gx, (unsigned)nT), 32 * 17, sm2, st>>>(d_block, nnu, nP, (const double*)(base + offyt),
+                                                                            nullptr, nP, nP, tb->coef, 2, gP);
+        CS_CUDA(cudaGetLastError());
+    } else {
+        dim3 gA((unsigned)((nnu + 127) / 128), (unsigned)nP);
+        cheb_pass_kernel<<<gA, 128, sizeof(double) * nT * nT, st>>>(d_block, d_block, nnu, nT, nP, 0, (const double*)base);
+        CS_CUDA(cudaGetLastError());
+        dim3 gB((unsigned)((nnu + 127) / 128), (unsigned)nT);
+        cheb_pass_kernel<<<gB, 128, sizeof(double) * nP * nP, st>>>(d_block, tb->coef, nnu, nT, nP, 1,
+                                                                    (const double*)(base + offy));
+        CS_CUDA(cudaGetLastError());
+    }
     cs_count_launch(ctx, 3);
     CS_CUDA(cudaEventRecord(ctx->ev1, st));
     unsigned long long nz = 0;
@@ -555,7 +596,8 @@ int32_t eval_table(cs_table* tb, int64_t nlev, const double* T, const double* P,
         const size_t sm2 = sizeof(double) * GM_STAGES * 2 * GM_BK * GM_LD;
         CS_CUDA(cudaFuncSetAttribute(table_eval_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
         dim3 g2((unsigned)((tb->nnu + GM_BM - 1) / GM_BM), (unsigned)nby);
-        table_eval_mma_kernel<<<g2, 32 * 17, sm2, st>>>(tb->coef, tb->nnu, nk, dB, dC, (int)nlev, lpb, d_out, mode);
+        GemmRows gr = {0, 1, (int64_t)nk * GM_BN, 0, 0};
+        table_eval_mma_kernel<<<g2, 32 * 17, sm2, st>>>(tb->coef, tb->nnu, nk, dB, dC, (int)nlev, lpb, d_out, mode, gr);
         cs_count_launch(ctx);
     } else {
         // FMA-pipe kernel: within a level block G warps of LB levels each, LB from {8, 12} chosen for the least padding
