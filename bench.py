@@ -32,7 +32,7 @@ UNIT = "evals/s"
 FLOP_PER_EVAL = 10.0   # Voigt, far-wing dominated
 # dram__bytes_read.sum + dram__bytes_write.sum of one line_sum_kernel<VOIGT> launch (one gas, 101 levels) on C2, from the
 # ncu --set full capture summarised in profiles/r1_ncu_full_line_sum_voigt.csv
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 1.658598e9 + 0.235005e9
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 1.662827e9 + 0.237128e9
 
 
 # ------------------------------------------------------------------------------------------------
@@ -234,6 +234,9 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device -- the engine has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
+        # NCCL_DEBUG=VERSION makes NCCL print its banner on stdout, which must carry exactly one JSON line
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     # run the library on torch's current (non-default) stream so that torch.cuda.Event brackets its kernels
     stream = torch.cuda.Stream(device=local)
