@@ -106,6 +106,32 @@ def test_fluxes_farfield_expansion(cs, orc, co2, expansion):
     assert not np.array_equal(F.Mup, Fd.Mup)        # the expansion really was used
 
 
+def test_farfield_expansion_corner_cases(cs, orc, co2, expansion):
+    """expansion mode on degenerate grids (one / two points: zero-width tile), through cs_bake, and on the shapes it does
+    not apply to (PHCO2, Doppler must be bit-identical to the direct mode)"""
+    sl = synthetic_lines(cs, 4000, seed=23, νmax=150.0)
+    T, P, Pp = np.array([200.0, 290.0]), np.array([2e3, 9e4]), np.array([1.0, 40.0])
+    for ν in (np.array([75.0]), np.array([40.0, 110.0]), 70.0 + 1e-4 * np.arange(257)):
+        for name, sid in (("lorentz", 1), ("voigt", 2)):
+            got = cs.xsec(name, ν, sl, T, P, Pp, 25.0)
+            assert relerr(got, orc.xsec(sid, sl, ν, T, P, Pp, 25.0, nthreads=0), 1e-290) < XSEC_TOL
+    ν = 60.0 + 0.01 * np.arange(2000)
+    for name in ("PHCO2", "doppler"):
+        x = cs.xsec(name, ν, sl, T, P, Pp, 25.0)
+        expansion.set_farfield("direct")
+        d = cs.xsec(name, ν, sl, T, P, Pp, 25.0)
+        expansion.set_farfield("expansion")
+        assert np.array_equal(x, d)
+    # bake with the expansion on: table values against the oracle's direct bake + fit
+    ν = 620.0 + 0.01 * np.arange(3000)
+    Ω = cs.AtmosphericDomain((150, 300), 6, (10, 1e5), 8)
+    gas = cs.Gas(co2, 400e-6, ν, Ω, "voigt", 25.0, keep_block=True)
+    block, nz = orc.bake(orc.VOIGT, co2, ν, Ω.T, Ω.P, np.full((Ω.nP, Ω.nT), 400e-6), 25.0, nthreads=0)
+    assert relerr(gas.σblock(), block, 1e-290) < XSEC_TOL
+    Tq, Pq = np.array([180.0, 260.0]), np.array([300.0, 5e4])
+    assert relerr(gas.rawσ(Tq, Pq), orc.gas_nodes(orc.table_fit(block), Ω.T, Ω.P, Tq, Pq, np.ones(2)), 1e-290) < XSEC_TOL
+
+
 def test_xsec_line_centres(cs, orc, co2):
     """evaluation points sitting exactly on / next to line centres at low pressure (Hui / Humlicek regions)"""
     νl = co2.ν[(co2.ν > 600) & (co2.ν < 760)][::7][:150]
