@@ -21,5 +21,5 @@ from .par import SpectralLines, parse_records_b200, readpar, readpar_b200, write
 from .quadrature import lobattonodes, streamnodes
 from .radau import Radau, outgoing
 from .rcm import RCM
-from .sharding import DeviceGroup, ShardedLineByLine, sharded_fluxes
+from .sharding import DeviceGroup, ShardedAbsorber, ShardedLineByLine, sharded_fluxes
 from .util import AtmosphericProfile, chebygrid, pressuregrid, trapz

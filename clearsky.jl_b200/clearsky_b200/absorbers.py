@@ -100,6 +100,8 @@ class UnifiedAbsorber(AbstractAbsorber):
         self.fun = tuple(a for a in absorbers if not isinstance(a, (AbstractGas, CIATables)))
         self.ν = getwavenumbers(self.gas)
         self.nν = len(self.ν)
+        # the context the member gases live on (None: the process-wide default context)
+        self.ctx = next((g.ctx for g in self.gas if getattr(g, "ctx", None) is not None), None)
 
     def update(self, T):   # update!(A::UnifiedAbsorber, T) is a no-op (absorbers.jl:80)
         return None
@@ -126,7 +128,7 @@ class UnifiedAbsorber(AbstractAbsorber):
 
     def __call__(self, T, P):
         """(U::UnifiedAbsorber)(T, P): Σ for every wavenumber at one (T, P) (absorbers.jl:97-99)"""
-        ws = SigmaWorkspace(self.ν, 1)
+        ws = SigmaWorkspace(self.ν, 1, self.ctx)
         self.sigma_nodes(ws, np.array([float(T)]), np.array([float(P)]))
         return ws.read()[0]
 
@@ -146,7 +148,7 @@ class AcceleratedAbsorber(AbstractAbsorber):
     """AcceleratedAbsorber(T, P, U) -- absorbers.jl:135-157: per-ν linear interpolation of ln σ in ln P at the
     given levels; Σ ignores T (absorbers.jl:203).  update!(A, T) re-evaluates the levels (absorbers.jl:173-200)."""
 
-    def __init__(self, T, P, *absorbers):
+    def __init__(self, T, P, *absorbers, ctx=None):
         U = absorbers[0] if len(absorbers) == 1 and isinstance(absorbers[0], UnifiedAbsorber) \
             else UnifiedAbsorber(*absorbers)
         self.U = U
@@ -157,7 +159,7 @@ class AcceleratedAbsorber(AbstractAbsorber):
         self.P = f64(P[idx])
         self.T = f64(T[idx])
         self.h = C.c_void_p()
-        self._ws = SigmaWorkspace(self.ν, len(self.P))
+        self._ws = SigmaWorkspace(self.ν, len(self.P), ctx or U.ctx)
         self.update(self.T)
 
     def update(self, T):

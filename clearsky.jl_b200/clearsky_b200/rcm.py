@@ -10,6 +10,7 @@ import numpy as np
 from .absorbers import AcceleratedAbsorber, unifyabsorbers
 from .core import Discretized, FluxPack
 from .fluxes import radiate_
+from .sharding import ShardedAbsorber
 from .util import AtmosphericProfile
 
 
@@ -43,13 +44,20 @@ class RCM:
             i += n - 1
         Pr[-1] = self.Pe[-1]
         self.Pr = np.sort(Pr)
-        U, _, nν = unifyabsorbers(absorbers)
-        self.A = U if isinstance(U, AcceleratedAbsorber) else AcceleratedAbsorber(self.Te, self.Pe, U)   # :89
+        if len(absorbers) == 1 and isinstance(absorbers[0], ShardedAbsorber):
+            # ν-sharded over a DeviceGroup: one AcceleratedAbsorber per slice, resident on the GPU that owns it
+            self.A = absorbers[0].accelerate(self.Te, self.Pe)
+            self.sharded = True
+            nν = len(self.A.ν)
+        else:
+            U, _, nν = unifyabsorbers(absorbers)
+            self.A = U if isinstance(U, AcceleratedAbsorber) else AcceleratedAbsorber(self.Te, self.Pe, U)   # :89
+            self.sharded = False
         self.ν, self.nν = self.A.ν, nν
         self.g, self.cs = float(g), float(cs)
         self.fμ, self.fS, self.fa, self.fcp = fμ, fS, fa, fcp
         self.core = core or Discretized()
-        self.F = FluxPack(nrad, nν)
+        self.F = FluxPack(nrad, 1 if self.sharded else nν)     # sharded: only the integrated fluxes come back
         self.np = n
         self.R = np.zeros(n)
         self.H = np.zeros(n)
@@ -58,7 +66,11 @@ class RCM:
     def heating_(self):
         """heating!(ℛ) -- radiative_convective.jl:109-144"""
         fT = AtmosphericProfile(self.P, self.T)
-        radiate_(self.F, self.core, self.Pr, self.g, fT, self.fμ, self.fS, self.fa, self.A, materialize=False)
+        if self.sharded:
+            self.F.Fup[:], self.F.Fdn[:], self.F.Fnet[:] = self.A.fluxes(self.Pr, self.g, fT, self.fμ, self.fS, self.fa,
+                                                                         core=self.core)
+        else:
+            radiate_(self.F, self.core, self.Pr, self.g, fT, self.fμ, self.fS, self.fa, self.A, materialize=False)
         fF = AtmosphericProfile(self.Pr, self.F.Fnet)
         self.R[:] = -fF(self.Pe)
         for i in range(self.np - 1):

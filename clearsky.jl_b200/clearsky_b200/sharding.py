@@ -114,45 +114,63 @@ class DeviceGroup:
             pass
 
 
-class ShardedLineByLine:
-    """Exact line-by-line gases sharded over a DeviceGroup by contiguous ν slices.  Slicing, line uploads and the
-    per-device Σ workspaces are done once; every `fluxes` call is then K1/K2 + K6/K7 per device (one host thread
-    each) and one all-reduce.   gases: list of (SpectralLines, fC, shape, Δνcut)."""
+class ShardedAbsorber:
+    """Any set of absorbers sharded over a DeviceGroup by contiguous ν slices: tables, line
+    gases, CIA and accelerated absorbers stay resident on the GPU that owns the slice; every `fluxes` call is Σ + K6/K7 per
+    device (one host thread each) and ONE all-reduce of the 2·np integrated fluxes.
 
-    def __init__(self, group, gases, ν, cia=()):
-        """cia: iterable of (CIATables, i, j) pairing the tables with gases[i] and gases[j]
-        (CIA functor, collision_induced_absorption.jl:431-465)"""
-        self.cia = list(cia)
+    build(ν_slice, ctx) -> absorber or tuple of absorbers living on `ctx` (e.g. `Gas(sl, fC, ν_slice, Ω, ctx=ctx)`),
+    called once per device; cost: optional per-ν weights used to balance the slices (default: equal point counts)."""
+
+    def __init__(self, group, ν, build, cost=None):
+        from .absorbers import AbstractAbsorber, UnifiedAbsorber
         self.group = group
         self.ν = f64(np.asarray(ν, dtype=np.float64))
         assert np.all(np.diff(self.ν) > 0), "wavenumbers must be unique and in ascending order"
-        self.gases = list(gases)
         n = len(group)
-        cost = sum(slice_cost(self.ν, [sl.ν], cut) for sl, _, _, cut in self.gases)
-        self.edges = balanced_slices(cost, n)
+        self.edges = balanced_slices(np.ones(len(self.ν)) if cost is None else cost, n)
         self.wg = trapz_weights(self.ν)
         self.parts = []
-        for i in range(n):
+
+        def make(i):
             a, b = self.edges[i], self.edges[i + 1]
             if b <= a:
-                self.parts.append(None)
-                continue
+                return None
             νs = np.ascontiguousarray(self.ν[a:b])
-            ctx = group.ctx[i]
-            lg = [LineGas(slice_lines(sl, νs[0], νs[-1], cut), fC, νs, shape, cut, ctx=ctx) for sl, fC, shape, cut in self.gases]
-            self.parts.append(dict(a=a, b=b, ν=νs, gases=lg, ws={}, w=np.ascontiguousarray(self.wg[a:b])))
-        self._pairs = []
-        for x, i, j in self.cia:
-            assert sorted((self.gases[i][0].formula, self.gases[j][0].formula)) == sorted(x.formulae), \
-                f"gases do not match the {x.name} CIA tables"
-            self._pairs.append((x, i, j))
+            objs = build(νs, group.ctx[i])
+            A = objs if isinstance(objs, AbstractAbsorber) else UnifiedAbsorber(*(objs if isinstance(objs, (tuple, list)) else (objs,)))
+            return dict(a=a, b=b, ν=νs, A=A, ws={}, w=np.ascontiguousarray(self.wg[a:b]))
+
+        self.parts = list(group.pool.map(make, range(n)))     # uploads / bakes of all devices run concurrently
+
+    def accelerate(self, T, P):
+        """wrap every slice in an AcceleratedAbsorber built at the levels (T, P) (absorbers.jl:135-157); returns self"""
+        from .absorbers import AcceleratedAbsorber
+
+        def acc(i):
+            part = self.parts[i]
+            if part is not None and not isinstance(part["A"], AcceleratedAbsorber):
+                part["A"] = AcceleratedAbsorber(T, P, part["A"], ctx=self.group.ctx[i])
+        list(self.group.pool.map(acc, range(len(self.group))))
+        return self
+
+    def update(self, T):
+        """update!(A, T) on every slice (absorbers.jl:173-200)"""
+        list(self.group.pool.map(lambda i: self.parts[i] is not None and self.parts[i]["A"].update(T), range(len(self.group))))
+
+    def checkpressures(self, Ps, Pt):
+        for part in self.parts:
+            if part is not None:
+                part["A"].checkpressures(Ps, Pt)
 
     def fluxes(self, P, g, T, μ, fS=None, fa=None, core=None, θs=0.841):
+        """fluxes(P, g, T, μ, 𝒻S, 𝒻a, absorbers...; core, θₛ) (fluxes.jl:311-340) -> (F⁺, F⁻, Fnet)"""
         core = core or Discretized()
         group, n = self.group, len(self.group)
         P = f64(np.asarray(P, dtype=np.float64))
         assert np.all(np.diff(P) >= 0), "pressure coordinates must be in ascending order (sorted)"
         checkazimuth(θs)
+        self.checkpressures(P[-1], P[0])
         fT, fμ = formprofile(P, T), formprofile(P, μ)
         Tl, μl, Pn = lobattoevaluations(P, fT, fμ, core.nlobatto)
         Tn, Pq = _unique_nodes(P, Tl, Pn, core.nlobatto)
@@ -179,12 +197,7 @@ class ShardedLineByLine:
                 ws = part["ws"][len(Tn)] = SigmaWorkspace(part["ν"], len(Tn), ctx)
             else:
                 ws.zero()
-            for lg in part["gases"]:
-                lg.add_to(ws, Tn, Pq)
-            for x, gi, gj in self._pairs:
-                C1 = f64(part["gases"][gi].concentration(Tn, Pq))
-                C2 = f64(part["gases"][gj].concentration(Tn, Pq))
-                check(lib().cs_sigma_add_cia(ws.h, x.handle(ctx), ptr(Tn), ptr(Pq), ptr(C1), ptr(C2)))
+            part["A"].sigma_nodes(ws, Tn, Pq)
             check(lib().cs_fluxes_device(ws.h, npl, ptr(P), core.nlobatto, ptr(wl), ptr(μl), ptr(Tlev), float(g),
                                          ptr(np.ascontiguousarray(fSν[a:b])) if fSν is not None else None,
                                          ptr(np.ascontiguousarray(faν[a:b])) if faν is not None else None,
@@ -194,6 +207,28 @@ class ShardedLineByLine:
         group.allreduce_sum(2 * npl)
         F = group.read(0, 2 * npl)
         return F[:npl].copy(), F[npl:].copy(), F[:npl] - F[npl:]
+
+
+class ShardedLineByLine(ShardedAbsorber):
+    """Exact line-by-line gases sharded over a DeviceGroup: every device uploads only the lines within its slice ± the
+    cut-off, and slices are balanced by the evaluation-count cost model.   gases: list of (SpectralLines, fC, shape, Δνcut);
+    cia: iterable of CIATables (or (CIATables, i, j) tuples), paired with the gases by formula exactly like
+    UnifiedAbsorber does (collision_induced_absorption.jl:431-465)."""
+
+    def __init__(self, group, gases, ν, cia=()):
+        self.gases = list(gases)
+        self.cia = [x[0] if isinstance(x, (tuple, list)) else x for x in cia]
+        ν = f64(np.asarray(ν, dtype=np.float64))
+        cost = sum(slice_cost(ν, [sl.ν], cut) for sl, _, _, cut in self.gases)
+
+        def build(νs, ctx):
+            lg = [LineGas(slice_lines(sl, νs[0], νs[-1], cut), fC, νs, shape, cut, ctx=ctx) for sl, fC, shape, cut in self.gases]
+            return tuple(lg) + tuple(self.cia)
+
+        super().__init__(group, ν, build, cost=cost)
+        for part in self.parts:
+            if part is not None:
+                part["gases"] = list(part["A"].gas)
 
 
 def sharded_fluxes(group, P, g, T, μ, fS, fa, gases, ν, core=None, θs=0.841):

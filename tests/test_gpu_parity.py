@@ -652,6 +652,37 @@ def test_single_process_device_group_with_cia(cs, co2):
     grp.close()
 
 
+def test_sharded_tables_and_rcm(cs, co2, h2o):
+    """ShardedAbsorber: opacity tables baked per ν slice on every device of the group, AcceleratedAbsorber per slice, and the
+    RCM loop on top (BASELINE configs[4]); equals the single-context run"""
+    ν = np.linspace(400.0, 1000.0, 2401)
+    Ω = cs.AtmosphericDomain((140, 320), 8, (5, 1.1e5), 12)
+    Pe = cs.pressuregrid(10.0, 1e5, 13)
+    Γ = cs.DryAdiabat(288.0, 1e5, 1040.0, 0.029, Ptropo=1e4)
+    Te = Γ(Pe)
+    grp = cs.DeviceGroup(list(range(cs.device_count())))
+    sh = cs.ShardedAbsorber(grp, ν, lambda νs, ctx: (cs.Gas(co2, 400e-6, νs, Ω, ctx=ctx), cs.Gas(h2o, 1e-3, νs, Ω, ctx=ctx)))
+    g1, g2 = cs.Gas(co2, 400e-6, ν, Ω), cs.Gas(h2o, 1e-3, ν, Ω)
+    P = cs.pressuregrid(10.0, 1e5, 25)
+    Fup, Fdn, Fnet = sh.fluxes(P, 9.8, Γ, 0.029, lambda x: 0.3 + 0 * x, 0.25)
+    F = cs.radiate(P, 9.8, Γ, 0.029, lambda x: 0.3 + 0 * x, 0.25, g1, g2)
+    assert relerr(Fup, F.Fup) < 1e-12 and relerr(Fdn, F.Fdn) < 1e-12
+    with pytest.raises(AssertionError):
+        sh.fluxes(cs.pressuregrid(1.0, 1e5, 9), 9.8, Γ, 0.029)       # below the table domain (checkpressures)
+    a = cs.RCM(Pe, Te, 9.8, 0.029, None, None, 1040.0, 1e7, sh, radmul=2)
+    b = cs.RCM(Pe, Te, 9.8, 0.029, None, None, 1040.0, 1e7, g1, g2, radmul=2)
+    for _ in range(3):
+        a.step_(3600.0)
+        b.step_(3600.0)
+    assert relerr(a.T, b.T) < 1e-12 and relerr(a.H, b.H, 1e-30) < 1e-9
+    sh.update(a.Te + 1.0)                                               # update! re-snapshots every slice
+    b.A.update(b.Te + 1.0)
+    a.heating_(); b.heating_()
+    assert relerr(a.H, b.H, 1e-30) < 1e-9
+    del a, sh
+    grp.close()
+
+
 def test_line_params_and_functors(cs, orc, co2):
     """vector forms of scaleintensity / αdoppler / γlorentz (line_shapes.jl:125-132,146-148,259-261), the Gas and
     UnifiedAbsorber functors (gases.jl:256-281, absorbers.jl:97-99) and the CIATables functor / cia()"""
