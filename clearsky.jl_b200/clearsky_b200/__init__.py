@@ -10,7 +10,7 @@ from .absorbers import (AcceleratedAbsorber, SigmaWorkspace, UnifiedAbsorber, ge
 from .atmospherics import DryAdiabat
 from .cia import CIA, CIATables, readcia
 from .core import B200Discretized, Discretized, FluxPack
-from .fluxes import (fluxes, monochromaticfluxes, monochromaticfluxes_, netfluxes, opticaldepth, radiate, radiate_,
+from .fluxes import (fluxes, fluxes_batch, monochromaticfluxes, monochromaticfluxes_, netfluxes, opticaldepth, radiate, radiate_,
                      transmittance)
 from .gases import AtmosphericDomain, Gas, GrayGas, LineGas, SemiGrayGas
 from .line_shapes import (PHCO2, PHCO2_b200_inplace, DeviceLines, device_lines, doppler, doppler_b200_inplace,

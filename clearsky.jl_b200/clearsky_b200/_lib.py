@@ -69,6 +69,8 @@ SIGNATURES = {
                   _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp],
     "cs_fluxes_device": [_vp, C.c_int64, _dp, C.c_int32, _dp, _dp, _dp, C.c_double, _dp, _dp, C.c_double,
                          C.c_int32, _dp, _dp, _dp, _vp],
+    "cs_fluxes_batch": [_vp, C.c_int64, _dp, C.c_int32, _dp, _dp, C.c_int64, _dp, C.c_double, _dp, _dp, C.c_double,
+                        C.c_int32, _dp, _dp, _dp, _dp],
     "cs_opticaldepth": [_vp, C.c_int64, _dp, C.c_int32, _dp, _dp, C.c_double, C.c_double, _dp],
     "cs_par_parse": [_vp, C.c_int64, C.c_char_p, C.c_int32, C.c_int64, C.POINTER(C.c_int16), C.POINTER(C.c_int16),
                      _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, C.POINTER(C.c_uint8)],

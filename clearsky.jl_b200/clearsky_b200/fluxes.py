@@ -184,6 +184,30 @@ def fluxes(P, g, T, μ, fS, fa, *absorbers, core=None, θs=0.841):
     return Fup, Fdn
 
 
+def fluxes_batch(P, g, Ts, μ, fS, fa, A, core=None, θs=0.841):
+    """fluxes for several temperature profiles `Ts` (callables or vectors on P) over ONE AcceleratedAbsorber, whose Σ does
+    not depend on T (absorbers.jl:203): all layer depths and transmittances are shared (cs_fluxes_batch).  This is what
+    jacobian! (radiative_convective.jl:154-171) amounts to.  -> F⁺[nbatch, np], F⁻[nbatch, np]"""
+    from .absorbers import AcceleratedAbsorber
+    assert isinstance(A, AcceleratedAbsorber), "batched fluxes need an absorber whose Σ ignores T (AcceleratedAbsorber)"
+    core = core or Discretized()
+    P = f64(np.asarray(P, dtype=np.float64))
+    assert np.all(np.diff(P) >= 0), "pressure coordinates must be in ascending order (sorted)"
+    A.checkpressures(P[-1], P[0])
+    checkstreams(core.nstream)
+    checkazimuth(θs)
+    fTs = [formprofile(P, T) for T in Ts]
+    _, ν, nν, P, _, μl, ws = _prepare(P, fTs[0], μ, (A,), core.nlobatto)      # Σ and μ at the nodes (T-independent here)
+    Tlev = f64(np.stack([_vec(fT, P) for fT in fTs]))
+    m, W = streamnodes(core.nstream)
+    _, w = lobattonodes(core.nlobatto)
+    fSν, faν = _eval_spectral(fS, ν), _eval_spectral(fa, ν)
+    F = np.empty((len(fTs), 2 * len(P)))
+    check(lib().cs_fluxes_batch(ws.h, len(P), ptr(P), core.nlobatto, ptr(f64(w)), ptr(f64(μl)), len(fTs), ptr(Tlev), float(g),
+                                ptr(fSν), ptr(faν), float(θs), core.nstream, ptr(f64(m)), ptr(f64(W)), None, ptr(F)))
+    return F[:, :len(P)].copy(), F[:, len(P):].copy()
+
+
 def netfluxes(P, g, T, μ, fS, fa, *absorbers, **kwargs):
     """fluxes.jl:342-352"""
     Fup, Fdn = fluxes(P, g, T, μ, fS, fa, *absorbers, **kwargs)

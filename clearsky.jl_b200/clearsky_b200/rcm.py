@@ -9,7 +9,7 @@ import numpy as np
 
 from .absorbers import AcceleratedAbsorber, unifyabsorbers
 from .core import Discretized, FluxPack
-from .fluxes import radiate_
+from .fluxes import fluxes_batch, radiate_
 from .sharding import ShardedAbsorber
 from .util import AtmosphericProfile
 
@@ -87,8 +87,36 @@ class RCM:
         self.T += Δt * self.H
         return None
 
-    def jacobian_(self, ϵ=1.0):
-        """jacobian!(ℛ, ϵ) -- radiative_convective.jl:154-171"""
+    def _heating_from(self, Fnet):
+        """the O(np) tail of heating! (radiative_convective.jl:123-143) for a given net-flux profile -> H"""
+        fF = AtmosphericProfile(self.Pr, Fnet)
+        R = -fF(self.Pe)
+        H = np.empty(self.np)
+        for i in range(self.np - 1):
+            cp = self.fcp(self.T[i], self.P[i]) if callable(self.fcp) else float(self.fcp)
+            H[i] = (self.g / cp) * (R[i] - R[i + 1]) / (self.Pe[i + 1] - self.Pe[i])
+        H[-1] = R[-1] / self.cs
+        return H
+
+    def jacobian_(self, ϵ=1.0, batched=True):
+        """jacobian!(ℛ, ϵ) -- radiative_convective.jl:154-171.  The np+1 flux solves differ only in the temperature profile
+        and the AcceleratedAbsorber ignores T, so they run as ONE batched call (cs_fluxes_batch) that shares every layer
+        depth and transmittance; batched=False is the reference's loop of heating! calls."""
+        if batched and not self.sharded and (not callable(self.fμ)):
+            Ts = [self.T.copy()]
+            for i in range(self.np):
+                T = self.T.copy()
+                T[i] += ϵ
+                Ts.append(T)
+            Fup, Fdn = fluxes_batch(self.Pr, self.g, [AtmosphericProfile(self.P, T) for T in Ts], self.fμ, self.fS, self.fa,
+                                    self.A, core=self.core)
+            H0 = self._heating_from(Fup[0] - Fdn[0])
+            self.F.Fup[:], self.F.Fdn[:], self.F.Fnet[:] = Fup[0], Fdn[0], Fup[0] - Fdn[0]
+            self.H[:] = H0
+            self.R[:] = -AtmosphericProfile(self.Pr, self.F.Fnet)(self.Pe)
+            for i in range(self.np):
+                self.J[:, i] = (self._heating_from(Fup[i + 1] - Fdn[i + 1]) - H0) / ϵ
+            return None
         self.heating_()
         H = self.H.copy()
         for i in range(self.np):

@@ -181,6 +181,163 @@ __global__ void __launch_bounds__(RT_THREADS) rt_kernel(RtArgs a)
     }
 }
 
+// ---- batched K6: NB temperature profiles over the SAME optical depths (Sigma does not depend on T for an
+// AcceleratedAbsorber, absorbers.jl:203; jacobian! is np+1 such solves, radiative_convective.jl:154-171).  The layer
+// depths and the (2 ns + 1) transmittances per layer -- all the exponentials except Planck's -- are computed once and
+// shared by the NB recurrences a thread carries in registers.  Only the spectrally integrated fluxes are produced.
+constexpr int RTB_NB = 8;
+struct RtBatchArgs {
+    RtArgs a;
+    int nb;                // profiles in this launch (<= RTB_NB)
+    const double* rkT;     // [nb][np]  1/(k T) per profile and level
+    double* B_b;           // scratch [RTB_NB][np][nnu]
+    double* part_b;        // [nblocks][nb][2][np]
+};
+
+template <int NS>
+__global__ void __launch_bounds__(RT_THREADS) rt_batch_kernel(RtBatchArgs ba)
+{
+    extern __shared__ double sm[];
+    const RtArgs& a = ba.a;
+    const int np = a.np, L = np - 1, nlob = a.nlob, nb = ba.nb;
+    const int ns = (NS > 0) ? NS : a.ns;
+    const int nsmall = np + nlob * L + nlob + np + 3 * ns;
+    double* sP = sm;
+    double* smu = sP + np;
+    double* swl = smu + nlob * L;
+    double* sm_m = swl + nlob + np;
+    double* sW = sm_m + ns;
+    double* srm = sW + ns;
+    double* skT = sm + nsmall;                 // [nb][np]
+    double* red = skT + RTB_NB * np;           // [RTB_NB][2][np][RT_WARPS]
+    for (int t = threadIdx.x; t < nsmall; t += RT_THREADS) sm[t] = a.small[t];
+    for (int t = threadIdx.x; t < RTB_NB * np; t += RT_THREADS) skT[t] = t < nb * np ? ba.rkT[t] : ba.rkT[t % np];
+    for (int t = threadIdx.x; t < RTB_NB * 2 * np * RT_WARPS; t += RT_THREADS) red[t] = 0.0;
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t jraw = (int64_t)blockIdx.x * RT_THREADS + threadIdx.x;
+    const bool live = jraw < a.nnu;
+    const int64_t j = live ? jraw : a.nnu - 1;
+    const int64_t nnu = a.nnu;
+    const double wj = live ? a.w[j] : 0.0;
+    const double nuj = a.nu[j];
+    const double num = 100.0 * nuj;
+    const double hcn = CS_H * CS_C * num;
+    const double pref = 2 * CS_H * (CS_C * CS_C) * (num * num * num);
+    const double Cg = a.Cg;
+    const double c = a.cos_s;
+    const double rc = 1.0 / c;
+    constexpr int NSMAX = (NS > 0) ? NS : CS_MAX_STREAMS;
+    auto planck = [&](int b, int lev) { return 100.0 * pref / (exp(hcn * skT[b * np + lev]) - 1.0); };
+    auto RED = [&](int b, int dir, int lev) -> double& { return red[((b * 2 + dir) * np + lev) * RT_WARPS + warp]; };
+
+    double I[RTB_NB][NSMAX], Bp[RTB_NB];
+#pragma unroll
+    for (int b = 0; b < RTB_NB; b++) {
+#pragma unroll
+        for (int k = 0; k < NSMAX; k++) I[b][k] = 0.0;
+        Bp[b] = planck(b, 0);
+        ba.B_b[((size_t)b * np) * nnu + j] = Bp[b];
+    }
+    double beta1 = Cg * (a.sig[j] / smu[0]);
+    double beam = c * (a.fS ? a.fS[j] : 0.0);
+    {
+        double r = warp_sum(wj * beam);
+        if (lane == 0)
+            for (int b = 0; b < nb; b++) RED(b, 1, 0) += r;
+    }
+    double Mdn[RTB_NB];
+    for (int i = 0; i < L; i++) {
+        double dP = sP[i + 1] - sP[i];
+        double ti = (dP * swl[0]) * beta1;
+        for (int n = 1; n < nlob - 1; n++) {
+            double bn = Cg * (a.sig[(size_t)(n + (nlob - 1) * i) * nnu + j] / smu[n + nlob * i]);
+            ti += (dP * swl[n]) * bn;
+        }
+        double bn = Cg * (a.sig[(size_t)((nlob - 1) * (i + 1)) * nnu + j] / smu[(nlob - 1) + nlob * i]);
+        ti += (dP * swl[nlob - 1]) * bn;
+        beta1 = bn;
+        double tau = fmax(ti, a.tau_floor);
+        a.tau_s[(size_t)i * nnu + j] = tau;
+        const double rtau = cs_rcp(tau);
+        double Bn[RTB_NB], dB[RTB_NB];
+#pragma unroll
+        for (int b = 0; b < RTB_NB; b++) {
+            Bn[b] = planck(b, i + 1);
+            ba.B_b[((size_t)b * np + i + 1) * nnu + j] = Bn[b];
+            dB[b] = Bp[b] - Bn[b];
+            Mdn[b] = 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < NSMAX; k++) {
+            if (k < ns) {
+                // layerplanck(B1,B2) = B2 (1-t) + (B1-B2) ((1-t)/tau_k - t): the two stream factors are shared by all profiles
+                const double tr = exp(-(tau * sm_m[k]));
+                const double c1 = 1.0 - tr, c2 = fma(c1, rtau * srm[k], -tr);
+#pragma unroll
+                for (int b = 0; b < RTB_NB; b++) {
+                    I[b][k] = fma(I[b][k], tr, fma(Bn[b], c1, dB[b] * c2));
+                    Mdn[b] = fma(sW[k], I[b][k], Mdn[b]);
+                }
+            }
+        }
+        beam *= exp(-tau * rc);
+#pragma unroll
+        for (int b = 0; b < RTB_NB; b++) {
+            Mdn[b] += beam;
+            double r = warp_sum(wj * Mdn[b]);
+            if (lane == 0 && b < nb) RED(b, 1, i + 1) += r;
+            Bp[b] = Bn[b];
+        }
+    }
+    const double alb = a.fa ? a.fa[j] : 0.0;
+#pragma unroll
+    for (int b = 0; b < RTB_NB; b++) {
+        const double Is = Mdn[b] * alb / CS_PI + Bp[b];
+        double r = warp_sum(wj * (Is * CS_PI));
+        if (lane == 0 && b < nb) RED(b, 0, L) += r;
+#pragma unroll
+        for (int k = 0; k < NSMAX; k++) I[b][k] = Is;
+    }
+    for (int i = L - 1; i >= 0; i--) {
+        const double tau = a.tau_s[(size_t)i * nnu + j];
+        const double rtau = cs_rcp(tau);
+        double Bn[RTB_NB], Ms[RTB_NB], dB[RTB_NB];
+#pragma unroll
+        for (int b = 0; b < RTB_NB; b++) {
+            Bn[b] = ba.B_b[((size_t)b * np + i) * nnu + j];
+            dB[b] = Bp[b] - Bn[b];
+            Ms[b] = 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < NSMAX; k++) {
+            if (k < ns) {
+                const double tr = exp(-(tau * sm_m[k]));
+                const double c1 = 1.0 - tr, c2 = fma(c1, rtau * srm[k], -tr);
+#pragma unroll
+                for (int b = 0; b < RTB_NB; b++) {
+                    I[b][k] = fma(I[b][k], tr, fma(Bn[b], c1, dB[b] * c2));
+                    Ms[b] = fma(sW[k], I[b][k], Ms[b]);
+                }
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < RTB_NB; b++) {
+            double r = warp_sum(wj * Ms[b]);
+            if (lane == 0 && b < nb) RED(b, 0, i) += r;
+            Bp[b] = Bn[b];
+        }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < nb * 2 * np; t += RT_THREADS) {
+        double s = 0.0;
+#pragma unroll
+        for (int q = 0; q < RT_WARPS; q++) s += red[t * RT_WARPS + q];
+        ba.part_b[(size_t)blockIdx.x * nb * 2 * np + t] = s;
+    }
+}
+
 // K7 second stage: fixed-order sum over CTAs; F[0..np) = up, F[np..2np) = down.  One warp per output: lanes
 // stride over the CTAs in a fixed pattern and finish with a fixed shuffle tree -> run-to-run bit-stable.
 __global__ void __launch_bounds__(128) flux_reduce_kernel(const double* __restrict__ part, int nblocks, int n2, double* F)
@@ -379,6 +536,95 @@ extern "C" int32_t cs_fluxes_device(cs_sigma* s, int64_t np, const double* P, in
     CS_REQUIRE(d_F, CS_ERR_ARG, "null device output");
     return fluxes_impl(s, np, P, nlob, wlob, mu, Tlev, g, fS, fa, theta_s, nstream, m, W, nu_weights, nullptr, nullptr,
                        nullptr, nullptr, d_F);
+}
+
+// fluxes for nbatch temperature profiles over the same Sigma workspace: F[b][0..np) = F+, F[b][np..2np) = F-
+extern "C" int32_t cs_fluxes_batch(cs_sigma* s, int64_t np, const double* P, int32_t nlob, const double* wlob,
+                                   const double* mu, int64_t nbatch, const double* Tlev, double g, const double* fS,
+                                   const double* fa, double theta_s, int32_t nstream, const double* m, const double* W,
+                                   const double* nu_weights, double* F)
+{
+    CS_REQUIRE(s && P && wlob && mu && Tlev && m && W && F, CS_ERR_ARG, "null argument");
+    CS_REQUIRE(nbatch >= 1, CS_ERR_ARG, "empty batch");
+    cs_ctx* ctx = s->ctx;
+    CS_TRY(check_profile_args(s, np, P, nlob));
+    CS_REQUIRE(nstream >= 1 && nstream <= CS_MAX_STREAMS, CS_ERR_ARG, "nstream must be in [1,%d]", CS_MAX_STREAMS);
+    CS_REQUIRE(theta_s >= 0 && theta_s < CS_PI / 2, CS_ERR_ARG, "azimuth angle theta must be in [0,pi/2)");
+    CS_REQUIRE(g > 0, CS_ERR_ARG, "gravity must be positive");
+    std::lock_guard<std::recursive_mutex> lk(ctx->mtx);
+    CS_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int64_t nnu = s->nnu;
+    const int L = (int)np - 1;
+    std::vector<double> small;
+    small.insert(small.end(), P, P + np);
+    small.insert(small.end(), mu, mu + (size_t)nlob * L);
+    small.insert(small.end(), wlob, wlob + nlob);
+    small.insert(small.end(), (size_t)np, 0.0);                 // slot of the single-profile 1/(kT) table (unused here)
+    small.insert(small.end(), m, m + nstream);
+    small.insert(small.end(), W, W + nstream);
+    for (int k = 0; k < nstream; k++) small.push_back(1.0 / m[k]);
+    std::vector<double> rkT((size_t)nbatch * np);
+    for (size_t i = 0; i < rkT.size(); i++) rkT[i] = 1.0 / (CS_KB * Tlev[i]);
+
+    const int nblocks = (int)((nnu + RT_THREADS - 1) / RT_THREADS);
+    auto al = [](size_t b) { return ((b + 255) / 256) * 256; };
+    const size_t off_w = al(small.size() * sizeof(double));
+    const size_t off_fS = off_w + al((size_t)nnu * sizeof(double));
+    const size_t off_fa = off_fS + al((size_t)nnu * sizeof(double));
+    const size_t off_kT = off_fa + al((size_t)nnu * sizeof(double));
+    const size_t off_F = off_kT + al(rkT.size() * sizeof(double));
+    CS_TRY(ctx->s_misc.reserve(off_F + sizeof(double) * 2 * (size_t)np * RTB_NB));
+    char* base = ctx->s_misc.as<char>();
+    CS_CUDA(cudaMemcpyAsync(base, small.data(), small.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (nu_weights) CS_CUDA(cudaMemcpyAsync(base + off_w, nu_weights, sizeof(double) * (size_t)nnu, cudaMemcpyHostToDevice, st));
+    if (fS) CS_CUDA(cudaMemcpyAsync(base + off_fS, fS, sizeof(double) * (size_t)nnu, cudaMemcpyHostToDevice, st));
+    if (fa) CS_CUDA(cudaMemcpyAsync(base + off_fa, fa, sizeof(double) * (size_t)nnu, cudaMemcpyHostToDevice, st));
+    CS_CUDA(cudaMemcpyAsync(base + off_kT, rkT.data(), rkT.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    CS_TRY(ctx->s_tau.reserve(sizeof(double) * (size_t)L * nnu));
+    CS_TRY(ctx->s_planck.reserve(sizeof(double) * (size_t)RTB_NB * np * nnu));
+    CS_TRY(ctx->s_part.reserve(sizeof(double) * (size_t)nblocks * RTB_NB * 2 * np));
+
+    RtBatchArgs ba;
+    RtArgs& a = ba.a;
+    a.sig = s->sig; a.nu = s->nu; a.w = nu_weights ? (const double*)(base + off_w) : s->w;
+    a.fS = fS ? (const double*)(base + off_fS) : nullptr;
+    a.fa = fa ? (const double*)(base + off_fa) : nullptr;
+    a.small = (const double*)base;
+    a.nnu = nnu; a.np = (int)np; a.nlob = nlob; a.ns = nstream;
+    a.Cg = 1e-4 * CS_NA / g;
+    a.cos_s = cos(theta_s);
+    a.tau_floor = ctx->tau_floor;
+    a.tau_s = ctx->s_tau.as<double>(); a.B_s = nullptr;
+    a.tau_out = nullptr; a.Mup_out = nullptr; a.Mdn_out = nullptr; a.part = nullptr;
+    ba.B_b = ctx->s_planck.as<double>();
+    ba.part_b = ctx->s_part.as<double>();
+    const size_t smem = sizeof(double) * (small.size() + (size_t)RTB_NB * np + (size_t)RTB_NB * 2 * np * RT_WARPS);
+    CS_REQUIRE(smem <= 200 * 1024, CS_ERR_ARG, "too many pressure levels for a batched flux call (%lld): per-CTA tables need %zu bytes",
+               (long long)np, smem);
+    CS_CUDA(cudaFuncSetAttribute(rt_batch_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CS_CUDA(cudaFuncSetAttribute(rt_batch_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CS_CUDA(cudaEventRecord(ctx->ev0, st));
+    double* dF = (double*)(base + off_F);
+    for (int64_t b0 = 0; b0 < nbatch; b0 += RTB_NB) {
+        ba.nb = (int)std::min<int64_t>(RTB_NB, nbatch - b0);
+        ba.rkT = (const double*)(base + off_kT) + (size_t)b0 * np;
+        if (nstream == 5) rt_batch_kernel<5><<<nblocks, RT_THREADS, smem, st>>>(ba);
+        else rt_batch_kernel<0><<<nblocks, RT_THREADS, smem, st>>>(ba);
+        CS_CUDA(cudaGetLastError());
+        const int n2 = ba.nb * 2 * (int)np;
+        flux_reduce_kernel<<<(n2 + 3) / 4, 128, 0, st>>>(ba.part_b, nblocks, n2, dF);
+        CS_CUDA(cudaGetLastError());
+        cs_count_launch(ctx, 2);
+        CS_CUDA(cudaMemcpyAsync(F + (size_t)b0 * 2 * np, dF, sizeof(double) * (size_t)n2, cudaMemcpyDeviceToHost, st));
+        CS_CUDA(cudaStreamSynchronize(st));       // dF and the scratch are reused by the next chunk
+    }
+    CS_CUDA(cudaEventRecord(ctx->ev1, st));
+    CS_CUDA(cudaEventSynchronize(ctx->ev1));
+    float ms;
+    CS_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    ctx->last_kernel_ms[CS_T_RT] = ms;
+    return CS_OK;
 }
 
 extern "C" int32_t cs_opticaldepth(cs_sigma* s, int64_t np, const double* P, int32_t nlob, const double* wlob,

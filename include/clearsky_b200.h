@@ -191,6 +191,13 @@ int32_t cs_fluxes_device(cs_sigma* sig, int64_t np, const double* P, int32_t nlo
                          const double* mu, const double* Tlev, double g, const double* fS,
                          const double* fa, double theta_s, int32_t nstream, const double* m,
                          const double* W, const double* nu_weights, double* d_F);
+/* jacobian!(R, eps) (src/radiative_convective.jl:154-171) is np+1 flux solves that differ only in the temperature
+ * profile.  When Sigma does not depend on T (AcceleratedAbsorber, absorbers.jl:203) they share every layer depth and
+ * transmittance: cs_fluxes_batch runs nbatch profiles Tlev[nbatch][np] over ONE workspace, eight per launch, and returns
+ * only the integrated fluxes F[nbatch][2*np] (F+ then F- per profile).  Same arguments as cs_fluxes otherwise. */
+int32_t cs_fluxes_batch(cs_sigma* sig, int64_t np, const double* P, int32_t nlob, const double* wlob, const double* mu,
+                        int64_t nbatch, const double* Tlev, double g, const double* fS, const double* fa, double theta_s,
+                        int32_t nstream, const double* m, const double* W, const double* nu_weights, double* F);
 /* opticaldepth(P::Vector, g, T, mu, theta, absorbers...; nlobatto) (src/fluxes.jl:68-97,
  * core/discretized.jl:92-134): total slant-path optical depth per wavenumber, no floor. */
 int32_t cs_opticaldepth(cs_sigma* sig, int64_t np, const double* P, int32_t nlob, const double* wlob,

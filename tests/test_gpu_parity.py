@@ -518,6 +518,34 @@ def test_rcm_heating_and_step(cs, orc, co2):
         assert np.max(np.abs(rcm.T - T)) < 1e-9 * np.max(T)
 
 
+def test_rcm_jacobian_batched(cs, co2):
+    """jacobian! (radiative_convective.jl:154-171): the np+1 flux solves as one batched call (cs_fluxes_batch, shared
+    layer depths and transmittances) equal the reference's loop of heating! calls; 11 profiles = two launches (8 + 3);
+    with sun and albedo, nstream 5 (specialised kernel) and 3 (generic kernel)"""
+    ν = np.linspace(50.0, 2000.0, 777)
+    Pe = cs.pressuregrid(50.0, 1e5, 10)
+    Te = cs.DryAdiabat(288.0, 1e5, 1040.0, 0.029, Ptropo=1.5e4)(Pe)
+    Ω = cs.AtmosphericDomain((120, 330), 8, (20, 1.1e5), 12)
+    gas = cs.Gas(co2, 400e-6, ν, Ω)
+    fS = lambda x: 0.3 * np.exp(-((x - 1200.0) / 500.0) ** 2)
+    for core in (cs.Discretized(5, 2), cs.Discretized(3, 3)):
+        a = cs.RCM(Pe, Te, 9.8, 0.029, fS, 0.25, 1040.0, 1e7, gas, radmul=2, core=core)
+        b = cs.RCM(Pe, Te, 9.8, 0.029, fS, 0.25, 1040.0, 1e7, gas, radmul=2, core=core)
+        a.jacobian_(0.5)
+        b.jacobian_(0.5, batched=False)
+        b.heating_()          # the loop leaves H and F of the last perturbed profile behind; the batch leaves the base state
+        assert np.max(np.abs(a.H - b.H)) < 1e-10 * np.max(np.abs(b.H)) and relerr(a.F.Fnet, b.F.Fnet) < 1e-11
+        assert np.max(np.abs(a.J - b.J)) < 1e-9 * np.max(np.abs(b.J))
+    # the batched entry point on its own: every profile equals a plain fluxes() call
+    A = cs.AcceleratedAbsorber(Te, Pe, gas)
+    P = cs.pressuregrid(50.0, 1e5, 19)
+    Ts = [cs.AtmosphericProfile(Pe, Te + d) for d in (0.0, 3.0, -7.0)]
+    Fup, Fdn = cs.fluxes_batch(P, 9.8, Ts, 0.029, fS, 0.25, A)
+    for k, fT in enumerate(Ts):
+        u, d = cs.fluxes(P, 9.8, fT, 0.029, fS, 0.25, A)
+        assert relerr(Fup[k], u) < 1e-11 and relerr(Fdn[k], d) < 1e-11
+
+
 def test_full_size_properties_c2(cs):
     """BASELINE configs[1] at FULL size (500k lines, 300k ν, 101 levels): size-independent properties.
     (1) additivity over a partition of the line list, (2) ν-sharding invariance of the spectrally integrated fluxes

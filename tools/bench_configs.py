@@ -113,9 +113,20 @@ def c5(small):
         rcm.step_(600.0)
     dt = time.perf_counter() - t0
     tm = cs.default_context().timers()
+    # jacobian!: np+1 = 52 flux solves, as one batched call and as the reference's loop
+    rcm.jacobian_(1.0)
+    t0 = time.perf_counter()
+    rcm.jacobian_(1.0)
+    tjb = time.perf_counter() - t0
+    tjk = cs.default_context().timers()["rt"]
+    t0 = time.perf_counter()
+    rcm.jacobian_(1.0, batched=False)
+    tjl = time.perf_counter() - t0
     return {"config": "c5", "n_nu": nν, "nrad": len(rcm.Pr), "steps": steps, "steps_per_s": steps / dt, "ms_per_step": dt / steps * 1e3,
             "rt_kernel_ms": tm["rt"], "reduce_kernel_ms": tm["reduce"], "accelerated_absorber_setup_s": tsetup,
-            "OLR": float(rcm.F.Fup[0]), "Tsurf": float(rcm.T[-1])}
+            "OLR": float(rcm.F.Fup[0]), "Tsurf": float(rcm.T[-1]),
+            "jacobian_profiles": rcm.np + 1, "jacobian_batched_ms": tjb * 1e3, "jacobian_batched_kernels_ms": tjk,
+            "jacobian_loop_ms": tjl * 1e3}
 
 
 def c5sharded(small):
