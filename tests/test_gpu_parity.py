@@ -58,10 +58,11 @@ def test_xsec_fine_grid_all_regions(cs, orc, name, sid, cut):
 def expansion(cs):
     """switch the default context to the far-field expansion for one test"""
     ctx = cs.default_context()
+    prev = ctx.get_farfield()        # "direct" unless the suite runs with CS_FARFIELD=expansion
     ctx.set_farfield("expansion")
     assert ctx.get_farfield() == "expansion"
     yield ctx
-    ctx.set_farfield("direct")
+    ctx.set_farfield(prev)
 
 
 @pytest.mark.parametrize("name,sid", [("lorentz", 1), ("voigt", 2)])
