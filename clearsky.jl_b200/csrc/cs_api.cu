@@ -233,6 +233,12 @@ extern "C" int32_t cs_lines_upload(cs_ctx* ctx, int64_t n, const double* nu, con
     L->h_nu.assign(nu, nu + n);
     L->mu_min = mu[0];
     for (int64_t j = 1; j < n; j++) L->mu_min = std::min(L->mu_min, mu[j]);
+    L->g_max = 0.0; L->na_min = na[0]; L->na_max = na[0];
+    for (int64_t j = 0; j < n; j++) {
+        L->g_max = std::max(L->g_max, std::max(ga[j], gs[j]));
+        L->na_min = std::min(L->na_min, na[j]);
+        L->na_max = std::max(L->na_max, na[j]);
+    }
     cudaStream_t st = ctx->stream;
     int32_t rc = CS_OK;
     if ((rc = upload(&L->nu, nu, n, st)) || (rc = upload(&L->S, S, n, st)) || (rc = upload(&L->ga, ga, n, st)) ||

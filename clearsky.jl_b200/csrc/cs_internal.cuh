@@ -113,6 +113,7 @@ struct cs_lines {
     double* cheb;     // [niso][CS_MAXCHEB]
     std::vector<double> h_nu;  // host copy of line positions (window searches, eval counting)
     double mu_min;             // lightest isotopologue present (bounds the Doppler width)
+    double g_max, na_min, na_max;   // max(gamma_a, gamma_s) and the range of the temperature exponent (bound gamma per level)
 };
 
 struct cs_sigma {

@@ -49,12 +49,16 @@ constexpr int LS_STAGES = CS_LS_STAGES;
 constexpr int LS_QCAP = 256;                      // per-warp queue of evaluations that need the general routine
 constexpr int MP_P = 20;                          // order of the far-field expansion
 constexpr double MP_THETA = 4.0;                  // separation (in half tile widths) beyond which lines are expanded
+// PHCO2 far wings (|dnu| >= 30 cm^-1 for every point of the tile): orders of the three power-law series (see the kernel)
+constexpr int PX_P2 = 10, PX_P4 = 6, PX_P6 = 4;
+constexpr double PX_HMAX = 2.0;                   // half tile widths above this keep the pair-by-pair sum (ratio h/|u| <= 1/16)
+constexpr int LS_NSEG = 9;                        // segments of the chunk stream (expansion segments first)
 
 struct LevelParams {
     double T, P, Pp, scale;
     double B1, B2;   // PHCO2 chi coefficients of this level (line_shapes.jl:472,476)
     double cnear;    // lines with |nul - nu| > cnear*nul are safely in the far wing at this level (< 0: no near range)
-    double pad1;
+    double pexp_ok;  // PHCO2: 1 when (chi*gamma/dnu)^2 < 1e-4 for every line with |dnu| >= 30 at this level (expansion allowed)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -448,7 +452,7 @@ __global__ void __launch_bounds__(LS_THREADS, 16 / LS_WARPS) line_sum_kernel(Lin
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[LS_WARPS][LS_STAGES];
-    __shared__ int seg_tab[LS_WARPS][16];   // per warp: 5 segment starts, 5 ends, 5 chunk counts (window-relative)
+    __shared__ int seg_tab[LS_WARPS][3 * LS_NSEG];   // per warp: segment starts, ends, chunk counts (window-relative)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int lev = blockIdx.y;
@@ -496,35 +500,83 @@ __global__ void __launch_bounds__(LS_THREADS, 16 / LS_WARPS) line_sum_kernel(Lin
     nlo = min(max(nlo, ilo), ihi);
     nhi = min(max(nhi, nlo), ihi);
     if (mp) { mlo = min(mlo, nlo); mhi = max(mhi, nhi); }   // never expand lines of the near-centre range
-    // segments streamed through the ring, in this order; a chunk never spans two segments.
-    //   expansion: [ilo,mlo) [mhi,ihi)      direct: [0,ilo) [mlo,mhi) [ihi,whi)   (one direct segment [0,whi) without mp)
+    // ---- PHCO2 chi-class borders (window-relative), needed before the chunk stream is laid out
+    //   E | F4- | G | F3- | G | F2- | G | plain | near | plain | G | F2+ | G | F3+ | G | F4+ | E
+    constexpr size_t EXTRA_ = ls_extra_bytes<SHAPE, R>();
+    int* bnd = reinterpret_cast<int*>(xb + EXTRA_) - 36;      // last 18 int64 slots of the warp's extras hold 18 ints
+    if (SHAPE == CS_PHCO2) {
+        if (lane == 0) {
+            int b[18];
+            b[0] = 0; b[1] = ilo;
+            for (int k = 0; k < 6; k++) b[2 + k] = min(max(rel(6 + k), ilo), nlo);    // never intrude into the near range
+            b[8] = nlo; b[9] = nhi;
+            for (int k = 0; k < 6; k++) b[10 + k] = max(min(rel(12 + k), ihi), nhi);
+            b[16] = ihi; b[17] = whi;
+            for (int k = 1; k < 18; k++) b[k] = max(b[k], b[k - 1]);
+            for (int k = 0; k < 18; k++) bnd[k] = b[k];
+        }
+        __syncwarp();
+    }
+    // PHCO2 far-wing expansion: classes F3 and F4 (|dnu| >= 30 for every point of the tile) of a narrow enough tile at a
+    // level where the chi*gamma correction series converges fast (flag set by the host)
+    const double tile_h = 0.5 * (a.nu[min(tile0 + TILE, a.nnu) - 1] - a.nu[tile0]);
+    const bool px = SHAPE == CS_PHCO2 && a.mp_theta > 0.0 && lp.pexp_ok > 0.0 && tile_h <= PX_HMAX;
+    // segments streamed through the ring, in this order; a chunk never spans two segments.  The first NA segments are
+    // summed through expansions (phase A), the others pair by pair (phase B).
+    //   Voigt/Lorentz: A = [ilo,mlo) [mhi,ihi)                 B = [0,ilo) [mlo,mhi) [ihi,whi)
+    //   PHCO2:         A = F4- F3- F3+ F4+                      B = the five ranges between and around them
+    //   no expansion:  A empty, B = [0,whi)
     // (kept in shared memory: indexed dynamically by the chunk number, warp-uniform)
+    constexpr int NA = SHAPE == CS_PHCO2 ? 4 : 2;
+    const bool multi = mp || px;
     int* slo = seg_tab[warp];
-    int* shi = seg_tab[warp] + 5;
-    int* sch = seg_tab[warp] + 10;
+    int* shi = seg_tab[warp] + LS_NSEG;
+    int* sch = seg_tab[warp] + 2 * LS_NSEG;
     if (lane == 0) {
-        slo[0] = ilo; shi[0] = mp ? mlo : ilo;
-        slo[1] = mhi; shi[1] = mp ? ihi : mhi;
-        slo[2] = 0;   shi[2] = mp ? ilo : whi;
-        slo[3] = mlo; shi[3] = mp ? mhi : mlo;
-        slo[4] = ihi; shi[4] = mp ? whi : ihi;
-        for (int q = 0; q < 5; q++) sch[q] = (shi[q] - slo[q] + LS_CHUNK - 1) / LS_CHUNK;
+        for (int q = 0; q < LS_NSEG; q++) { slo[q] = 0; shi[q] = 0; }
+        if (mp) {
+            slo[0] = ilo; shi[0] = mlo;
+            slo[1] = mhi; shi[1] = ihi;
+            slo[2] = 0;   shi[2] = ilo;
+            slo[3] = mlo; shi[3] = mhi;
+            slo[4] = ihi; shi[4] = whi;
+        } else if (px) {
+            slo[0] = bnd[1];  shi[0] = bnd[2];     // F4-
+            slo[1] = bnd[3];  shi[1] = bnd[4];     // F3-
+            slo[2] = bnd[13]; shi[2] = bnd[14];    // F3+
+            slo[3] = bnd[15]; shi[3] = bnd[16];    // F4+
+            slo[4] = 0;       shi[4] = bnd[1];
+            slo[5] = bnd[2];  shi[5] = bnd[3];
+            slo[6] = bnd[4];  shi[6] = bnd[13];
+            slo[7] = bnd[14]; shi[7] = bnd[15];
+            slo[8] = bnd[16]; shi[8] = whi;
+        } else {
+            shi[NA] = whi;
+        }
+        for (int q = 0; q < LS_NSEG; q++) sch[q] = (shi[q] - slo[q] + LS_CHUNK - 1) / LS_CHUNK;
     }
     __syncwarp();
-    const int nchunkA = sch[0] + sch[1];
-    const int nchunk = nchunkA + sch[2] + sch[3] + sch[4];
+    int nchunkA = 0, nchunk = 0;
+#pragma unroll
+    for (int q = 0; q < LS_NSEG; q++) {
+        if (q < NA) nchunkA += sch[q];
+        nchunk += sch[q];
+    }
     const double4* rec_lev = a.rec + (size_t)lev * a.nl + wlo64;          // records of the window
     if (w.slow_lev) w.slow_lev += wlo64;
-    auto chunk_bounds = [&](int c, int& c0, int& c1) {
-        if (!mp) {            // one segment
+    // chunk number -> line range [c0,c1); returns the segment index
+    auto chunk_bounds = [&](int c, int& c0, int& c1) -> int {
+        int q = NA;
+        if (!multi) {            // one segment
             c0 = c * LS_CHUNK;
+            c1 = min(c0 + LS_CHUNK, whi);
         } else {
-            int q = 0;
-            while (q < 4 && c >= sch[q]) { c -= sch[q]; q++; }
+            q = 0;
+            while (q < LS_NSEG - 1 && c >= sch[q]) { c -= sch[q]; q++; }
             c0 = slo[q] + c * LS_CHUNK;
-            c1 = shi[q];
+            c1 = min(c0 + LS_CHUNK, shi[q]);
         }
-        c1 = min(c0 + LS_CHUNK, mp ? c1 : whi);
+        return q;
     };
 
     auto issue = [&](int c) {   // lane 0 only
@@ -554,7 +606,6 @@ __global__ void __launch_bounds__(LS_THREADS, 16 / LS_WARPS) line_sum_kernel(Lin
     // F = exp(-c0 - B (+-(nu0 - nul) - a)): one multiplication per evaluation instead of one exp.
     double* Etab = reinterpret_cast<double*>(w.queue + LS_QCAP);
     double* Fp = Etab + 6 * TILE;
-    int* bnd = reinterpret_cast<int*>(Fp + LS_CHUNK);
     const double nu0 = w.nutile[0];
     if (SHAPE == CS_PHCO2) {
         const double Bc[3] = {lp.B1, lp.B2, 0.0232};
@@ -566,18 +617,6 @@ __global__ void __launch_bounds__(LS_THREADS, 16 / LS_WARPS) line_sum_kernel(Lin
                 Etab[(2 * cc + 0) * TILE + 32 * r + lane] = exp(-Bc[cc] * dx);   // line below the point
                 Etab[(2 * cc + 1) * TILE + 32 * r + lane] = exp(Bc[cc] * dx);    // line above the point
             }
-        }
-        if (lane == 0) {
-            // segment borders in line order:
-            // E | F4- | G | F3- | G | F2- | G | plain | near | plain | G | F2+ | G | F3+ | G | F4+ | E
-            int b[18];
-            b[0] = 0; b[1] = ilo;
-            for (int k = 0; k < 6; k++) b[2 + k] = min(max(rel(6 + k), ilo), nlo);    // never intrude into the near range
-            b[8] = nlo; b[9] = nhi;
-            for (int k = 0; k < 6; k++) b[10 + k] = max(min(rel(12 + k), ihi), nhi);
-            b[16] = ihi; b[17] = whi;
-            for (int k = 1; k < 18; k++) b[k] = max(b[k], b[k - 1]);
-            for (int k = 0; k < 18; k++) bnd[k] = b[k];
         }
         __syncwarp();
     }
@@ -641,6 +680,92 @@ __global__ void __launch_bounds__(LS_THREADS, 16 / LS_WARPS) line_sum_kernel(Lin
             for (int k = MP_P - 2; k >= 0; k--) v = fma(v, t, am[k]);
             acc[r] = v;
         }
+    }
+
+    // ---- phase A, PHCO2: far wings of class F3 / F4 lines (|dnu| >= 30 cm^-1 for every point of the tile).  With
+    // ge = chi*gamma = E(nu) Fg (per-point factor E, per-line factor Fg as in the direct path) and eps = (ge/dnu)^2,
+    //   K ge/(dnu^2 + ge^2) = K ge/dnu^2 (1 - eps + eps^2 - ...) = E [K Fg/dnu^2] - E^3 [K Fg^3/dnu^4] + E^5 [K Fg^5/dnu^6] - ...
+    // (eps < 1e-4 at the levels the host enables, so the first neglected term is below 1e-12), and each bracket, summed over
+    // the lines, is a power law expanded about the tile centre: with u = nul - cen, r = h/u, t = (nu - cen)/h,
+    //   1/(h t - u)^(2m) = u^(-2m) sum_k C(k+2m-1, k) r^k t^k,   |r| <= 1/16 because |u| >= 30 + h and h <= 2,
+    // so a lane only accumulates the power sums G_m[k] = sum_j w_j r_j^k (2 FP64 ops per term); 10 / 6 / 4 terms keep the
+    // truncation below 1e-11 of the line's own value.  One exp per line (its chi factor) instead of one per evaluation
+    // or one multiplication per evaluation in the factorised direct path.
+    if (px && nchunkA > 0) {
+        const double cen = 0.5 * (w.nutile[0] + a.nu[min(tile0 + TILE, a.nnu) - 1]);
+        const double h = tile_h;
+        const double ih = h > 0.0 ? 1.0 / h : 0.0;
+        constexpr int NG = PX_P2 + PX_P4 + PX_P6;
+        double G[NG];
+        int cur = -1;
+        auto flush = [&](int q) {
+            // q: 0 F4-, 1 F3-, 2 F3+, 3 F4+  ->  chi class 2,1,1,2 and side below/below/above/above
+            const int tab = q == 0 ? 4 : (q == 1 ? 2 : (q == 2 ? 3 : 5));
+#pragma unroll
+            for (int k = 0; k < NG; k++) {
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) G[k] += __shfl_xor_sync(0xffffffffu, G[k], off);
+            }
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const double t = (nup[r] - cen) * ih;
+                const double E = Etab[tab * TILE + 32 * r + lane], E2 = E * E;
+                double p2 = (double)PX_P2 * G[PX_P2 - 1];
+#pragma unroll
+                for (int k = PX_P2 - 2; k >= 0; k--) p2 = fma(p2, t, (double)(k + 1) * G[k]);
+                double p4 = (double)((PX_P4 + 2) * (PX_P4 + 1) * PX_P4 / 6) * G[PX_P2 + PX_P4 - 1];
+#pragma unroll
+                for (int k = PX_P4 - 2; k >= 0; k--) p4 = fma(p4, t, (double)((k + 3) * (k + 2) * (k + 1) / 6) * G[PX_P2 + k]);
+                double p6 = (double)((PX_P6 + 4) * (PX_P6 + 3) * (PX_P6 + 2) * (PX_P6 + 1) * PX_P6 / 120) * G[NG - 1];
+#pragma unroll
+                for (int k = PX_P6 - 2; k >= 0; k--)
+                    p6 = fma(p6, t, (double)((k + 5) * (k + 4) * (k + 3) * (k + 2) * (k + 1) / 120) * G[PX_P2 + PX_P4 + k]);
+                acc[r] = fma(E, fma(-E2, fma(-E2, p6, p4), p2), acc[r]);
+            }
+        };
+        for (int c = 0; c < nchunkA; c++) {
+            const int s = c % LS_STAGES;
+            const uint32_t ph = (c / LS_STAGES) & 1;
+            int c0, c1;
+            const int q = chunk_bounds(c, c0, c1);
+            if (q != cur) {
+                if (cur >= 0) flush(cur);
+                cur = q;
+#pragma unroll
+                for (int k = 0; k < NG; k++) G[k] = 0.0;
+            }
+            mbar_wait(&full_bar[warp][s], ph);
+            const double4* st = ring + (size_t)s * LS_CHUNK;
+            const int n = c1 - c0;
+            const bool up = q >= 2;
+            const bool cls2 = (q == 0) || (q == 3);
+            const double B = cls2 ? 0.0232 : lp.B2;
+            const double c0c = cls2 ? lp.B1 * 27.0 + lp.B2 * 90.0 : lp.B1 * 27.0;
+            const double aa = cls2 ? 120.0 : 30.0;
+            for (int jj = lane; jj < n; jj += 32) {
+                const double4 rc = st[jj];
+                const double d = up ? (rc.x - nu0) - aa : (nu0 - rc.x) - aa;
+                const double Fg = exp(-c0c - B * d) * rc.y;                  // chi's line factor times gamma
+                const double u = rc.x - cen;
+                const double iu = copysign(cs_rcp(fabs(u)), u);
+                const double r = h * iu, iu2 = iu * iu, Fg2 = Fg * Fg;
+                double w2 = (rc.z * Fg) * iu2;
+                double w4 = (w2 * Fg2) * iu2;
+                double w6 = (w4 * Fg2) * iu2;
+#pragma unroll
+                for (int k = 0; k < PX_P2; k++) { G[k] += w2; w2 *= r; }
+#pragma unroll
+                for (int k = 0; k < PX_P4; k++) { G[PX_P2 + k] += w4; w4 *= r; }
+#pragma unroll
+                for (int k = 0; k < PX_P6; k++) { G[PX_P2 + PX_P4 + k] += w6; w6 *= r; }
+            }
+            __syncwarp();
+            if (lane == 0 && c + LS_STAGES < nchunk) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                issue(c + LS_STAGES);
+            }
+        }
+        if (cur >= 0) flush(cur);
     }
 
     for (int c = nchunkA; c < nchunk; c++) {
@@ -814,7 +939,7 @@ template <int SHAPE, int R> int32_t launch_line_sum(cs_ctx* ctx, LineSumArgs a, 
     constexpr int TILE = 32 * R;
     cudaStream_t st = ctx->stream;
     a.ntiles = (a.nnu + TILE - 1) / TILE;
-    if (!(SHAPE == CS_VOIGT || SHAPE == CS_LORENTZ)) a.mp_theta = 0.0;
+    if (SHAPE == CS_DOPPLER) a.mp_theta = 0.0;
     a.nr = (SHAPE == CS_PHCO2) ? LS_NR : (a.mp_theta > 0.0 ? 8 : 6);
     CS_TRY(ctx->s_w.reserve(sizeof(int64_t) * a.nr * (size_t)a.ntiles));
     a.ranges = ctx->s_w.as<int64_t>();
@@ -951,7 +1076,15 @@ int32_t cs_lines_accumulate(cs_lines* L, int32_t shape, int64_t nnu, const doubl
                 lp.cnear = sqrt(746.0) * vth * (1.0 + 1e-6);
             else
                 lp.cnear = -1.0;
-            lp.pad1 = 0;
+            // PHCO2 far-wing expansion: allowed where eps = (chi*gamma/dnu)^2 < 1e-4 for every line with |dnu| >= 30:
+            // gamma <= (296/T)^na * max(gamma_a, gamma_s) * P/atm, chi <= exp(-27 B1) there (B2 and 0.0232 are positive)
+            {
+                double tr = CS_TREF / lp.T;
+                double gb = std::max(pow(tr, L->na_min), pow(tr, L->na_max)) * L->g_max * (lp.P / CS_ATM);
+                double chimax = exp(-27.0 * lp.B1);
+                double e = chimax * gb / 30.0;
+                lp.pexp_ok = (e * e < 1e-4) ? 1.0 : 0.0;
+            }
         }
         // pageable H2D of a few KB; synchronous with respect to the host buffer
         CS_CUDA(cudaMemcpyAsync(ctx->s_lev.p, hl.data(), sizeof(LevelParams) * (size_t)kb, cudaMemcpyHostToDevice, st));

@@ -69,15 +69,20 @@ int32_t cs_ctx_synchronize(cs_ctx* ctx);
 /* timers[CS_NTIMERS] of the last compute call; launches = kernels launched so far on this context */
 int32_t cs_ctx_timers(cs_ctx* ctx, double* timers_ms);
 int32_t cs_ctx_launches(cs_ctx* ctx, int64_t* launches);
-/* Far-wing treatment of the windowed line sum (Voigt and Lorentz; PHCO2 and Doppler always sum directly).
+/* Far-wing treatment of the windowed line sum (Voigt, Lorentz, PHCO2; Doppler far lines contribute exactly 0).
  *   CS_FARFIELD_DIRECT (default): every (nu, line) pair inside the cut-off is evaluated, as surf! does
  *     (src/absorption/line_shapes.jl:53-87).
- *   CS_FARFIELD_EXPANSION: lines that are inside the cut-off for ALL points of a 128-point tile, provably in the
- *     far wing (where the reference's Voigt equals S*gamma/(pi*(dnu^2+gamma^2))) and at least 4 half tile widths
- *     from the tile centre are summed through a 20-term local Taylor expansion about the tile centre; the
- *     truncation error is below 3e-11 of each line's own contribution (all contributions are positive), i.e. two
- *     orders inside the 1e-9 parity tolerance.  Everything else (cut-off edges, near lines, line centres) is
- *     evaluated exactly as in the direct mode.
+ *   CS_FARFIELD_EXPANSION: lines that are inside the cut-off for ALL points of a 128-point tile and provably in the
+ *     far wing are summed through local expansions about the tile centre instead of pair by pair.
+ *       Voigt / Lorentz: lines at least 4 half tile widths away, where the reference's Voigt equals
+ *         S*gamma/(pi*(dnu^2+gamma^2)): 20-term Taylor expansion, truncation below 3e-11 of each line's own value.
+ *       PHCO2: lines at least 30 cm^-1 from every point of the tile (chi classes 30-120 and >= 120, where chi factorises
+ *         into a per-point and a per-line exponential): power-law expansions of K ge/dnu^2 (1 - eps + eps^2),
+ *         eps = (chi*gamma/dnu)^2, used only at levels where the host bounds eps < 1e-4 and for tiles narrower than
+ *         4 cm^-1; truncation below 1e-11.
+ *     All contributions are positive, so these bounds also hold for the sum: two orders inside the 1e-9 parity
+ *     tolerance.  Everything else (cut-off edges, near lines, line centres, chi-class borders) is evaluated exactly as
+ *     in the direct mode.
  * The CS_FARFIELD environment variable ("direct" | "expansion") sets the default of new contexts. */
 #define CS_FARFIELD_DIRECT 0
 #define CS_FARFIELD_EXPANSION 1

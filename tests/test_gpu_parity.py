@@ -108,8 +108,8 @@ def test_fluxes_farfield_expansion(cs, orc, co2, expansion):
 
 
 def test_farfield_expansion_corner_cases(cs, orc, co2, expansion):
-    """expansion mode on degenerate grids (one / two points: zero-width tile), through cs_bake, and on the shapes it does
-    not apply to (PHCO2, Doppler must be bit-identical to the direct mode)"""
+    """expansion mode on degenerate grids (one / two points: zero-width tile), through cs_bake, and on the shape it does
+    not apply to (Doppler must be bit-identical to the direct mode)"""
     sl = synthetic_lines(cs, 4000, seed=23, νmax=150.0)
     T, P, Pp = np.array([200.0, 290.0]), np.array([2e3, 9e4]), np.array([1.0, 40.0])
     for ν in (np.array([75.0]), np.array([40.0, 110.0]), 70.0 + 1e-4 * np.arange(257)):
@@ -117,12 +117,11 @@ def test_farfield_expansion_corner_cases(cs, orc, co2, expansion):
             got = cs.xsec(name, ν, sl, T, P, Pp, 25.0)
             assert relerr(got, orc.xsec(sid, sl, ν, T, P, Pp, 25.0, nthreads=0), 1e-290) < XSEC_TOL
     ν = 60.0 + 0.01 * np.arange(2000)
-    for name in ("PHCO2", "doppler"):
-        x = cs.xsec(name, ν, sl, T, P, Pp, 25.0)
-        expansion.set_farfield("direct")
-        d = cs.xsec(name, ν, sl, T, P, Pp, 25.0)
-        expansion.set_farfield("expansion")
-        assert np.array_equal(x, d)
+    x = cs.xsec("doppler", ν, sl, T, P, Pp, 25.0)
+    expansion.set_farfield("direct")
+    d = cs.xsec("doppler", ν, sl, T, P, Pp, 25.0)
+    expansion.set_farfield("expansion")
+    assert np.array_equal(x, d)
     # bake with the expansion on: table values against the oracle's direct bake + fit
     ν = 620.0 + 0.01 * np.arange(3000)
     Ω = cs.AtmosphericDomain((150, 300), 6, (10, 1e5), 8)
@@ -636,6 +635,30 @@ def test_phco2_all_chi_classes(cs, orc):
     got = cs.xsec("PHCO2", ν2, sl, T, P, 0.5 * P, 500.0)
     ref = orc.xsec(orc.PHCO2, sl, ν2, T, P, 0.5 * P, 500.0, nthreads=0)
     assert relerr(got, ref, 1e-290) < XSEC_TOL
+
+
+def test_phco2_farfield_expansion(cs, orc, expansion):
+    """expansion mode for PHCO2: the F3/F4 chi classes (|dnu| >= 30 for the whole tile) go through power-law expansions
+    with the chi*gamma correction series; parity against the oracle at 1e-9 and against the direct mode at 1e-10, over
+    pressures from 10 Pa to 2 bar, at 50 bar (series not allowed by the host bound: direct sum), on a grid with wide
+    tiles (no expansion) and with cut-offs that remove some classes"""
+    sl = synthetic_lines(cs, 8000, seed=29, νmax=1500.0)
+    ν = 700.0 + 0.01 * np.arange(2900)
+    T = np.array([120.0, 200.0, 250.0, 310.0, 250.0])
+    P = np.array([10.0, 3e3, 2e5, 2e5, 5e6])
+    for cut, Pp in ((500.0, P), (500.0, 0.3 * P), (100.0, P), (25.0, P)):
+        got = cs.xsec("PHCO2", ν, sl, T, P, Pp, cut)
+        assert relerr(got, orc.xsec(orc.PHCO2, sl, ν, T, P, Pp, cut, nthreads=0), 1e-290) < XSEC_TOL
+        expansion.set_farfield("direct")
+        direct = cs.xsec("PHCO2", ν, sl, T, P, Pp, cut)
+        expansion.set_farfield("expansion")
+        assert relerr(got, direct, 1e-290) < 1e-10
+        if cut == 500.0:
+            assert not np.array_equal(got[2], direct[2])      # the expansion really ran at 2 bar
+            assert np.array_equal(got[4], direct[4])          # ... and did not at 50 bar
+    ν2 = np.unique(np.concatenate([np.linspace(300, 300.9, 100), np.linspace(301, 330, 120), np.linspace(331, 900, 130)]))
+    got = cs.xsec("PHCO2", ν2, sl, T, P, 0.5 * P, 500.0)
+    assert relerr(got, orc.xsec(orc.PHCO2, sl, ν2, T, P, 0.5 * P, 500.0, nthreads=0), 1e-290) < XSEC_TOL
 
 
 def test_single_process_device_group(cs, orc, co2):
