@@ -50,7 +50,8 @@ constexpr int LS_QCAP = 256;                      // per-warp queue of evaluatio
 constexpr int MP_P = 20;                          // order of the far-field expansion
 constexpr double MP_THETA = 4.0;                  // separation (in half tile widths) beyond which lines are expanded
 // PHCO2 far wings (|dnu| >= 30 cm^-1 for every point of the tile): orders of the three power-law series (see the kernel)
-constexpr int PX_P2 = 10, PX_P4 = 6, PX_P6 = 4;
+constexpr int PX_P2 = 10, PX_P4 = 6, PX_P6 = 4;     // classes 30-120: |r| <= 1/16
+constexpr int PX_Q2 = 7, PX_Q4 = 5, PX_Q6 = 3;      // class >= 120: |r| <= 1/61, the series can stop earlier
 constexpr double PX_HMAX = 2.0;                   // half tile widths above this keep the pair-by-pair sum (ratio h/|u| <= 1/16)
 constexpr int LS_NSEG = 9;                        // segments of the chunk stream (expansion segments first)
 
@@ -159,6 +160,9 @@ struct LineSumArgs {
     int nr;                 // entries per tile in ranges (6, 8 with the far-field expansion, or LS_NR for PHCO2)
     const int64_t* ranges;  // [ntiles][nr], see tile_ranges_kernel
     double mp_theta;        // > 0: far-field expansion for lines farther than mp_theta half tile widths (Voigt, Lorentz)
+    double nul_lo, nul_hi;  // first / last prefiltered line position (host copy)
+    const double2* chix;    // PHCO2 expansion: {X, 1/X}, X = exp(0.0232 (nul - chix_ref)) per prefiltered line (or null)
+    double chix_ref;
 };
 
 // Voigt evaluation of one (line, point) that is not safely in the far wing: decides the region exactly like
@@ -237,6 +241,17 @@ __device__ __forceinline__ double eval_checked(const double4 rc, double dnu, con
         if (__double2hiint(rc.w * q) > CS_S1_HI) return (rc.z * ge) * cs_rcp(q);
         return voigt_near(slow, j, dnu, chi);
     }
+}
+
+// PHCO2 expansion: the chi factor of the >= 120 cm^-1 class, exp(-+0.0232 (nu0 - nul)), split into a per-tile scalar and a
+// per-line factor that depends on neither the tile nor the level: one exp per line per call instead of one per line per
+// (tile, level).  ref keeps the arguments small (|nul - ref| <= half the span of the line list).
+__global__ void chix_kernel(const double* __restrict__ nul, int64_t nl, double ref, double2* __restrict__ chix)
+{
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nl) return;
+    double x = exp(0.0232 * (nul[j] - ref));
+    chix[j] = make_double2(x, 1.0 / x);
 }
 
 // per-tile line classification, computed once per call (it does not depend on the level):
@@ -520,7 +535,7 @@ __global__ void __launch_bounds__(LS_THREADS, 16 / LS_WARPS) line_sum_kernel(Lin
     // PHCO2 far-wing expansion: classes F3 and F4 (|dnu| >= 30 for every point of the tile) of a narrow enough tile at a
     // level where the chi*gamma correction series converges fast (flag set by the host)
     const double tile_h = 0.5 * (a.nu[min(tile0 + TILE, a.nnu) - 1] - a.nu[tile0]);
-    const bool px = SHAPE == CS_PHCO2 && a.mp_theta > 0.0 && lp.pexp_ok > 0.0 && tile_h <= PX_HMAX;
+    const bool px = SHAPE == CS_PHCO2 && a.mp_theta > 0.0 && lp.pexp_ok > 0.0 && tile_h <= PX_HMAX && a.chix != nullptr;
     // segments streamed through the ring, in this order; a chunk never spans two segments.  The first NA segments are
     // summed through expansions (phase A), the others pair by pair (phase B).
     //   Voigt/Lorentz: A = [ilo,mlo) [mhi,ihi)                 B = [0,ilo) [mlo,mhi) [ihi,whi)
@@ -739,25 +754,48 @@ __global__ void __launch_bounds__(LS_THREADS, 16 / LS_WARPS) line_sum_kernel(Lin
             const int n = c1 - c0;
             const bool up = q >= 2;
             const bool cls2 = (q == 0) || (q == 3);
-            const double B = cls2 ? 0.0232 : lp.B2;
-            const double c0c = cls2 ? lp.B1 * 27.0 + lp.B2 * 90.0 : lp.B1 * 27.0;
-            const double aa = cls2 ? 120.0 : 30.0;
-            for (int jj = lane; jj < n; jj += 32) {
-                const double4 rc = st[jj];
-                const double d = up ? (rc.x - nu0) - aa : (nu0 - rc.x) - aa;
-                const double Fg = exp(-c0c - B * d) * rc.y;                  // chi's line factor times gamma
-                const double u = rc.x - cen;
-                const double iu = copysign(cs_rcp(fabs(u)), u);
-                const double r = h * iu, iu2 = iu * iu, Fg2 = Fg * Fg;
-                double w2 = (rc.z * Fg) * iu2;
-                double w4 = (w2 * Fg2) * iu2;
-                double w6 = (w4 * Fg2) * iu2;
+            if (cls2) {
+                // chi line factor = Cq * X^(-+1): Cq carries everything that does not depend on the line
+                const double c0c = lp.B1 * 27.0 + lp.B2 * 90.0;
+                const double Cq = up ? exp(-c0c + 0.0232 * (120.0 + (nu0 - a.chix_ref)))
+                                     : exp(-c0c - 0.0232 * ((nu0 - a.chix_ref) - 120.0));
+                const double2* cx = a.chix + wlo64 + c0;
+                for (int jj = lane; jj < n; jj += 32) {
+                    const double4 rc = st[jj];
+                    const double2 xx = cx[jj];
+                    const double Fg = (Cq * (up ? xx.y : xx.x)) * rc.y;         // chi's line factor times gamma
+                    const double u = rc.x - cen;
+                    const double iu = copysign(cs_rcp(fabs(u)), u);
+                    const double r = h * iu, iu2 = iu * iu, Fg2 = Fg * Fg;
+                    double w2 = (rc.z * Fg) * iu2;
+                    double w4 = (w2 * Fg2) * iu2;
+                    double w6 = (w4 * Fg2) * iu2;
 #pragma unroll
-                for (int k = 0; k < PX_P2; k++) { G[k] += w2; w2 *= r; }
+                    for (int k = 0; k < PX_Q2; k++) { G[k] += w2; w2 *= r; }
 #pragma unroll
-                for (int k = 0; k < PX_P4; k++) { G[PX_P2 + k] += w4; w4 *= r; }
+                    for (int k = 0; k < PX_Q4; k++) { G[PX_P2 + k] += w4; w4 *= r; }
 #pragma unroll
-                for (int k = 0; k < PX_P6; k++) { G[PX_P2 + PX_P4 + k] += w6; w6 *= r; }
+                    for (int k = 0; k < PX_Q6; k++) { G[PX_P2 + PX_P4 + k] += w6; w6 *= r; }
+                }
+            } else {
+                const double B = lp.B2, c0c = lp.B1 * 27.0, aa = 30.0;
+                for (int jj = lane; jj < n; jj += 32) {
+                    const double4 rc = st[jj];
+                    const double d = up ? (rc.x - nu0) - aa : (nu0 - rc.x) - aa;
+                    const double Fg = exp(-c0c - B * d) * rc.y;                  // chi's line factor times gamma
+                    const double u = rc.x - cen;
+                    const double iu = copysign(cs_rcp(fabs(u)), u);
+                    const double r = h * iu, iu2 = iu * iu, Fg2 = Fg * Fg;
+                    double w2 = (rc.z * Fg) * iu2;
+                    double w4 = (w2 * Fg2) * iu2;
+                    double w6 = (w4 * Fg2) * iu2;
+#pragma unroll
+                    for (int k = 0; k < PX_P2; k++) { G[k] += w2; w2 *= r; }
+#pragma unroll
+                    for (int k = 0; k < PX_P4; k++) { G[PX_P2 + k] += w4; w4 *= r; }
+#pragma unroll
+                    for (int k = 0; k < PX_P6; k++) { G[PX_P2 + PX_P4 + k] += w6; w6 *= r; }
+                }
             }
             __syncwarp();
             if (lane == 0 && c + LS_STAGES < nchunk) {
@@ -941,12 +979,26 @@ template <int SHAPE, int R> int32_t launch_line_sum(cs_ctx* ctx, LineSumArgs a, 
     a.ntiles = (a.nnu + TILE - 1) / TILE;
     if (SHAPE == CS_DOPPLER) a.mp_theta = 0.0;
     a.nr = (SHAPE == CS_PHCO2) ? LS_NR : (a.mp_theta > 0.0 ? 8 : 6);
-    CS_TRY(ctx->s_w.reserve(sizeof(int64_t) * a.nr * (size_t)a.ntiles));
+    // scratch: the per-tile ranges, then (PHCO2 expansion) the per-line chi factors of the >= 120 cm^-1 class, which are
+    // level-independent; they are skipped when the span of the line list would overflow exp (the expansion is then off
+    // and every pair is summed directly)
+    const size_t off = ((sizeof(int64_t) * a.nr * (size_t)a.ntiles + 255) / 256) * 256;
+    const bool want_chix = SHAPE == CS_PHCO2 && a.mp_theta > 0.0 && a.nl > 0 && 0.0232 * 0.5 * (a.nul_hi - a.nul_lo) < 600.0;
+    CS_TRY(ctx->s_w.reserve(off + (want_chix ? sizeof(double2) * (size_t)a.nl : 0)));
     a.ranges = ctx->s_w.as<int64_t>();
     tile_ranges_kernel<<<(unsigned)((a.ntiles * a.nr + 127) / 128), 128, 0, st>>>(a.nu, a.nnu, a.nul, a.nl, a.cut, cn, TILE,
                                                                                   a.ntiles, a.nr, a.mp_theta,
                                                                                   ctx->s_w.as<int64_t>());
     CS_CUDA(cudaGetLastError());
+    a.chix = nullptr;
+    a.chix_ref = 0.0;
+    if (want_chix) {
+        double2* cx = reinterpret_cast<double2*>(ctx->s_w.as<char>() + off);
+        a.chix_ref = 0.5 * (a.nul_lo + a.nul_hi);
+        chix_kernel<<<(unsigned)((a.nl + 255) / 256), 256, 0, st>>>(a.nul, a.nl, a.chix_ref, cx);
+        CS_CUDA(cudaGetLastError());
+        a.chix = cx;
+    }
     size_t smem = (size_t)LS_WARPS * (LS_STAGES * LS_CHUNK * sizeof(double4) + ls_extra_bytes<SHAPE, R>());
     if (smem > 48 * 1024)   // per device: not cached, several contexts may live on different GPUs
         CS_CUDA(cudaFuncSetAttribute(line_sum_kernel<SHAPE, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1109,6 +1161,7 @@ int32_t cs_lines_accumulate(cs_lines* L, int32_t shape, int64_t nnu, const doubl
         la.rec = pa.rec; la.slow = pa.slow; la.lev = pa.lev; la.cut = cut;
         la.out = d_out + (size_t)k0 * nnu; la.accumulate = accumulate;
         la.mp_theta = ctx->farfield == CS_FARFIELD_EXPANSION ? MP_THETA : 0.0;
+        la.nul_lo = ln[(size_t)j0]; la.nul_hi = ln[(size_t)j1 - 1];
         double cn = 0.0;
         for (int64_t k = 0; k < kb; k++) cn = std::max(cn, hl[(size_t)k].cnear);
         switch (shape) {
