@@ -53,7 +53,7 @@ constexpr double MP_THETA = 4.0;                  // separation (in half tile wi
 constexpr int PX_P2 = 10, PX_P4 = 6, PX_P6 = 4;     // classes 30-120: |r| <= 1/16
 constexpr int PX_Q2 = 7, PX_Q4 = 5, PX_Q6 = 3;      // class >= 120: |r| <= 1/61, the series can stop earlier
 constexpr double PX_HMAX = 2.0;                   // half tile widths above this keep the pair-by-pair sum (ratio h/|u| <= 1/16)
-constexpr int LS_NSEG = 9;                        // segments of the chunk stream (expansion segments first)
+constexpr int LS_NSEG = 5;                        // direct-sum segments of the chunk stream
 
 struct LevelParams {
     double T, P, Pp, scale;
@@ -143,6 +143,14 @@ template <typename Pred> __device__ __forceinline__ int64_t first_false(const do
         if (pred(nul[m])) lo = m + 1; else hi = m;
     }
     return lo;
+}
+
+// read-only global load of one 32-byte record (two 16-byte loads through the non-coherent path)
+__device__ __forceinline__ double4 ld_rec(const double4* p)
+{
+    const double2* q = reinterpret_cast<const double2*>(p);
+    const double2 lo = __ldg(q), hi = __ldg(q + 1);
+    return make_double4(lo.x, lo.y, hi.x, hi.y);
 }
 
 struct LineSumArgs {
@@ -536,13 +544,13 @@ __global__ void __launch_bounds__(LS_THREADS, 16 / LS_WARPS) line_sum_kernel(Lin
     // level where the chi*gamma correction series converges fast (flag set by the host)
     const double tile_h = 0.5 * (a.nu[min(tile0 + TILE, a.nnu) - 1] - a.nu[tile0]);
     const bool px = SHAPE == CS_PHCO2 && a.mp_theta > 0.0 && lp.pexp_ok > 0.0 && tile_h <= PX_HMAX && a.chix != nullptr;
-    // segments streamed through the ring, in this order; a chunk never spans two segments.  The first NA segments are
-    // summed through expansions (phase A), the others pair by pair (phase B).
-    //   Voigt/Lorentz: A = [ilo,mlo) [mhi,ihi)                 B = [0,ilo) [mlo,mhi) [ihi,whi)
-    //   PHCO2:         A = F4- F3- F3+ F4+                      B = the five ranges between and around them
-    //   no expansion:  A empty, B = [0,whi)
+    // segments streamed through the ring, in this order; a chunk never spans two segments:
+    //   Voigt/Lorentz with the expansion: expanded [ilo,mlo) [mhi,ihi) (phase A), then direct [0,ilo) [mlo,mhi) [ihi,whi)
+    //   PHCO2 with the expansion:         the five direct ranges between and around F4-, F3-, F3+, F4+; the expanded lines
+    //                                     are read straight from global memory, one line per lane (their 1000+ chunks per
+    //                                     tile would cost more in chunk prologues than the ring saves)
+    //   no expansion:                     [0,whi)
     // (kept in shared memory: indexed dynamically by the chunk number, warp-uniform)
-    constexpr int NA = SHAPE == CS_PHCO2 ? 4 : 2;
     const bool multi = mp || px;
     int* slo = seg_tab[warp];
     int* shi = seg_tab[warp] + LS_NSEG;
@@ -550,48 +558,40 @@ __global__ void __launch_bounds__(LS_THREADS, 16 / LS_WARPS) line_sum_kernel(Lin
     if (lane == 0) {
         for (int q = 0; q < LS_NSEG; q++) { slo[q] = 0; shi[q] = 0; }
         if (mp) {
-            slo[0] = ilo; shi[0] = mlo;
+            slo[0] = ilo; shi[0] = mlo;     // expanded (phase A), streamed first
             slo[1] = mhi; shi[1] = ihi;
             slo[2] = 0;   shi[2] = ilo;
             slo[3] = mlo; shi[3] = mhi;
             slo[4] = ihi; shi[4] = whi;
         } else if (px) {
-            slo[0] = bnd[1];  shi[0] = bnd[2];     // F4-
-            slo[1] = bnd[3];  shi[1] = bnd[4];     // F3-
-            slo[2] = bnd[13]; shi[2] = bnd[14];    // F3+
-            slo[3] = bnd[15]; shi[3] = bnd[16];    // F4+
-            slo[4] = 0;       shi[4] = bnd[1];
-            slo[5] = bnd[2];  shi[5] = bnd[3];
-            slo[6] = bnd[4];  shi[6] = bnd[13];
-            slo[7] = bnd[14]; shi[7] = bnd[15];
-            slo[8] = bnd[16]; shi[8] = whi;
+            slo[0] = 0;       shi[0] = bnd[1];
+            slo[1] = bnd[2];  shi[1] = bnd[3];
+            slo[2] = bnd[4];  shi[2] = bnd[13];
+            slo[3] = bnd[14]; shi[3] = bnd[15];
+            slo[4] = bnd[16]; shi[4] = whi;
         } else {
-            shi[NA] = whi;
+            shi[0] = whi;
         }
         for (int q = 0; q < LS_NSEG; q++) sch[q] = (shi[q] - slo[q] + LS_CHUNK - 1) / LS_CHUNK;
     }
     __syncwarp();
-    int nchunkA = 0, nchunk = 0;
+    int nchunk = 0;
 #pragma unroll
-    for (int q = 0; q < LS_NSEG; q++) {
-        if (q < NA) nchunkA += sch[q];
-        nchunk += sch[q];
-    }
+    for (int q = 0; q < LS_NSEG; q++) nchunk += sch[q];
+    const int nchunkA = mp ? sch[0] + sch[1] : 0;
     const double4* rec_lev = a.rec + (size_t)lev * a.nl + wlo64;          // records of the window
     if (w.slow_lev) w.slow_lev += wlo64;
-    // chunk number -> line range [c0,c1); returns the segment index
-    auto chunk_bounds = [&](int c, int& c0, int& c1) -> int {
-        int q = NA;
+    // chunk number -> line range [c0,c1)
+    auto chunk_bounds = [&](int c, int& c0, int& c1) {
         if (!multi) {            // one segment
             c0 = c * LS_CHUNK;
             c1 = min(c0 + LS_CHUNK, whi);
         } else {
-            q = 0;
+            int q = 0;
             while (q < LS_NSEG - 1 && c >= sch[q]) { c -= sch[q]; q++; }
             c0 = slo[q] + c * LS_CHUNK;
             c1 = min(c0 + LS_CHUNK, shi[q]);
         }
-        return q;
     };
 
     auto issue = [&](int c) {   // lane 0 only
@@ -706,13 +706,12 @@ __global__ void __launch_bounds__(LS_THREADS, 16 / LS_WARPS) line_sum_kernel(Lin
     // so a lane only accumulates the power sums G_m[k] = sum_j w_j r_j^k (2 FP64 ops per term); 10 / 6 / 4 terms keep the
     // truncation below 1e-11 of the line's own value.  One exp per line (its chi factor) instead of one per evaluation
     // or one multiplication per evaluation in the factorised direct path.
-    if (px && nchunkA > 0) {
+    if (px) {
         const double cen = 0.5 * (w.nutile[0] + a.nu[min(tile0 + TILE, a.nnu) - 1]);
         const double h = tile_h;
         const double ih = h > 0.0 ? 1.0 / h : 0.0;
         constexpr int NG = PX_P2 + PX_P4 + PX_P6;
         double G[NG];
-        int cur = -1;
         auto flush = [&](int q) {
             // q: 0 F4-, 1 F3-, 2 F3+, 3 F4+  ->  chi class 2,1,1,2 and side below/below/above/above
             const int tab = q == 0 ? 4 : (q == 1 ? 2 : (q == 2 ? 3 : 5));
@@ -738,20 +737,13 @@ __global__ void __launch_bounds__(LS_THREADS, 16 / LS_WARPS) line_sum_kernel(Lin
                 acc[r] = fma(E, fma(-E2, fma(-E2, p6, p4), p2), acc[r]);
             }
         };
-        for (int c = 0; c < nchunkA; c++) {
-            const int s = c % LS_STAGES;
-            const uint32_t ph = (c / LS_STAGES) & 1;
-            int c0, c1;
-            const int q = chunk_bounds(c, c0, c1);
-            if (q != cur) {
-                if (cur >= 0) flush(cur);
-                cur = q;
+#pragma unroll 1
+        for (int q = 0; q < 4; q++) {
+            const int lo = bnd[q == 0 ? 1 : (q == 1 ? 3 : (q == 2 ? 13 : 15))];
+            const int hi = bnd[q == 0 ? 2 : (q == 1 ? 4 : (q == 2 ? 14 : 16))];
+            if (lo >= hi) continue;
 #pragma unroll
-                for (int k = 0; k < NG; k++) G[k] = 0.0;
-            }
-            mbar_wait(&full_bar[warp][s], ph);
-            const double4* st = ring + (size_t)s * LS_CHUNK;
-            const int n = c1 - c0;
+            for (int k = 0; k < NG; k++) G[k] = 0.0;
             const bool up = q >= 2;
             const bool cls2 = (q == 0) || (q == 3);
             if (cls2) {
@@ -759,10 +751,10 @@ __global__ void __launch_bounds__(LS_THREADS, 16 / LS_WARPS) line_sum_kernel(Lin
                 const double c0c = lp.B1 * 27.0 + lp.B2 * 90.0;
                 const double Cq = up ? exp(-c0c + 0.0232 * (120.0 + (nu0 - a.chix_ref)))
                                      : exp(-c0c - 0.0232 * ((nu0 - a.chix_ref) - 120.0));
-                const double2* cx = a.chix + wlo64 + c0;
-                for (int jj = lane; jj < n; jj += 32) {
-                    const double4 rc = st[jj];
-                    const double2 xx = cx[jj];
+                const double2* cx = a.chix + wlo64;
+                for (int j = lo + lane; j < hi; j += 32) {
+                    const double4 rc = ld_rec(rec_lev + j);
+                    const double2 xx = __ldg(cx + j);
                     const double Fg = (Cq * (up ? xx.y : xx.x)) * rc.y;         // chi's line factor times gamma
                     const double u = rc.x - cen;
                     const double iu = copysign(cs_rcp(fabs(u)), u);
@@ -779,8 +771,8 @@ __global__ void __launch_bounds__(LS_THREADS, 16 / LS_WARPS) line_sum_kernel(Lin
                 }
             } else {
                 const double B = lp.B2, c0c = lp.B1 * 27.0, aa = 30.0;
-                for (int jj = lane; jj < n; jj += 32) {
-                    const double4 rc = st[jj];
+                for (int j = lo + lane; j < hi; j += 32) {
+                    const double4 rc = ld_rec(rec_lev + j);
                     const double d = up ? (rc.x - nu0) - aa : (nu0 - rc.x) - aa;
                     const double Fg = exp(-c0c - B * d) * rc.y;                  // chi's line factor times gamma
                     const double u = rc.x - cen;
@@ -797,13 +789,8 @@ __global__ void __launch_bounds__(LS_THREADS, 16 / LS_WARPS) line_sum_kernel(Lin
                     for (int k = 0; k < PX_P6; k++) { G[PX_P2 + PX_P4 + k] += w6; w6 *= r; }
                 }
             }
-            __syncwarp();
-            if (lane == 0 && c + LS_STAGES < nchunk) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                issue(c + LS_STAGES);
-            }
+            flush(q);
         }
-        if (cur >= 0) flush(cur);
     }
 
     for (int c = nchunkA; c < nchunk; c++) {
