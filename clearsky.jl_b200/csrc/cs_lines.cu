@@ -793,6 +793,7 @@ __global__ void __launch_bounds__(LS_THREADS, 16 / LS_WARPS) line_sum_kernel(Lin
         }
     }
 
+    int sgc = 0;   // PHCO2: cursor into the 17 chi-class segments
     for (int c = nchunkA; c < nchunk; c++) {
         const int s = c % LS_STAGES;
         const uint32_t ph = (c / LS_STAGES) & 1;
@@ -825,8 +826,11 @@ __global__ void __launch_bounds__(LS_THREADS, 16 / LS_WARPS) line_sum_kernel(Lin
                 }
             }
             __syncwarp();
+            // chunks arrive in ascending line order: a cursor skips the segments that end before this chunk, and the loop
+            // stops at the first segment that starts after it (1-2 iterations instead of 17)
+            while (sgc < 16 && bnd[sgc + 1] <= c0) sgc++;
 #pragma unroll 1
-            for (int sgm = 0; sgm < 17; sgm++) {
+            for (int sgm = sgc; sgm < 17 && bnd[sgm] < c1; sgm++) {
                 const int x0 = min(max(bnd[sgm] - c0, 0), n), x1 = min(max(bnd[sgm + 1] - c0, 0), n);
                 if (x0 >= x1) continue;
                 if (sgm == 0 || sgm == 16) { cold_edge<SHAPE, R>(w, st, c0, x0, x1); continue; }
