@@ -13,16 +13,21 @@
 // K2 design (FP64 CUDA cores; the roofline that bounds it is the FP64 FMA pipe, not HBM):
 //   work unit = one warp = (tile of 32*R consecutive nu, one level); one warp per CTA, 16 CTAs per SM.  A lane owns
 //   R points strided by 32 (coalesced).  Lines are sorted, so the lines that can touch a tile form one contiguous
-//   index range; an elected lane streams that range through the warp's private 4-stage shared-memory ring with
-//   cp.async.bulk (TMA 1-D bulk copy) completing on per-stage mbarriers.  Binary searches done once per call
-//   (tile_ranges_kernel) classify every line of the window per tile: inside the cut-off for ALL points and provably
-//   in the far wing (hot loop: no test of any kind), inside for SOME points (edge: exact inclusive predicate
-//   |nu - nul| <= cut, line_shapes.jl:10, folded into the numerators), centre close to the tile (near: Faddeyeva
-//   region decided per evaluation), outside (never touched).
+//   index range; an elected lane streams that range through the warp's private 2-stage shared-memory ring with
+//   cp.async.bulk (TMA 1-D bulk copy, 128 records per stage) completing on per-stage mbarriers.  Binary searches done
+//   once per call (tile_ranges_kernel) classify every line of the window per tile: inside the cut-off for ALL points
+//   and provably in the far wing (hot loop: no test of any kind), inside for SOME points (edge: exact inclusive
+//   predicate |nu - nul| <= cut, line_shapes.jl:10, folded into the numerators), centre close to the tile (near:
+//   Faddeyeva region decided per evaluation), outside (never touched).  All per-chunk index arithmetic is 32-bit and
+//   relative to the first line of the window.
 //   Far-wing Voigt (|z|^2 >= 1.6e4, >99 % of evaluations) is algebraically the Lorentz profile
 //   S*gamma/(pi*(dnu^2+gamma^2)); four lines share one reciprocal: n1/d1 + n2/d2 = (n1 d2 + n2 d1)/(d1 d2), twice.
 //   Evaluations that need the general Algorithm-985 routine are compacted into a per-warp queue and evaluated with
 //   all lanes busy.  PHCO2 factorises chi into per-point and per-line exponentials (see the kernel).
+//   Opt-in far-field expansion (cs_ctx_set_farfield): well-separated far-wing lines are summed through local expansions
+//   about the tile centre, one line per lane, instead of pair by pair -- a 20-term Taylor series for Voigt / Lorentz
+//   ("phase A" in the kernel), power-law series with a chi*gamma correction for the PHCO2 classes >= 30 cm^-1; the
+//   direct classes above then only see what is left.
 #include "cs_internal.cuh"
 #include <algorithm>
 #include <cstdlib>
