@@ -155,3 +155,32 @@ def test_bench_sharding_logic():
     e = bench.balanced_slices(cnt, 4)
     parts = sum(np.dot(w[a:b], y[a:b]) for a, b in zip(e, e[1:]))
     assert abs(parts - np.trapezoid(y, ν)) < 1e-10
+
+
+def test_radau_refinement_logic(cs):
+    """the Radau-equivalent refinement (radau.py): Richardson estimate and extrapolation of a second-order sequence,
+    the per-call level cap, and the core tag's defaults (shared.jl:40-47)"""
+    from clearsky_b200 import radau
+    assert cs.Radau() == cs.Radau(nstream=5, tol=1e-5)
+    exact = np.array([1.0, 2.0, 0.5])
+    seq = lambda n: exact * (1 + 0.3 / n ** 2)                      # error ~ C/n^2, like the linear-in-tau source scheme
+    assert not radau._converged(seq(4), seq(2), 1e-5)
+    assert radau._converged(seq(256), seq(128), 1e-5)
+    assert np.max(np.abs(radau._extrapolate(seq(8), seq(4)) - exact)) < 1e-15
+    # values far below the spectral maximum are judged against 1e-3 of it, not against themselves
+    a, b = np.array([1.0, 1e-9]), np.array([1.0, 2e-9])
+    assert radau._converged(a, b, 1e-5)
+    assert radau._fits(1000, radau.MAX_LEVELS, 4) and not radau._fits(1000, radau.MAX_LEVELS + 1, 4)
+    assert not radau._fits(10 ** 7, 1025, 4)                        # the sigma workspace of one refinement level is capped
+
+
+def test_dispatch_of_scalar_and_vector_pressure_forms(cs):
+    """opticaldepth(P::Vector, ...) and opticaldepth(P1, P2, ...) (fluxes.jl:68 and :39) share a name in the reference;
+    the Python twin dispatches on the first argument, and both fail loudly without a device (no CPU fallback)"""
+    gray = cs.GrayGas(1e-26, np.linspace(1.0, 100.0, 10))
+    with pytest.raises((cs.ClearSkyError, ImportError)):
+        cs.opticaldepth(np.array([10.0, 1e5]), 9.8, 250.0, 0.029, 0.0, gray)
+    with pytest.raises((cs.ClearSkyError, ImportError)):
+        cs.opticaldepth(1e5, 10.0, 9.8, 250.0, 0.029, 0.0, gray)
+    with pytest.raises(AssertionError):
+        cs.opticaldepth(1e5, 10.0, 9.8, 250.0, 0.029, 2.0, gray)       # checkazimuth before any device work
