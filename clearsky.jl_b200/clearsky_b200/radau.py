@@ -5,10 +5,11 @@ implicit ODE solver (ScalarRadau.jl, third party) to a tolerance `tol` (src/flux
 :133-158 `outgoing(Pₛ,…)`, :197-236 `monochromaticfluxes!(…, core::Radau, …)`; src/core/radau.jl).  An adaptive
 per-wavenumber step sequence has no place on a GPU and cannot be matched beyond its own tolerance, so the same entry
 points are provided here on the B200 Discretized core (K6): the pressure range is divided into layers equally spaced
-in ln P, every layer's optical depth is a 4-point Gauss-Lobatto integral, and the number of layers n is doubled until
-the Richardson error estimate |R(2n) - R(n)|/3 of the second-order scheme (linear-in-τ source function) is below `tol`
-(relative, per wavenumber, against a floor of 1e-3 of the spectral maximum); the extrapolated value (4R(2n) - R(n))/3
-is returned.  One flux call holds at most MAX_LEVELS levels (per-CTA tables of K6 live in shared memory).
+in ln P, every layer's optical depth is a 4-point Gauss-Lobatto integral, and the number of layers n is doubled until two
+successive Richardson extrapolates E(n) = (4 F(2n) - F(n))/3 of the second-order scheme (linear-in-τ source function;
+measured error ratio 4.0 per doubling) agree to `tol` (relative, per wavenumber, against a floor of 1e-3 of the spectral
+maximum); the last extrapolate is returned.  One flux call holds at most MAX_LEVELS levels (per-CTA tables of K6 live in
+shared memory).
 The layer-depth floor of the Discretized core (1e-6, discretized.jl:174) is lowered to 1e-9 for these calls so that
 hundreds of thin layers do not add opacity in spectral windows.
 
@@ -55,9 +56,9 @@ def _fits(nν, nlev, nlobatto):
 
 
 def _converged(new, old, tol):
-    """Richardson error estimate of `new` (twice the layers of `old`) for a second-order scheme"""
+    """do two successive results agree to tol (relative, against a floor of 1e-3 of the maximum)?"""
     scale = np.maximum(np.abs(new), 1e-3 * np.max(np.abs(new)) + np.finfo(float).tiny)
-    return float(np.max(np.abs(new - old) / (3.0 * scale))) < tol
+    return float(np.max(np.abs(new - old) / scale)) < tol
 
 
 def _extrapolate(new, old):
@@ -95,7 +96,7 @@ def opticaldepth_between(P1, P2, g, fT, fμ, θ, *absorbers, tol=1e-5, nlobatto=
         check(lib().cs_opticaldepth(ws.h, len(P), ptr(P), nlobatto, ptr(f64(w)), ptr(μl), float(g), float(θ), ptr(τ)))
         ws.close()
         # the Lobatto rule integrates dτ/dP to high order: no extrapolation, plain successive difference
-        if prev is not None and _converged(τ, prev, 3.0 * tol):
+        if prev is not None and _converged(τ, prev, tol):
             return τ
         if not _fits(nν, 2 * n + 1, nlobatto):
             warnings.warn(f"opticaldepth: refinement stopped at {n} layers before reaching tol = {tol}")
@@ -153,18 +154,19 @@ def outgoing(P, g, T, μ, *absorbers, Ptop=1.0, nstream=5, tol=1e-5, nlobatto=No
     A.checkpressures(Ps, Ptop)
     fT, fμ = formprofile(None, T), formprofile(None, μ)
     nlob = 4 if nlobatto is None else int(nlobatto)
-    prev, n = None, n0
+    prev, prevE, n = None, None, n0
     while True:
         Pg = f64(np.exp(np.linspace(np.log(Ptop), np.log(Ps), n + 1)))
         Pg[0], Pg[-1] = Ptop, Ps
         Mup, _, _, _ = _sweep(A, ν, Pg, g, fT, fμ, None, None, 0.841, nstream, nlob, True)
         olr = np.ascontiguousarray(Mup[:, 0])
-        if prev is not None and _converged(olr, prev, tol):
-            return _extrapolate(olr, prev)
+        E = None if prev is None else _extrapolate(olr, prev)
+        if prevE is not None and _converged(E, prevE, tol):
+            return E
         if not _fits(nν, 2 * n + 1, nlob):
             warnings.warn(f"outgoing: refinement stopped at {n} layers before reaching tol = {tol}")
-            return olr if prev is None else _extrapolate(olr, prev)
-        prev, n = olr, 2 * n
+            return olr if E is None else E
+        prev, prevE, n = olr, E, 2 * n
 
 
 def monochromaticfluxes_radau(Mup, Mdn, τ, core, P, g, T, μ, fS, fa, *absorbers, θs=0.841, nlobatto=4, k0=2):
@@ -183,7 +185,7 @@ def monochromaticfluxes_radau(Mup, Mdn, τ, core, P, g, T, μ, fS, fa, *absorber
     if τ is not None:
         τ[...] = np.nan
     lnP = np.log(P)
-    prev, prevF, k = None, None, k0
+    prev, prevF, prevE, k = None, None, None, k0
     while True:
         frac = np.arange(k) / k
         fine = np.concatenate([np.exp(lnP[:-1, None] + (lnP[1:] - lnP[:-1])[:, None] * frac[None, :]).ravel(), P[-1:]])
@@ -193,17 +195,19 @@ def monochromaticfluxes_radau(Mup, Mdn, τ, core, P, g, T, μ, fS, fa, *absorber
         npl = len(P)
         cur = np.concatenate([Mu[:, ::k], Md[:, ::k]], axis=1)
         curF = np.concatenate([Fup[::k], Fdn[::k]])
-        done = prev is not None and _converged(cur, prev, core.tol)
+        E = None if prev is None else _extrapolate(cur, prev)
+        EF = None if prev is None else _extrapolate(curF, prevF)
+        done = prevE is not None and _converged(E, prevE, core.tol)
         if not done and not _fits(nν, 2 * k * (npl - 1) + 1, nlobatto):
             warnings.warn(f"monochromaticfluxes!(Radau): refinement stopped at {k} sub-layers before reaching tol = {core.tol}")
             done = True
         if done:
-            if prev is not None:
-                cur, curF = _extrapolate(cur, prev), _extrapolate(curF, prevF)
+            if E is None:
+                E, EF = cur, curF
             if Mup is not None:
-                Mup[...] = cur[:, :npl]
+                Mup[...] = E[:, :npl]
             if Mdn is not None:
-                Mdn[...] = cur[:, npl:]
+                Mdn[...] = E[:, npl:]
             # the spectral integrals at the levels of P (∫F!, shared.jl:125-137) are linear in M: same extrapolation
-            return curF[:npl].copy(), curF[npl:].copy(), curF[:npl] - curF[npl:]
-        prev, prevF, k = cur, curF, 2 * k
+            return EF[:npl].copy(), EF[npl:].copy(), EF[:npl] - EF[npl:]
+        prev, prevF, prevE, k = cur, curF, E, 2 * k

@@ -221,22 +221,24 @@ function ClearSky.radiate!(F::FluxPack, core::B200Discretized, P::AbstractVector
 end
 
 # ---- Radau-core equivalents (src/fluxes.jl:39-66, 133-158): same entry points on the Discretized GPU core, layers
-# equally spaced in ln P doubled until the Richardson estimate is below tol (see clearsky_b200/radau.py, the executed twin)
+# equally spaced in ln P doubled until two successive Richardson extrapolates agree to tol (see clearsky_b200/radau.py, the
+# executed twin)
 function outgoing_b200(Pₛ::Real, g::Real, 𝒻T, 𝒻μ, absorbers...; Ptop::Real=1.0, nstream::Int=5, tol::Real=1e-5)
     taufloor!(1e-9)
     try
-        prev, n = nothing, 32
+        prev, prevE, n = nothing, nothing, 32
         while true
             P = exp.(range(log(Ptop), log(Pₛ), length=n + 1))
             ν = first(a for a in absorbers if a isa AbstractGas).ν
             M⁺, M⁻ = zeros(n + 1, length(ν)), zeros(n + 1, length(ν))
             fluxes_b200(B200Discretized(nstream, 4), P, g, 𝒻T, 𝒻μ, x -> 0.0, x -> 0.0, absorbers...; M⁺=M⁺, M⁻=M⁻)
             olr = M⁺[1, :]
-            if prev !== nothing
-                scale = max.(abs.(olr), 1e-3 * maximum(abs.(olr)))
-                (maximum(abs.(olr .- prev) ./ (3 .* scale)) < tol || 2n + 1 > 1025) && return (4 .* olr .- prev) ./ 3
+            E = prev === nothing ? nothing : (4 .* olr .- prev) ./ 3          # Richardson extrapolate of the O(n⁻²) scheme
+            if prevE !== nothing
+                scale = max.(abs.(E), 1e-3 * maximum(abs.(E)))
+                (maximum(abs.(E .- prevE) ./ scale) < tol || 2n + 1 > 1025) && return E
             end
-            prev, n = olr, 2n
+            prev, prevE, n = olr, E, 2n
         end
     finally
         taufloor!(1e-6)

@@ -165,8 +165,12 @@ def test_radau_refinement_logic(cs):
     exact = np.array([1.0, 2.0, 0.5])
     seq = lambda n: exact * (1 + 0.3 / n ** 2)                      # error ~ C/n^2, like the linear-in-tau source scheme
     assert not radau._converged(seq(4), seq(2), 1e-5)
-    assert radau._converged(seq(256), seq(128), 1e-5)
+    assert radau._converged(seq(512), seq(256), 1e-5)
     assert np.max(np.abs(radau._extrapolate(seq(8), seq(4)) - exact)) < 1e-15
+    # successive Richardson extrapolates of a sequence with a fourth-order remainder agree long before the raw values do
+    seq4 = lambda n: exact * (1 + 0.3 / n ** 2 + 2.0 / n ** 4)
+    E = lambda n: radau._extrapolate(seq4(2 * n), seq4(n))
+    assert radau._converged(E(32), E(16), 1e-5) and not radau._converged(seq4(64), seq4(32), 1e-5)
     # values far below the spectral maximum are judged against 1e-3 of it, not against themselves
     a, b = np.array([1.0, 1e-9]), np.array([1.0, 2e-9])
     assert radau._converged(a, b, 1e-5)
