@@ -30,12 +30,16 @@ def per_point_counts(ν, νl, cut):
     return (hi - lo).astype(np.int64)
 
 
-def slice_cost(ν, line_lists, cut, kappa=5.6e-5):
+# per-ν cost = evaluations * (1 + kappa * ν): fitted to the per-slice line-sum times of an 8-way split of C2 (tools/slice_balance.py).
+# The slope is the near-centre work (Doppler widths grow with ν); in expansion mode the far wings are nearly free, so it weighs more.
+KAPPA = {"direct": 4.9e-5, "expansion": 2.0e-4}
+
+
+def slice_cost(ν, line_lists, cut, kappa=None, farfield="direct"):
     """per-ν cost model for balancing slices: evaluations, inflated by the near-centre work that grows with ν
-    (Doppler widths are proportional to ν, so the share of near-centre lines per tile is too).  kappa was calibrated
-    on the measured per-slice kernel times of the 8-way split (profiles/r1_slice_balance.txt)."""
+    (Doppler widths are proportional to ν, so the share of near-centre lines per tile is too)."""
     counts = sum(per_point_counts(ν, νl, cut) for νl in line_lists)
-    return counts * (1.0 + kappa * ν)
+    return counts * (1.0 + (KAPPA[farfield] if kappa is None else kappa) * ν)
 
 
 def balanced_slices(cost, n):
@@ -219,7 +223,9 @@ class ShardedLineByLine(ShardedAbsorber):
         self.gases = list(gases)
         self.cia = [x[0] if isinstance(x, (tuple, list)) else x for x in cia]
         ν = f64(np.asarray(ν, dtype=np.float64))
-        cost = sum(slice_cost(ν, [sl.ν], cut) for sl, _, _, cut in self.gases)
+        mode = group.ctx[0].get_farfield()
+        cost = sum(slice_cost(ν, [sl.ν], cut, farfield=mode if shape in ("voigt", "lorentz", 1, 2) else "direct")
+                   for sl, _, shape, cut in self.gases)
 
         def build(νs, ctx):
             lg = [LineGas(slice_lines(sl, νs[0], νs[-1], cut), fC, νs, shape, cut, ctx=ctx) for sl, fC, shape, cut in self.gases]
