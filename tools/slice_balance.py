@@ -11,7 +11,10 @@ N = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 wl = bench.make_workload(cs, "c2")
 ν, P, T = wl["ν"], wl["P"], wl["T"]; nlev = len(P); cut = 25.0
 ctx = cs.default_context()
-counts = bench.slice_cost(ν, wl["gases"], cut) if os.environ.get("COSTMODEL", "1") == "1" else sum(bench.per_point_counts(ν, sl.ν, cut) for sl, _ in wl["gases"])
+from clearsky_b200 import sharding
+counts = (sharding.slice_cost(ν, [sl.ν for sl, _ in wl["gases"]], cut, farfield=ctx.get_farfield()) if os.environ.get("COSTMODEL", "1") == "1"
+          else sum(bench.per_point_counts(ν, sl.ν, cut) for sl, _ in wl["gases"]))
+print("far-field mode:", ctx.get_farfield(), "cost model:", os.environ.get("COSTMODEL", "1"))
 edges = bench.balanced_slices(counts, N)
 Tn, Pn = f64(T), f64(P)
 res = []
