@@ -234,9 +234,9 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device -- the engine has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
-        # NCCL_DEBUG=VERSION makes NCCL print its banner on stdout, which must carry exactly one JSON line
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # with NCCL_DEBUG=VERSION or WARN in the environment NCCL prints its version banner on stdout, which must carry
+        # exactly one JSON line: send NCCL's own log to stderr instead
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     # run the library on torch's current (non-default) stream so that torch.cuda.Event brackets its kernels
     stream = torch.cuda.Stream(device=local)
