@@ -234,10 +234,20 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device -- the engine has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
-        # with NCCL_DEBUG=VERSION or WARN in the environment NCCL prints its version banner on stdout, which must carry
-        # exactly one JSON line: send NCCL's own log to stderr instead
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL prints a version banner on stdout when its first communicator comes up; stdout must carry exactly one
+        # JSON line, so file descriptor 1 points at stderr while the communicator is created (first collective included)
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            warm = torch.zeros(1, device=f"cuda:{local}")
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     # run the library on torch's current (non-default) stream so that torch.cuda.Event brackets its kernels
     stream = torch.cuda.Stream(device=local)
     torch.cuda.set_stream(stream)
