@@ -53,3 +53,53 @@ def test_random_cases_both_modes(cs, orc, seed):
                     assert relerr(got, ref, 1e-290) < 1e-9, (seed, case, name, mode, cut, nl, len(ν))
     finally:
         ctx.set_farfield(prev)
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_random_flux_solves(cs, orc, seed):
+    """K6/K7 and the depth kernel on random atmospheres: Σ supplied from the host (log-uniform over 12 decades so that
+    layers range from transparent -- the 1e-6 floor -- to opaque), random level counts / spacing, streams, Lobatto orders,
+    stellar beam, albedo, zenith angle; F±, M±, τ and the total optical depth against the oracle at the 1e-8 bar"""
+    from clearsky_b200.fluxes import _unique_nodes, formprofile, lobattoevaluations
+    rng = np.random.default_rng(5000 + seed)
+    nν = int(rng.choice([1, 31, 128, 129, 777]))
+    ν = np.sort(rng.uniform(1.0, 3000.0, nν)) if nν > 1 else np.array([667.0])
+    npl = int(rng.integers(2, 60))
+    P = np.sort(10 ** rng.uniform(0.5, 5.0, npl))
+    P = np.unique(P)
+    if len(P) < 2:
+        P = np.array([10.0, 1e5])
+    nstream, nlob = int(rng.integers(1, 12)), int(rng.integers(2, 7))
+    Tsurf, Ttop = rng.uniform(220, 330), rng.uniform(120, 220)
+    fT = cs.AtmosphericProfile(np.array([P[0], P[-1]]), np.array([Ttop, Tsurf]))
+    μ = float(rng.uniform(0.002, 0.044))
+    g = float(rng.uniform(1.0, 25.0))
+    Tl, μl, Pn = lobattoevaluations(P, fT, formprofile(P, μ), nlob)
+    Tn, Pq = _unique_nodes(P, Tl, Pn, nlob)
+    σ = 10 ** rng.uniform(-32, -20, (len(Tn), nν)) * (1.0 + Pq[:, None] / 1e4)
+    has_sun, has_alb = rng.random() < 0.6, rng.random() < 0.6
+    fS = (lambda x: 0.5 + 1e-4 * x) if has_sun else None
+    fa = (lambda x: 0.05 + 1e-4 * x) if has_alb else None
+    θs = float(rng.uniform(0.0, 1.5))
+    ws = cs.SigmaWorkspace(ν, len(Tn))
+    ws.add_host(σ)
+    from clearsky_b200._lib import check, f64, lib, ptr
+    m, W = cs.streamnodes(nstream)
+    x, w = cs.lobattonodes(nlob)
+    Tlev = f64(fT(P))
+    F = cs.FluxPack(len(P), nν)
+    Fup, Fdn, Fnet = np.empty(len(P)), np.empty(len(P)), np.empty(len(P))
+    check(lib().cs_fluxes(ws.h, len(P), ptr(f64(P)), nlob, ptr(f64(w)), ptr(f64(μl)), ptr(Tlev), g,
+                          ptr(f64(fS(ν))) if fS else None, ptr(f64(fa(ν))) if fa else None, θs, nstream, ptr(f64(m)),
+                          ptr(f64(W)), None, ptr(F.τ), ptr(F.Mup), ptr(F.Mdn), ptr(Fup), ptr(Fdn), ptr(Fnet)))
+    ref = orc.fluxes(ν, P, nlob, w, np.full((len(P) - 1, nlob), μ), Tlev, σ, g, fS(ν) if fS else None,
+                     fa(ν) if fa else None, θs, nstream, m, W, nthreads=0)
+    tol = 1e-8
+    assert relerr(F.τ, ref["τ"]) < tol, (seed, "tau")
+    assert relerr(F.Mup, ref["Mup"], 1e-300) < tol and relerr(F.Mdn, ref["Mdn"], 1e-300) < tol, (seed, "M")
+    if nν > 1:
+        assert relerr(Fup, ref["Fup"], 1e-300) < tol and relerr(Fdn, ref["Fdn"], 1e-300) < tol, (seed, "F")
+        assert relerr(Fnet, ref["Fup"] - ref["Fdn"], 1e-12 * np.max(np.abs(ref["Fup"]))) < 1e-6
+    τtot = np.empty(nν)
+    check(lib().cs_opticaldepth(ws.h, len(P), ptr(f64(P)), nlob, ptr(f64(w)), ptr(f64(μl)), g, min(θs, 1.4), ptr(τtot)))
+    assert relerr(τtot, orc.opticaldepth(P, nlob, w, μl, σ, g, min(θs, 1.4)), 1e-300) < tol
