@@ -42,8 +42,9 @@ end
 const CTX = Ref{Union{Nothing,Context}}(nothing)
 context() = (CTX[] === nothing && (CTX[] = Context()); CTX[])
 
-# far-wing treatment of the Voigt/Lorentz line sum: :direct (every pair, like surf!) or :expansion (20-term local
-# expansion of well-separated far-wing lines, truncation < 3e-11; include/clearsky_b200.h)
+# far-wing treatment of the line sum: :direct (every pair, like surf!) or :expansion (local expansions of well-separated
+# far-wing lines about each 128-point tile: Voigt/Lorentz and the PHCO2 classes >= 30 cm^-1; truncation < 3e-11;
+# include/clearsky_b200.h)
 farfield!(mode::Symbol) = check(ccall((:cs_ctx_set_farfield, LIB), Int32, (Ptr{Cvoid}, Int32), context().h,
                                       mode === :expansion ? Int32(1) : Int32(0)))
 # floor on the vertical optical depth of a layer in the flux kernel (reference: 1e-6, src/core/discretized.jl:174)
