@@ -105,15 +105,20 @@ __global__ void __launch_bounds__(RT_THREADS) rt_kernel(RtArgs a)
         double r = warp_sum(wj * Mdn);
         if (lane == 0) red[(np + 0) * RT_WARPS + warp] += r;
     }
+    // the end-node cross-section of the NEXT layer is loaded one iteration ahead: the load is the only long-latency
+    // operation of the loop and everything after it depends on it
+    double sig_end = a.sig[(size_t)(nlob - 1) * nnu + j];
     for (int i = 0; i < L; i++) {
         double dP = sP[i + 1] - sP[i];
         double ti = 0.0;
         ti += (dP * swl[0]) * beta1;
+        const double sig_cur = sig_end;
+        if (i + 1 < L) sig_end = a.sig[(size_t)((nlob - 1) * (i + 2)) * nnu + j];
         for (int n = 1; n < nlob - 1; n++) {
             double bn = Cg * (a.sig[(size_t)(n + (nlob - 1) * i) * nnu + j] / smu[n + nlob * i]);
             ti += (dP * swl[n]) * bn;
         }
-        double bn = Cg * (a.sig[(size_t)((nlob - 1) * (i + 1)) * nnu + j] / smu[(nlob - 1) + nlob * i]);
+        double bn = Cg * (sig_cur / smu[(nlob - 1) + nlob * i]);
         ti += (dP * swl[nlob - 1]) * bn;
         beta1 = bn;
         double tau = fmax(ti, a.tau_floor);              // floor on the vertical depth (discretized.jl:174)
@@ -152,9 +157,10 @@ __global__ void __launch_bounds__(RT_THREADS) rt_kernel(RtArgs a)
 #pragma unroll
     for (int k = 0; k < NSMAX; k++) I[k] = Is;
     double B1 = Bprev;
+    double tau_n = a.tau_s[(size_t)(L - 1) * nnu + j], B_n = a.B_s[(size_t)(L - 1) * nnu + j];
     for (int i = L - 1; i >= 0; i--) {
-        double tau = a.tau_s[(size_t)i * nnu + j];
-        double B2 = a.B_s[(size_t)i * nnu + j];
+        const double tau = tau_n, B2 = B_n;
+        if (i > 0) { tau_n = a.tau_s[(size_t)(i - 1) * nnu + j]; B_n = a.B_s[(size_t)(i - 1) * nnu + j]; }
         double Msum = 0.0;
         const double rtau = cs_rcp(tau);
 #pragma unroll
