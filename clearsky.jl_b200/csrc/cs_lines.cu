@@ -173,6 +173,7 @@ struct LineSumArgs {
     int nr;                 // entries per tile in ranges (6, 8 with the far-field expansion, or LS_NR for PHCO2)
     const int64_t* ranges;  // [ntiles][nr], see tile_ranges_kernel
     double mp_theta;        // > 0: far-field expansion for lines farther than mp_theta half tile widths (Voigt, Lorentz)
+    const double* ffc;      // far-field coefficients [nlev][ntiles][MP_P] precomputed by farfield_kernel (or null)
     double nul_lo, nul_hi;  // first / last prefiltered line position (host copy)
     const double2* chix;    // PHCO2 expansion: {X, 1/X}, X = exp(0.0232 (nul - chix_ref)) per prefiltered line (or null)
     double chix_ref;
@@ -471,6 +472,172 @@ __device__ __noinline__ void cold_phco2_generic(const WarpCold& w, const double4
     for (int r = 0; r < R; r++) w.cacc[32 * r + lane] += acc[r];
 }
 
+// ------------------------------------------------------------------------------------------------
+// Far field through cluster moments (expansion mode, Voigt far wing and Lorentz).  The per-line expansion of K2 costs
+// ~70 FP64 operations per eligible line per (tile, level); most of those lines are many tile widths away, where whole
+// clusters of 32 consecutive lines can be translated at once:
+//   P2M (moments_kernel, once per level):  K/((nu-nul)^2+g^2) = Im[s/(nu-z)], z = nul + i g, s = K/g, so about a real
+//        cluster centre zc:  sum_j = sum_{m>=1} mu_m/(nu-zc)^(m+1),  mu_m = Im sum_j s_j (z_j-zc)^m = sum_j K_j C_m,
+//        C_1 = 1, A_1 = u, C_{m+1} = u C_m + A_m, A_{m+1} = u A_m - g^2 C_m   (u = nul_j - zc)
+//   M2L (farfield_kernel, per tile and level):  with R = zc - cen, t = (nu-cen)/h:
+//        a_k -= (h/R)^k/R * S_k,  S_k = sum_m C(m+k,k) beta_m,  beta_m = mu_m (-1/R)^m, and S_k is element 0 of the
+//        (k+1)-th suffix-sum pass over (0, beta_1, .., beta_p): no binomials, p^2/2 additions per cluster.
+// A cluster is translated when |R| >= FF_THETA (h + rho), rho = its radius including the largest half width; with
+// FF_P = 14 terms the truncation is below 1e-13 (tools/proto/m2l_lorentz.py measures 8e-15).  Clusters that are too close,
+// and the lines of the eligible ranges that do not fill a cluster, take the per-line expansion here as well, so K2 only
+// has to evaluate the resulting polynomial (MP_P coefficients per (tile, level)).
+constexpr int FF_P = 14;
+constexpr double FF_THETA = 8.0;
+constexpr int FF_REC = 16;      // doubles per (level, cluster): mu_1..mu_14, zc, rho
+
+__global__ void __launch_bounds__(128) moments_kernel(const double4* __restrict__ rec, int64_t nl, int64_t ncl,
+                                                      double* __restrict__ mom)
+{
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lev = blockIdx.y;
+    if (c >= ncl) return;
+    const double4* r = rec + (size_t)lev * nl + c * 32;
+    const double x0 = r[0].x, x1 = r[31].x;
+    const double zc = 0.5 * (x0 + x1);
+    double mu[FF_P];
+#pragma unroll
+    for (int m = 0; m < FF_P; m++) mu[m] = 0.0;
+    double g2max = 0.0;
+    for (int j = 0; j < 32; j++) {
+        const double4 rc = r[j];
+        const double u = rc.x - zc, g2 = rc.y, K = rc.z;
+        g2max = fmax(g2max, g2);
+        double C = 1.0, A = u;
+#pragma unroll
+        for (int m = 0; m < FF_P; m++) {
+            mu[m] = fma(K, C, mu[m]);
+            const double Cn = fma(u, C, A);
+            A = fma(u, A, -(g2 * C));
+            C = Cn;
+        }
+    }
+    double* o = mom + ((size_t)lev * ncl + c) * FF_REC;
+#pragma unroll
+    for (int m = 0; m < FF_P; m++) o[m] = mu[m];
+    o[FF_P] = zc;
+    const double ext = 0.5 * (x1 - x0);
+    o[FF_P + 1] = sqrt(fma(ext, ext, g2max));
+}
+
+struct FarFieldArgs {
+    const double* nu;
+    int64_t nnu, nl, ncl, ntiles;
+    const double4* rec;       // [nlev][nl]
+    const double* mom;        // [nlev][ncl][FF_REC]
+    const int64_t* ranges;    // [ntiles][8]
+    double* ffc;              // [nlev][ntiles][MP_P]
+    int tile_pts, lorentz;
+};
+
+__global__ void __launch_bounds__(128) farfield_kernel(FarFieldArgs a)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t tile = (int64_t)blockIdx.x * 4 + warp;
+    const int lev = blockIdx.y;
+    if (tile >= a.ntiles) return;
+    // the same line classes as line_sum_kernel (indices relative to the prefiltered list)
+    const int64_t* rg = a.ranges + tile * 8;
+    const int64_t wlo = rg[0], whi = rg[1];
+    int64_t ilo = min(max(rg[2], wlo), whi), ihi = min(max(rg[3], wlo), whi);
+    if (ilo >= ihi) { ilo = whi; ihi = whi; }
+    ihi = max(ihi, ilo);
+    int64_t mlo = min(max(rg[6], ilo), ihi), mhi = min(max(rg[7], mlo), ihi);
+    int64_t nlo = a.lorentz ? mlo : min(max(rg[4], wlo), whi), nhi = a.lorentz ? mlo : min(max(rg[5], wlo), whi);
+    nlo = min(max(nlo, ilo), ihi);
+    nhi = min(max(nhi, nlo), ihi);
+    mlo = min(mlo, nlo);
+    mhi = max(mhi, nhi);
+    const int64_t i0 = tile * a.tile_pts, i1 = min(i0 + (int64_t)a.tile_pts, a.nnu);
+    const double tmin = a.nu[i0], tmax = a.nu[i1 - 1];
+    const double cen = 0.5 * (tmin + tmax), h = 0.5 * (tmax - tmin);
+    const double h2 = h * h, twoh = 2.0 * h;
+    const double4* rec = a.rec + (size_t)lev * a.nl;
+    const double* mom = a.mom + (size_t)lev * a.ncl * FF_REC;
+    double am[MP_P];
+#pragma unroll
+    for (int k = 0; k < MP_P; k++) am[k] = 0.0;
+    // per-line expansion of lines [j0,j1), one line per lane (same series as phase A of line_sum_kernel)
+    auto p2l = [&](int64_t j0, int64_t j1) {
+        for (int64_t j = j0 + lane; j < j1; j += 32) {
+            const double4 rc = ld_rec(rec + j);
+            const double u = rc.x - cen;
+            const double r = cs_rcp(fma(u, u, rc.y));
+            const double al = (u * r) * twoh, be = r * h2;
+            double ck2 = rc.z * r;
+            double ck1 = al * ck2;
+            am[0] += ck2;
+            am[1] += ck1;
+#pragma unroll
+            for (int k = 2; k < MP_P; k++) {
+                double ck = fma(al, ck1, -(be * ck2));
+                am[k] += ck;
+                ck2 = ck1;
+                ck1 = ck;
+            }
+        }
+    };
+#pragma unroll 1
+    for (int side = 0; side < 2; side++) {
+        const int64_t ja = side ? mhi : ilo, jb = side ? ihi : mlo;
+        if (ja >= jb) continue;
+        const int64_t cf = (ja + 31) >> 5, cl = min(jb >> 5, a.ncl);
+        if (cf >= cl) { p2l(ja, jb); continue; }
+        p2l(ja, cf << 5);
+        p2l(cl << 5, jb);
+        for (int64_t cb = cf; cb < cl; cb += 32) {
+            const int64_t c = cb + lane;
+            bool near_ = false;
+            if (c < cl) {
+                const double* mm = mom + (size_t)c * FF_REC;
+                const double R = mm[FF_P] - cen, rho = mm[FF_P + 1];
+                if (fabs(R) >= FF_THETA * (h + rho)) {
+                    // beta_m = mu_m (-1/R)^m, then FF_P suffix-sum passes over the live triangle (m + k <= FF_P)
+                    const double ir = 1.0 / R, mir = -ir;
+                    double cc[FF_P + 1];
+                    cc[0] = 0.0;
+                    double pw = mir;
+#pragma unroll
+                    for (int m = 1; m <= FF_P; m++) { cc[m] = mm[m - 1] * pw; pw *= mir; }
+                    double sc = -ir;              // -(h/R)^k / R
+                    const double hr = h * ir;
+#pragma unroll
+                    for (int k = 0; k < FF_P; k++) {
+#pragma unroll
+                        for (int m = FF_P - k - 1; m >= 0; m--) cc[m] += cc[m + 1];
+                        am[k] = fma(sc, cc[0], am[k]);
+                        sc *= hr;
+                    }
+                } else {
+                    near_ = true;
+                }
+            }
+            // clusters that are too close for the translation: their 32 lines take the per-line expansion
+            unsigned todo = __ballot_sync(0xffffffffu, near_);
+            while (todo) {
+                const int b = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const int64_t cc0 = (cb + b) << 5;
+                p2l(cc0, cc0 + 32);
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < MP_P; k++) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) am[k] += __shfl_xor_sync(0xffffffffu, am[k], off);
+    }
+    if (lane == 0) {
+        double* o = a.ffc + ((size_t)lev * a.ntiles + tile) * MP_P;
+#pragma unroll
+        for (int k = 0; k < MP_P; k++) o[k] = am[k];
+    }
+}
+
 // K2.  Work unit = one warp = (tile of 32*R consecutive wavenumbers, level).  Each warp streams the records of
 // ITS OWN line window through a private shared-memory ring fed by TMA bulk copies (one elected lane issues
 // cp.async.bulk, completion on a per-stage mbarrier), so warps never wait for each other.  The 8 warps of a CTA
@@ -563,8 +730,9 @@ __global__ void __launch_bounds__(LS_THREADS, 16 / LS_WARPS) line_sum_kernel(Lin
     if (lane == 0) {
         for (int q = 0; q < LS_NSEG; q++) { slo[q] = 0; shi[q] = 0; }
         if (mp) {
-            slo[0] = ilo; shi[0] = mlo;     // expanded (phase A), streamed first
-            slo[1] = mhi; shi[1] = ihi;
+            // expanded lines (phase A) are streamed first -- unless farfield_kernel already summed them
+            slo[0] = ilo; shi[0] = a.ffc ? ilo : mlo;
+            slo[1] = mhi; shi[1] = a.ffc ? mhi : ihi;
             slo[2] = 0;   shi[2] = ilo;
             slo[3] = mlo; shi[3] = mhi;
             slo[4] = ihi; shi[4] = whi;
@@ -648,6 +816,21 @@ __global__ void __launch_bounds__(LS_THREADS, 16 / LS_WARPS) line_sum_kernel(Lin
     // (all terms of the sum are positive, so that also bounds the relative error of the sum).  A lane sums the
     // coefficients of every 32nd line (3 FP64 ops per coefficient), a butterfly reduces them over the warp, and every
     // point then costs MP_P FMAs (Horner) instead of 5.25 FP64 ops per line.
+    if (mp && a.ffc) {
+        // far field precomputed per (tile, level) by farfield_kernel: evaluate its polynomial at the lane's points
+        const double cen = 0.5 * (w.nutile[0] + a.nu[min(tile0 + TILE, a.nnu) - 1]);
+        const double h = 0.5 * (a.nu[min(tile0 + TILE, a.nnu) - 1] - w.nutile[0]);
+        const double ih = h > 0.0 ? 1.0 / h : 0.0;
+        const double* fc = a.ffc + ((size_t)lev * a.ntiles + tile) * MP_P;
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const double t = (nup[r] - cen) * ih;
+            double v = fc[MP_P - 1];
+#pragma unroll
+            for (int k = MP_P - 2; k >= 0; k--) v = fma(v, t, fc[k]);
+            acc[r] = v;
+        }
+    }
     if (mp && nchunkA > 0) {
         const double cen = 0.5 * (w.nutile[0] + a.nu[min(tile0 + TILE, a.nnu) - 1]);
         const double h = 0.5 * (a.nu[min(tile0 + TILE, a.nnu) - 1] - w.nutile[0]);
@@ -976,11 +1159,18 @@ template <int SHAPE, int R> int32_t launch_line_sum(cs_ctx* ctx, LineSumArgs a, 
     if (SHAPE == CS_DOPPLER) a.mp_theta = 0.0;
     a.nr = (SHAPE == CS_PHCO2) ? LS_NR : (a.mp_theta > 0.0 ? 8 : 6);
     // scratch: the per-tile ranges, then (PHCO2 expansion) the per-line chi factors of the >= 120 cm^-1 class, which are
-    // level-independent; they are skipped when the span of the line list would overflow exp (the expansion is then off
-    // and every pair is summed directly)
-    const size_t off = ((sizeof(int64_t) * a.nr * (size_t)a.ntiles + 255) / 256) * 256;
+    // level-independent (skipped when the span of the line list would overflow exp: the expansion is then off and every
+    // pair is summed directly), or (Voigt / Lorentz expansion) the cluster moments and the far-field coefficients
+    auto al256 = [](size_t b) { return ((b + 255) / 256) * 256; };
+    const size_t off = al256(sizeof(int64_t) * a.nr * (size_t)a.ntiles);
     const bool want_chix = SHAPE == CS_PHCO2 && a.mp_theta > 0.0 && a.nl > 0 && 0.0232 * 0.5 * (a.nul_hi - a.nul_lo) < 600.0;
-    CS_TRY(ctx->s_w.reserve(off + (want_chix ? sizeof(double2) * (size_t)a.nl : 0)));
+    const bool want_ff = (SHAPE == CS_VOIGT || SHAPE == CS_LORENTZ) && a.mp_theta > 0.0 && a.nl > 0 &&
+                         getenv("CS_FARFIELD_NO_MOMENTS") == nullptr;
+    const int64_t ncl = a.nl / 32;
+    const size_t off_ffc = off + al256(sizeof(double) * FF_REC * (size_t)ncl * nlev);
+    const size_t total = want_chix ? off + sizeof(double2) * (size_t)a.nl
+                                   : (want_ff ? off_ffc + sizeof(double) * MP_P * (size_t)a.ntiles * nlev : off);
+    CS_TRY(ctx->s_w.reserve(total));
     a.ranges = ctx->s_w.as<int64_t>();
     tile_ranges_kernel<<<(unsigned)((a.ntiles * a.nr + 127) / 128), 128, 0, st>>>(a.nu, a.nnu, a.nul, a.nl, a.cut, cn, TILE,
                                                                                   a.ntiles, a.nr, a.mp_theta,
@@ -988,12 +1178,32 @@ template <int SHAPE, int R> int32_t launch_line_sum(cs_ctx* ctx, LineSumArgs a, 
     CS_CUDA(cudaGetLastError());
     a.chix = nullptr;
     a.chix_ref = 0.0;
+    a.ffc = nullptr;
     if (want_chix) {
         double2* cx = reinterpret_cast<double2*>(ctx->s_w.as<char>() + off);
         a.chix_ref = 0.5 * (a.nul_lo + a.nul_hi);
         chix_kernel<<<(unsigned)((a.nl + 255) / 256), 256, 0, st>>>(a.nul, a.nl, a.chix_ref, cx);
         CS_CUDA(cudaGetLastError());
         a.chix = cx;
+    }
+    if (want_ff) {
+        FarFieldArgs fa;
+        fa.nu = a.nu; fa.nnu = a.nnu; fa.nl = a.nl; fa.ncl = ncl; fa.ntiles = a.ntiles;
+        fa.rec = a.rec;
+        fa.mom = reinterpret_cast<const double*>(ctx->s_w.as<char>() + off);
+        fa.ranges = a.ranges;
+        fa.ffc = reinterpret_cast<double*>(ctx->s_w.as<char>() + off_ffc);
+        fa.tile_pts = TILE;
+        fa.lorentz = SHAPE == CS_LORENTZ;
+        if (ncl > 0) {
+            moments_kernel<<<dim3((unsigned)((ncl + 127) / 128), (unsigned)nlev), 128, 0, st>>>(
+                a.rec, a.nl, ncl, reinterpret_cast<double*>(ctx->s_w.as<char>() + off));
+            CS_CUDA(cudaGetLastError());
+        }
+        farfield_kernel<<<dim3((unsigned)((a.ntiles + 3) / 4), (unsigned)nlev), 128, 0, st>>>(fa);
+        CS_CUDA(cudaGetLastError());
+        cs_count_launch(ctx, 2);
+        a.ffc = fa.ffc;
     }
     size_t smem = (size_t)LS_WARPS * (LS_STAGES * LS_CHUNK * sizeof(double4) + ls_extra_bytes<SHAPE, R>());
     if (smem > 48 * 1024)   // per device: not cached, several contexts may live on different GPUs
