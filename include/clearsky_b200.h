@@ -75,7 +75,8 @@ int32_t cs_ctx_launches(cs_ctx* ctx, int64_t* launches);
  *   CS_FARFIELD_EXPANSION: lines that are inside the cut-off for ALL points of a 128-point tile and provably in the
  *     far wing are summed through local expansions about the tile centre instead of pair by pair.
  *       Voigt / Lorentz: lines at least 4 half tile widths away, where the reference's Voigt equals
- *         S*gamma/(pi*(dnu^2+gamma^2)): 20-term Taylor expansion, truncation below 3e-11 of each line's own value.
+ *         S*gamma/(pi*(dnu^2+gamma^2)): 20-term Taylor expansion, truncation below 3e-11 of each line's own value;
+ *         clusters of 32 lines at least 8 (h + cluster radius) away enter through 14 precomputed moments (< 1e-13).
  *       PHCO2: lines at least 30 cm^-1 from every point of the tile (chi classes 30-120 and >= 120, where chi factorises
  *         into a per-point and a per-line exponential): power-law expansions of K ge/dnu^2 (1 - eps + eps^2),
  *         eps = (chi*gamma/dnu)^2, used only at levels where the host bounds eps < 1e-4 and for tiles narrower than
