@@ -437,7 +437,7 @@ def run_ours(args):
                 "max_rel_diff_sigma_vs_direct": float(dσ.item()),
                 "linesum_kernel_ms_per_step": acc_x["linesum"] / args.steps,
                 "note": "far-wing lines >= 4 half tile widths away summed through a 20-term local expansion per tile (32-line clusters "
-                        "via 14 moments); truncation < 3e-11 per line"}
+                        "via 18 moments); truncation < 3e-11 per line"}
         except Exception as e:      # the extra section must never cost the headline line
             ctx.set_farfield("direct")
             line["farfield_expansion"] = {"error": repr(e)}

@@ -483,12 +483,13 @@ __device__ __noinline__ void cold_phco2_generic(const WarpCold& w, const double4
 //        a_k -= (h/R)^k/R * S_k,  S_k = sum_m C(m+k,k) beta_m,  beta_m = mu_m (-1/R)^m, and S_k is element 0 of the
 //        (k+1)-th suffix-sum pass over (0, beta_1, .., beta_p): no binomials, p^2/2 additions per cluster.
 // A cluster is translated when |R| >= FF_THETA (h + rho), rho = its radius including the largest half width; with
-// FF_P = 14 terms the truncation is below 1e-13 (tools/proto/m2l_lorentz.py measures 8e-15).  Clusters that are too close,
+// FF_THETA = 5 and FF_P = 18 terms the truncation is below 19 * 5^-18 = 5e-12 of the cluster's own contribution (measured:
+// the same 1.2e-12 agreement with the direct sum on C2 as the per-line expansion).  Clusters that are too close,
 // and the lines of the eligible ranges that do not fill a cluster, take the per-line expansion here as well, so K2 only
 // has to evaluate the resulting polynomial (MP_P coefficients per (tile, level)).
-constexpr int FF_P = 14;
-constexpr double FF_THETA = 8.0;
-constexpr int FF_REC = 16;      // doubles per (level, cluster): mu_1..mu_14, zc, rho
+constexpr int FF_P = 18;
+constexpr double FF_THETA = 5.0;
+constexpr int FF_REC = 20;      // doubles per (level, cluster): mu_1..mu_18, zc, rho
 
 __global__ void __launch_bounds__(128) moments_kernel(const double4* __restrict__ rec, int64_t nl, int64_t ncl,
                                                       double* __restrict__ mom)

@@ -76,7 +76,7 @@ int32_t cs_ctx_launches(cs_ctx* ctx, int64_t* launches);
  *     far wing are summed through local expansions about the tile centre instead of pair by pair.
  *       Voigt / Lorentz: lines at least 4 half tile widths away, where the reference's Voigt equals
  *         S*gamma/(pi*(dnu^2+gamma^2)): 20-term Taylor expansion, truncation below 3e-11 of each line's own value;
- *         clusters of 32 lines at least 8 (h + cluster radius) away enter through 14 precomputed moments (< 1e-13).
+ *         clusters of 32 lines at least 5 (h + cluster radius) away enter through 18 precomputed moments (< 5e-12).
  *       PHCO2: lines at least 30 cm^-1 from every point of the tile (chi classes 30-120 and >= 120, where chi factorises
  *         into a per-point and a per-line exponential): power-law expansions of K ge/dnu^2 (1 - eps + eps^2),
  *         eps = (chi*gamma/dnu)^2, used only at levels where the host bounds eps < 1e-4 and for tiles narrower than
