@@ -56,7 +56,7 @@ def main():
     g = rng.uniform(1e-5, 0.13, n)
     K = 10 ** rng.uniform(-30, -19, n) * g / np.pi
     direct = (K[:, None] / ((nu[None, :] - nul[:, None]) ** 2 + g[:, None] ** 2))
-    for theta, p in ((8.0, 14), (16.0, 11), (8.0, 12), (6.0, 16)):
+    for theta, p in ((5.0, 18), (8.0, 14), (16.0, 11), (8.0, 12), (6.0, 16)):      # the kernel uses (5, 18)
         a = np.zeros(p)
         used = np.zeros(n, bool)
         ncl = 0
