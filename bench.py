@@ -166,15 +166,38 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
+def host_threads():
+    """host cores this process may use (torchrun exports OMP_NUM_THREADS=1 for nproc > 1: never rely on the OpenMP default)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def workload_config(wl, world, total_evals):
+    """the `config` object of the JSON line -- identical for the repo arm and the reference arm"""
+    return {"workload": wl["name"], "lines": int(sum(len(sl.ν) for sl, _ in wl["gases"])), "n_nu": len(wl["ν"]),
+            "layers": wl["nlayer"], "shape": "voigt", "cutoff_cm-1": wl["cut"], "nstream": wl["nstream"],
+            "nlobatto": wl["nlob"], "evals_per_step": int(total_evals), "parallelism": f"nu-slices x{world}",
+            "l2": "per-step working set (line records 3.2 GB + sigma 0.24 GB) exceeds the 126 MB L2"}
+
+
+def total_evals_host(orc, wl):
+    """exact iterations of surf!'s inner loop (line_shapes.jl:75-82) over the whole workload, counted on the host"""
+    ν, cut = wl["ν"], wl["cut"]
+    return sum(orc.count_evals(ν, orc.included_lines(ν, sl.ν, cut), cut) for sl, _ in wl["gases"]) * len(wl["P"])
+
+
 def cpu_sample(cs, orc, wl, nthreads, target_evals=2.0e9):
     """bounded CPU sample of the same workload: a contiguous ν slice from the middle of the grid × all levels,
-    both gases, oracle restatement parallel over levels (like bake's @threads, gases.jl:115) then fluxes."""
+    both gases, oracle restatement parallel over levels (like bake's @threads, gases.jl:115) then fluxes.
+    run() -> (Σ[nlev, n], flux dict): the values are kept, the GPU is checked against them (parity_sample)."""
     ν, P, T = wl["ν"], wl["P"], wl["T"]
     nlev = len(P)
     per_ν = sum(len(sl.ν) for sl, _ in wl["gases"]) * (2 * wl["cut"]) / 3000.0 * nlev
     n = int(min(len(ν), max(64, target_evals / per_ν)))
     i0 = (len(ν) - n) // 2
-    νs = ν[i0:i0 + n]
+    νs = np.ascontiguousarray(ν[i0:i0 + n])
     evals = sum(orc.count_evals(νs, orc.included_lines(νs, sl.ν, wl["cut"]), wl["cut"]) for sl, _ in wl["gases"]) * nlev
     m, W = cs.streamnodes(wl["nstream"])
     x, w = cs.lobattonodes(wl["nlob"])
@@ -184,13 +207,17 @@ def cpu_sample(cs, orc, wl, nthreads, target_evals=2.0e9):
         σ = np.zeros((nlev, n))
         for sl, C in wl["gases"]:
             σ += C * orc.xsec(orc.VOIGT, sl, νs, T, P, C * P, wl["cut"], nthreads=nthreads)
-        return orc.fluxes(νs, P, wl["nlob"], w, μn, T, σ, wl["g"], None, None, 0.841, wl["nstream"], m, W,
-                          nthreads=nthreads, full=False)
+        F = orc.fluxes(νs, P, wl["nlob"], w, μn, T, σ, wl["g"], None, None, 0.841, wl["nstream"], m, W,
+                       nthreads=nthreads, full=False)
+        return σ, F
 
-    return run, evals, f"ν slice of {n} points (indices {i0}..{i0 + n - 1}) × all {nlev} levels, both gases, Voigt + fluxes"
+    sample = f"ν slice of {n} points (indices {i0}..{i0 + n - 1}) × all {nlev} levels, both gases, Voigt + fluxes"
+    return run, evals, sample, (i0, n)
 
 
 def run_reference(args):
+    """the reference's own CPU algorithm for the path (oracle/ port: no Julia runtime in the image), all host threads,
+    each step one bounded sample of the workload sized so that warm-up + steps end within a few minutes"""
     import clearsky_b200 as cs   # host-side generators/readers only: no CUDA call on this arm
     from oracle import oracle as orc
     rank = int(os.environ.get("RANK", "0"))
@@ -198,8 +225,18 @@ def run_reference(args):
         return
     orc.build()
     wl = make_workload(cs, args.workload)
-    nthreads = orc.max_threads()
-    run, evals, sample = cpu_sample(cs, orc, wl, 0, target_evals=args.cpu_evals)
+    nthreads = host_threads()
+    if args.cpu_evals > 0:
+        target = args.cpu_evals
+    else:
+        # calibrate on a small sample, then size the step so that (warm-up + steps) x t stays near 150 s
+        run, evals, _, _ = cpu_sample(cs, orc, wl, nthreads, target_evals=1.0e9)
+        run()
+        t0 = time.perf_counter()
+        run()
+        rate = evals / (time.perf_counter() - t0)
+        target = min(4.0e10, max(5.0e8, rate * 150.0 / max(1, args.steps + args.warmup)))
+    run, evals, sample, _ = cpu_sample(cs, orc, wl, nthreads, target_evals=target)
     for _ in range(args.warmup):
         run()
     t0 = time.perf_counter()
@@ -207,12 +244,14 @@ def run_reference(args):
         run()
     dt = (time.perf_counter() - t0) / args.steps
     v = evals / dt
+    cfg = workload_config(wl, args.gpus, total_evals_host(orc, wl))
+    cfg["sample"] = sample
+    cfg["note"] = ("CPU restatement of the reference (oracle/, C + OpenMP over levels like bake's @threads); the Julia "
+                   "reference cannot run here (no Julia runtime in the image)")
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl["name"], "note": "CPU restatement of the reference (oracle/, C + OpenMP); the Julia "
-                   "reference cannot run here (no Julia runtime in the image)"},
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": nthreads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -225,6 +264,7 @@ def run_ours(args):
     import torch.distributed as dist
 
     import clearsky_b200 as cs
+    from clearsky_b200 import sharding
     from clearsky_b200._lib import check, f64, lib, ptr
 
     rank = int(os.environ.get("RANK", "0"))
@@ -258,29 +298,23 @@ def run_ours(args):
     cut = wl["cut"]
 
     # ---- ν sharding: contiguous slices balanced by evaluations, global trapezoid weights
-    counts = sum(per_point_counts(ν, sl.ν, cut) for sl, _ in wl["gases"])
     edges = balanced_slices(slice_cost(ν, wl["gases"], cut), world)
     i0, i1 = edges[rank], edges[rank + 1]
     νs = np.ascontiguousarray(ν[i0:i1])
     wts = np.ascontiguousarray(trapz_weights(ν)[i0:i1])
-    # exact evaluation counts (iterations of surf!'s inner loop, line_shapes.jl:75-82) from the library's host counter
-    total_evals = my_evals = None
-
-    def slice_lines(sl):
-        # every line the slice can see: the per-point rule decides inside the kernel
-        keep = (sl.ν >= νs[0] - cut - 1e-9) & (sl.ν <= νs[-1] + cut + 1e-9)
-        return cs.SpectralLines(sl.name, sl.formula, int(keep.sum()), sl.M, sl.I[keep], sl.μ[keep], sl.A[keep],
-                                sl.ν[keep], sl.S[keep], sl.γa[keep], sl.γs[keep], sl.Epp[keep], sl.na[keep])
-
-    my_gases = [(slice_lines(sl), C) for sl, C in wl["gases"]]
+    # every line the slice can see: the inclusive per-point rule decides inside the kernel; the strict prefilter of
+    # includedlines is applied to the GLOBAL grid (cs_lines_set_grid_range), as in the unsharded run
+    my_gases = [(sharding.slice_lines(sl, νs[0], νs[-1], cut, grid=(ν[0], ν[-1])), C) for sl, C in wl["gases"]]
     m, W = cs.streamnodes(wl["nstream"])
     x, w = cs.lobattonodes(wl["nlob"])
+    m, W, w = f64(m), f64(W), f64(w)
     μn = f64(np.full((nlev - 1, wl["nlob"]), wl["μ"]))
     Tn, Pn = f64(T), f64(P)
     dF = torch.zeros(2 * nlev, dtype=torch.float64, device=f"cuda:{local}")
 
     # resident objects for the device-timed loop
     dls = [cs.DeviceLines(sl, ctx) for sl, _ in my_gases]
+    # exact evaluation counts (iterations of surf!'s inner loop, line_shapes.jl:75-82) from the library's host counter
     my_evals = sum(dl.count_evals(νs, cut) for dl in dls) * nlev
     if world > 1:
         t_ev = torch.tensor([float(my_evals)], dtype=torch.float64, device=f"cuda:{local}")
@@ -290,22 +324,14 @@ def run_ours(args):
         total_evals = my_evals
     ws = cs.SigmaWorkspace(νs, nlev, ctx)
     Cs = [f64(np.full(nlev, C)) for _, C in my_gases]
-    timers_acc = {"linesum": 0.0, "prep": 0.0, "rt": 0.0, "reduce": 0.0}
 
-    # the library accumulates linesum/prep timers across cs_sigma_add_lines calls: read deltas instead
-    def timed_step(acc):
-        t0 = ctx.timers()
+    def timed_step():
+        """one pass of the hot path with inputs resident in HBM; no host synchronisation anywhere in it"""
         ws.zero()
         for dl, C in zip(dls, Cs):
             check(lib().cs_sigma_add_lines(ws.h, dl.h, cs._lib.CS_VOIGT, ptr(Tn), ptr(Pn), ptr(C), cut))
-        t1 = ctx.timers()
-        acc["linesum"] += t1["linesum"] - t0["linesum"]
-        acc["prep"] += t1["prep"] - t0["prep"]
-        check(lib().cs_fluxes_device(ws.h, nlev, ptr(Pn), wl["nlob"], ptr(f64(w)), ptr(μn), ptr(Tn), wl["g"], None, None,
-                                     0.841, wl["nstream"], ptr(f64(m)), ptr(f64(W)), ptr(wts), dF.data_ptr()))
-        t2 = ctx.timers()
-        acc["rt"] += t2["rt"]
-        acc["reduce"] += t2["reduce"]
+        check(lib().cs_fluxes_device(ws.h, nlev, ptr(Pn), wl["nlob"], ptr(w), ptr(μn), ptr(Tn), wl["g"], None, None,
+                                     0.841, wl["nstream"], ptr(m), ptr(W), ptr(wts), dF.data_ptr()))
         if world > 1:
             dist.all_reduce(dF)
         return dF
@@ -316,41 +342,71 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # ---- end-to-end inputs: pinned host copies of everything a step uploads (the byte counts below are taken from
+    # these very arrays)
+    def pinned(a):
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        return t.numpy()
+
+    def pinned_lines(sl):
+        return cs.SpectralLines(sl.name, sl.formula, sl.N, sl.M, pinned(sl.I), pinned(sl.μ), pinned(sl.A), pinned(sl.ν),
+                                pinned(sl.S), pinned(sl.γa), pinned(sl.γs), pinned(sl.Epp), pinned(sl.na))
+
+    e2e_gases = []
+    for sl, C in my_gases:
+        pl = pinned_lines(sl)
+        if hasattr(sl, "grid_range"):
+            pl.grid_range = sl.grid_range
+        e2e_gases.append((pl, C))
+    νs_pin, wts_pin = pinned(νs), pinned(wts)
+    Fhost = torch.empty(2 * nlev, dtype=torch.float64).pin_memory()
+    h2d_step = 0
+    for sl, _ in e2e_gases:
+        niso, ncheb, cheb, has = sl.cheb_table()
+        h2d_step += sum(a.nbytes for a in (sl.ν, sl.S, sl.γa, sl.γs, sl.Epp, sl.na, sl.μ)) + len(sl.I) * 2
+        h2d_step += np.asarray(ncheb).nbytes + np.asarray(cheb).nbytes
+        h2d_step += nlev * 8 * 8                        # LevelParams block of cs_sigma_add_lines
+    h2d_step += 2 * νs_pin.nbytes                       # cs_sigma_create: ν and its trapezoid weights
+    h2d_step += wts_pin.nbytes                          # global trapezoid weights of cs_fluxes_device
+    h2d_step += (2 * nlev + wl["nlob"] * (nlev - 1) + wl["nlob"] + 3 * wl["nstream"]) * 8   # per-level tables of K6
+    d2h_step = Fhost.numel() * 8
+
     def e2e_step():
         """the call a user makes, from HOST buffers: upload lines + ν, Σ by exact line-by-line gas, fluxes, read F"""
-        gases = [cs.LineGas(_fresh(sl), C, νs, "voigt", cut, ctx=ctx) for sl, C in my_gases]
+        for sl, _ in e2e_gases:
+            sl.__dict__.pop("_dev", None)               # force a fresh cs_lines_upload every step
+        gases = [cs.LineGas(sl, C, νs_pin, "voigt", cut, ctx=ctx) for sl, C in e2e_gases]
         A = cs.UnifiedAbsorber(*gases)
-        wsx = cs.SigmaWorkspace(νs, nlev, ctx)
+        wsx = cs.SigmaWorkspace(νs_pin, nlev, ctx)
         A.sigma_nodes(wsx, Tn, Pn)
-        check(lib().cs_fluxes_device(wsx.h, nlev, ptr(Pn), wl["nlob"], ptr(f64(w)), ptr(μn), ptr(Tn), wl["g"], None, None,
-                                     0.841, wl["nstream"], ptr(f64(m)), ptr(f64(W)), ptr(wts), dF.data_ptr()))
+        check(lib().cs_fluxes_device(wsx.h, nlev, ptr(Pn), wl["nlob"], ptr(w), ptr(μn), ptr(Tn), wl["g"], None, None,
+                                     0.841, wl["nstream"], ptr(m), ptr(W), ptr(wts_pin), dF.data_ptr()))
         if world > 1:
             dist.all_reduce(dF)
-        return dF.cpu().numpy()
-
-    def _fresh(sl):
-        import copy
-        c = copy.copy(sl)
-        c.__dict__.pop("_dev", None)
-        return c
+        Fhost.copy_(dF, non_blocking=False)
+        return Fhost
 
     # ---- warm-up
-    for _ in range(max(args.warmup, 1)):
-        timed_step({"linesum": 0.0, "prep": 0.0, "rt": 0.0, "reduce": 0.0})
+    for _ in range(max(args.warmup, 3)):
+        timed_step()
+    barrier()
     fp64_peak = ctx.fp64_peak(20000)   # burst DFMA rate of this device [FLOP/s]
 
     # ---- device-timed region (inputs resident in HBM)
     barrier()
     l0 = ctx.launches()
+    tt0 = ctx.timers_total()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clk:
         ev0.record()
         for _ in range(args.steps):
-            timed_step(timers_acc)
+            timed_step()
         ev1.record()
         barrier()
         dt = ev0.elapsed_time(ev1) * 1e-3
     launches = ctx.launches() - l0
+    tt1 = ctx.timers_total()
+    timers_acc = {k: tt1[k] - tt0[k] for k in tt1}
     tmax = torch.tensor([dt], dtype=torch.float64, device=f"cuda:{local}")
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -358,21 +414,20 @@ def run_ours(args):
     F = dF.cpu().numpy()
     olr = float(F[0])
 
-    # ---- end-to-end through the public API with host buffers
-    e2e_step()
+    # ---- end-to-end through the public API with host buffers: the same number of steps, H2D and D2H inside
+    for _ in range(2):
+        e2e_step()
     barrier()
     t0 = time.perf_counter()
-    n_e2e = max(1, min(args.steps, 3))
-    for _ in range(n_e2e):
+    for _ in range(args.steps):
         e2e_step()
     barrier()
     dte = time.perf_counter() - t0
     te = torch.tensor([dte], dtype=torch.float64, device=f"cuda:{local}")
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    dte = float(te.item()) / n_e2e
-    h2d = sum(len(sl.ν) * (7 * 8 + 2) for sl, _ in my_gases) + len(νs) * 8 * 2 + nlev * 8 * 6
-    d2h = 2 * nlev * 8
+    dte = float(te.item()) / args.steps
+    Fe = Fhost.numpy().copy()
 
     ms_step = dt / args.steps * 1e3
     value = total_evals / (dt / args.steps)
@@ -381,22 +436,21 @@ def run_ours(args):
     achieved = FLOP_PER_EVAL * my_evals / (ls_ms * 1e-3) / 1e12 if ls_ms > 0 else None
 
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": wl["name"], "lines": int(sum(len(sl.ν) for sl, _ in wl["gases"])), "n_nu": len(ν),
-                   "layers": wl["nlayer"], "shape": "voigt", "cutoff_cm-1": cut, "nstream": wl["nstream"],
-                   "nlobatto": wl["nlob"], "evals_per_step": total_evals, "parallelism": f"nu-slices x{world}",
-                   "l2": "per-step working set (line records 3.2 GB + sigma 0.24 GB) exceeds the 126 MB L2"},
+        "config": workload_config(wl, world, total_evals),
         "olr_w_m2": olr, "olr_spectra_per_s": 1.0 / (dt / args.steps),
-        "e2e": {"value": total_evals / dte, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": dte * 1e3},
+        "e2e": {"value": total_evals / dte, "unit": UNIT, "h2d_bytes_per_step": int(h2d_step), "d2h_bytes_per_step": int(d2h_step),
+                "ms_per_step": dte * 1e3, "steps": args.steps, "host_memory": "pinned",
+                "max_rel_diff_fluxes_vs_resident": float(np.max(np.abs(Fe - F) / np.maximum(np.abs(F), 1e-300)))},
         "gpu_launches": int(launches),
         "clocks": clk.summary(),
         "roofline": {"bound": "fp64", "kernel": "line_sum_kernel<VOIGT>", "achieved": achieved, "peak": fp64_peak / 1e12,
                      "unit": "TFLOP/s", "frac": (achieved / (fp64_peak / 1e12)) if achieved else None,
                      "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH if wl["name"] == "c2" and world == 1 else None,
-                     "peak_source": "cs_fp64_peak DFMA microbenchmark run in this process (FP64 is not in MEASURED_PEAKS.json)",
+                     "peak_source": "cs_fp64_peak DFMA microbenchmark run in this process (FP64 is not in MEASURED_PEAKS.json; "
+                                    "recorded with clocks in profiles/r2_fp64_peak.json)",
                      "flop_per_eval": FLOP_PER_EVAL, "kernel_ms_per_step": ls_ms, "launches_per_step": n_ls_launch,
                      "kernel_share_of_step": ls_ms / ms_step if ms_step > 0 else None,
                      "rt_kernel_ms_per_step": timers_acc["rt"] / args.steps,
@@ -408,15 +462,17 @@ def run_ours(args):
     if not args.no_expansion:
         try:
             ctx.set_farfield("expansion")
-            acc_x = {"linesum": 0.0, "prep": 0.0, "rt": 0.0, "reduce": 0.0}
-            timed_step({"linesum": 0.0, "prep": 0.0, "rt": 0.0, "reduce": 0.0})
+            for _ in range(2):
+                timed_step()
             barrier()
+            tx0 = ctx.timers_total()
             ex0, ex1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ex0.record()
             for _ in range(args.steps):
-                timed_step(acc_x)
+                timed_step()
             ex1.record()
             barrier()
+            tx1 = ctx.timers_total()
             dtx = torch.tensor([ex0.elapsed_time(ex1) * 1e-3], dtype=torch.float64, device=f"cuda:{local}")
             if world > 1:
                 dist.all_reduce(dtx, op=dist.ReduceOp.MAX)
@@ -424,7 +480,7 @@ def run_ours(args):
             Fx = dF.cpu().numpy()
             Σx = ws.read()
             ctx.set_farfield("direct")
-            timed_step({"linesum": 0.0, "prep": 0.0, "rt": 0.0, "reduce": 0.0})
+            timed_step()
             Σd = ws.read()
             dσ = torch.tensor([float(np.max(np.abs(Σx - Σd) / np.maximum(Σd, 1e-300)))], dtype=torch.float64, device=f"cuda:{local}")
             del Σx, Σd
@@ -435,28 +491,61 @@ def run_ours(args):
                 "value": total_evals / dtx, "unit": UNIT, "ms_per_step": dtx * 1e3, "olr_spectra_per_s": 1.0 / dtx,
                 "olr_w_m2": float(Fx[0]), "max_rel_diff_fluxes_vs_direct": float(np.max(np.abs(Fx[nz] - F[nz]) / np.abs(F[nz]))),
                 "max_rel_diff_sigma_vs_direct": float(dσ.item()),
-                "linesum_kernel_ms_per_step": acc_x["linesum"] / args.steps,
+                "linesum_kernel_ms_per_step": (tx1["linesum"] - tx0["linesum"]) / args.steps,
                 "note": "far-wing lines >= 4 half tile widths away summed through a 20-term local expansion per tile (32-line clusters "
                         "via 18 moments); truncation < 3e-11 per line"}
         except Exception as e:      # the extra section must never cost the headline line
             ctx.set_farfield("direct")
             line["farfield_expansion"] = {"error": repr(e)}
 
-    # ---- CPU baseline (rank 0, N = 1 only): oracle port on the box's host cores, bounded sample
+    # ---- CPU baseline + parity sample (rank 0, N = 1 only): the oracle port on the box's host cores over a bounded ν
+    # slice of the SAME workload; its cross-sections and fluxes are kept and the GPU is run on the same slice in both
+    # far-field modes and compared (1e-9 on cross-sections, 1e-8 on fluxes: the north-star tolerances)
+    parity_fail = None
     if rank == 0 and world == 1 and not args.no_cpu:
         from oracle import oracle as orc
         orc.build()
-        run, evals, sample = cpu_sample(cs, orc, wl, 0, target_evals=args.cpu_evals)
+        nth = host_threads()
+        run, evals, sample, (j0, n) = cpu_sample(cs, orc, wl, nth, target_evals=args.cpu_evals if args.cpu_evals > 0 else 2.0e10)
         run()
         t0 = time.perf_counter()
-        run()
+        σo, Fo = run()
         tc = time.perf_counter() - t0
-        line["cpu_baseline"] = {"value": evals / tc, "unit": UNIT, "cores": orc.max_threads(), "kind": "port", "sample": sample,
+        line["cpu_baseline"] = {"value": evals / tc, "unit": UNIT, "cores": nth, "kind": "port", "sample": sample,
                                 "seconds": tc}
+        νp = np.ascontiguousarray(ν[j0:j0 + n])
+        wsp = cs.SigmaWorkspace(νp, nlev, ctx)
+        ps = {"n_nu": int(n), "levels": int(nlev), "sample": sample, "tol_sigma": 1e-9, "tol_flux": 1e-8}
+        keep = σo > 1e-290
+        try:
+            for mode in ("direct", "expansion"):
+                ctx.set_farfield(mode)
+                wsp.zero()
+                for dl, C in zip(dls, Cs):
+                    check(lib().cs_sigma_add_lines(wsp.h, dl.h, cs._lib.CS_VOIGT, ptr(Tn), ptr(Pn), ptr(C), cut))
+                Fg = np.empty(2 * nlev), np.empty(nlev)
+                Fup, Fdn, Fnet = np.empty(nlev), np.empty(nlev), np.empty(nlev)
+                check(lib().cs_fluxes(wsp.h, nlev, ptr(Pn), wl["nlob"], ptr(w), ptr(μn), ptr(Tn), wl["g"], None, None, 0.841,
+                                      wl["nstream"], ptr(m), ptr(W), None, None, None, None, ptr(Fup), ptr(Fdn), ptr(Fnet)))
+                Σg = wsp.read()
+                ps[f"max_rel_sigma_{mode}"] = float(np.max(np.abs(Σg[keep] - σo[keep]) / σo[keep]))
+                ef = max(float(np.max(np.abs(Fup - Fo["Fup"]) / np.abs(Fo["Fup"]))),
+                         float(np.max(np.abs(Fdn[1:] - Fo["Fdn"][1:]) / np.abs(Fo["Fdn"][1:]))))
+                ps[f"max_rel_flux_{mode}"] = ef
+            ps["max_rel_flux"] = max(ps["max_rel_flux_direct"], ps["max_rel_flux_expansion"])
+        finally:
+            ctx.set_farfield("direct")
+        ps["ok"] = bool(ps["max_rel_sigma_direct"] <= 1e-9 and ps["max_rel_sigma_expansion"] <= 1e-9 and ps["max_rel_flux"] <= 1e-8)
+        line["parity_sample"] = ps
+        if not ps["ok"]:
+            parity_fail = ps
     if rank == 0:
         print(json.dumps(line, ensure_ascii=False))
     if world > 1:
         dist.destroy_process_group()
+    if parity_fail is not None:
+        print(f"bench.py: PARITY FAILURE against the oracle on the sample: {parity_fail}", file=sys.stderr)
+        sys.exit(3)
 
 
 def main():
@@ -466,7 +555,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=["c2", "c2small"])
-    ap.add_argument("--cpu-evals", type=float, default=4.0e10, help="size of the bounded CPU sample [evals]")
+    ap.add_argument("--cpu-evals", type=float, default=0.0,
+                    help="size of the bounded CPU sample [evals]; 0 = 2e10 for the cpu_baseline leg, and for --impl reference "
+                         "a size calibrated so that warm-up + steps take about 150 s")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-expansion", action="store_true", help="skip the extra far-field-expansion measurement")
     args = ap.parse_args()

@@ -32,6 +32,7 @@ SIGNATURES = {
     "cs_ctx_free": [_vp],
     "cs_ctx_synchronize": [_vp],
     "cs_ctx_timers": [_vp, _dp],
+    "cs_ctx_timers_total": [_vp, _dp],
     "cs_ctx_launches": [_vp, _i64p],
     "cs_ctx_set_farfield": [_vp, C.c_int32],
     "cs_ctx_get_farfield": [_vp, C.POINTER(C.c_int32)],
@@ -40,6 +41,7 @@ SIGNATURES = {
     "cs_lines_upload": [_vp, C.c_int64, _dp, _dp, _dp, _dp, _dp, _dp, _dp, C.POINTER(C.c_int16), C.c_int32,
                         C.POINTER(C.c_int32), _dp, C.POINTER(C.c_uint8), C.POINTER(_vp)],
     "cs_lines_free": [_vp],
+    "cs_lines_set_grid_range": [_vp, C.c_double, C.c_double],
     "cs_line_params": [_vp, C.c_double, C.c_double, C.c_double, _dp, _dp, _dp],
     "cs_xsec": [_vp, C.c_int32, C.c_int64, _dp, C.c_int64, _dp, _dp, _dp, C.c_double, _dp],
     "cs_count_evals": [_vp, C.c_int64, _dp, C.c_double, _i64p],
@@ -154,6 +156,12 @@ class Context:
     def timers(self):
         t = np.zeros(CS_NTIMERS)
         check(lib().cs_ctx_timers(self.h, ptr(t)))
+        return dict(zip(TIMER_NAMES, t.tolist()))
+
+    def timers_total(self):
+        """the same timers accumulated since the context was created (take differences around a region)"""
+        t = np.zeros(CS_NTIMERS)
+        check(lib().cs_ctx_timers_total(self.h, ptr(t)))
         return dict(zip(TIMER_NAMES, t.tolist()))
 
     def launches(self):

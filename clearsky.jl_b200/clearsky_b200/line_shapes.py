@@ -39,6 +39,9 @@ class DeviceLines:
             ncheb.ctypes.data_as(C.POINTER(C.c_int32)), ptr(np.ascontiguousarray(cheb)),
             has.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(self.h)))
         self.N = len(sl.ν)
+        rng = getattr(sl, "grid_range", None)      # set by sharding.slice_lines on the line list of a ν slice
+        if rng is not None:
+            check(lib().cs_lines_set_grid_range(self.h, float(rng[0]), float(rng[1])))
 
     def count_evals(self, ν, Δνcut):
         ν = f64(ν)

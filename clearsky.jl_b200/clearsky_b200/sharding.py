@@ -61,13 +61,19 @@ def trapz_weights(ν):
     return w
 
 
-def slice_lines(sl, νlo, νhi, cut):
-    """every line a slice can see (the per-point inclusive rule decides inside the kernel)"""
+def slice_lines(sl, νlo, νhi, cut, grid=None):
+    """every line a slice [νlo, νhi] can see (the per-point inclusive rule decides inside the kernel).
+    grid = (first, last) point of the GLOBAL wavenumber grid: recorded on the slice's line list so that the library applies
+    the strict `includedlines` prefilter (line_shapes.jl:18-22) to the grid the reference would see -- a line exactly one
+    cut-off away from an INTERIOR slice edge then counts exactly as in the unsharded run (cs_lines_set_grid_range)."""
     keep = (sl.ν >= νlo - cut - 1e-9) & (sl.ν <= νhi + cut + 1e-9)
     if not keep.any():
         keep[np.argmin(np.abs(sl.ν - νlo))] = True      # keep one (out-of-window) line: an upload cannot be empty
-    return SpectralLines(sl.name, sl.formula, int(keep.sum()), sl.M, sl.I[keep], sl.μ[keep], sl.A[keep], sl.ν[keep],
-                         sl.S[keep], sl.γa[keep], sl.γs[keep], sl.Epp[keep], sl.na[keep])
+    out = SpectralLines(sl.name, sl.formula, int(keep.sum()), sl.M, sl.I[keep], sl.μ[keep], sl.A[keep], sl.ν[keep],
+                        sl.S[keep], sl.γa[keep], sl.γs[keep], sl.Epp[keep], sl.na[keep])
+    if grid is not None:
+        out.grid_range = (float(grid[0]), float(grid[1]))
+    return out
 
 
 class DeviceGroup:
@@ -228,7 +234,8 @@ class ShardedLineByLine(ShardedAbsorber):
                    for sl, _, shape, cut in self.gases)
 
         def build(νs, ctx):
-            lg = [LineGas(slice_lines(sl, νs[0], νs[-1], cut), fC, νs, shape, cut, ctx=ctx) for sl, fC, shape, cut in self.gases]
+            lg = [LineGas(slice_lines(sl, νs[0], νs[-1], cut, grid=(ν[0], ν[-1])), fC, νs, shape, cut, ctx=ctx)
+                  for sl, fC, shape, cut in self.gases]
             return tuple(lg) + tuple(self.cia)
 
         super().__init__(group, ν, build, cost=cost)

@@ -63,8 +63,16 @@ static int32_t ctx_create(int32_t device, void* stream, bool own, cs_ctx** out)
         c->stream = (cudaStream_t)stream;
     }
     c->own_stream = own;
+    {
+        DevBuf* bufs[] = {&c->s_nu, &c->s_lev, &c->s_rec, &c->s_slow, &c->s_sigma, &c->s_misc, &c->s_part,
+                          &c->s_tau, &c->s_planck, &c->s_out0, &c->s_out1, &c->s_out2, &c->s_w};
+        for (DevBuf* b : bufs) b->st = c->stream;
+    }
+    // environment switches are read once here, never in a launch path
     if (const char* ff = getenv("CS_FARFIELD"))
         c->farfield = (strcmp(ff, "expansion") == 0) ? CS_FARFIELD_EXPANSION : CS_FARFIELD_DIRECT;
+    c->ff_no_moments = getenv("CS_FARFIELD_NO_MOMENTS") != nullptr;
+    c->table_no_mma = getenv("CS_TABLE_EVAL_NO_MMA") != nullptr;
     {
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -90,6 +98,12 @@ extern "C" int32_t cs_ctx_free(cs_ctx* c)
     DevBuf* bufs[] = {&c->s_nu, &c->s_lev, &c->s_rec, &c->s_slow, &c->s_sigma, &c->s_misc, &c->s_part,
                       &c->s_tau, &c->s_planck, &c->s_out0, &c->s_out1, &c->s_out2, &c->s_w};
     for (DevBuf* b : bufs) b->release();
+    for (TimerSpan& sp : c->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+    for (cudaEvent_t e : c->ev_free) cudaEventDestroy(e);
+    for (StageSlot& sl : c->stage) {
+        if (sl.p) cudaFreeHost(sl.p);
+        if (sl.done) cudaEventDestroy(sl.done);
+    }
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
     cudaEventDestroy(c->ev2);
@@ -109,7 +123,20 @@ extern "C" int32_t cs_ctx_synchronize(cs_ctx* c)
 extern "C" int32_t cs_ctx_timers(cs_ctx* c, double* t)
 {
     CS_REQUIRE(c && t, CS_ERR_ARG, "null argument");
+    std::lock_guard<std::recursive_mutex> lk(c->mtx);
+    CS_CUDA(cudaSetDevice(c->device));
+    cs_spans_collect(c, true);
     for (int i = 0; i < CS_NTIMERS; i++) t[i] = c->last_kernel_ms[i];
+    return CS_OK;
+}
+
+extern "C" int32_t cs_ctx_timers_total(cs_ctx* c, double* t)
+{
+    CS_REQUIRE(c && t, CS_ERR_ARG, "null argument");
+    std::lock_guard<std::recursive_mutex> lk(c->mtx);
+    CS_CUDA(cudaSetDevice(c->device));
+    cs_spans_collect(c, true);
+    for (int i = 0; i < CS_NTIMERS; i++) t[i] = c->total_kernel_ms[i];
     return CS_OK;
 }
 
@@ -147,7 +174,97 @@ extern "C" int32_t cs_ctx_set_tau_floor(cs_ctx* c, double tau_min)
 
 void cs_reset_timers(cs_ctx* c)
 {
+    cs_spans_collect(c, false);
+    // spans still in flight belong to earlier calls: they keep counting towards the totals only
+    for (TimerSpan& sp : c->spans)
+        if (sp.id >= 0) sp.id = -1 - sp.id;
     for (int i = 0; i < CS_NTIMERS; i++) c->last_kernel_ms[i] = 0.0;
+}
+
+static cudaEvent_t ev_acquire(cs_ctx* c)
+{
+    cudaEvent_t e = nullptr;
+    if (!c->ev_free.empty()) {
+        e = c->ev_free.back();
+        c->ev_free.pop_back();
+    } else {
+        cudaEventCreate(&e);
+    }
+    return e;
+}
+
+int cs_span_begin(cs_ctx* c, int id, bool assign)
+{
+    if (c->spans.size() >= 1024) cs_spans_collect(c, true);   // nobody reads the timers: keep the list bounded
+    TimerSpan sp;
+    sp.a = ev_acquire(c);
+    sp.b = ev_acquire(c);
+    sp.id = id;
+    sp.assign = assign;
+    sp.closed = false;
+    cudaEventRecord(sp.a, c->stream);
+    c->spans.push_back(sp);
+    return (int)c->spans.size() - 1;
+}
+
+void cs_span_end(cs_ctx* c, int span)
+{
+    TimerSpan& sp = c->spans[(size_t)span];
+    cudaEventRecord(sp.b, c->stream);
+    sp.closed = true;
+}
+
+void cs_spans_collect(cs_ctx* c, bool block)
+{
+    size_t done = 0;
+    for (; done < c->spans.size(); done++) {
+        TimerSpan& sp = c->spans[done];
+        if (!sp.closed) break;
+        if (block) {
+            if (cudaEventSynchronize(sp.b) != cudaSuccess) { cudaGetLastError(); }
+        } else if (cudaEventQuery(sp.b) != cudaSuccess) {
+            cudaGetLastError();   // cudaErrorNotReady is not sticky, but clear it
+            break;
+        }
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, sp.a, sp.b) != cudaSuccess) { cudaGetLastError(); ms = 0.f; }
+        const bool stale = sp.id < 0;               // recorded before the last cs_reset_timers
+        const int id = stale ? -1 - sp.id : sp.id;
+        c->total_kernel_ms[id] += ms;
+        if (!stale) {
+            if (sp.assign) c->last_kernel_ms[id] = ms;
+            else c->last_kernel_ms[id] += ms;
+        }
+        c->ev_free.push_back(sp.a);
+        c->ev_free.push_back(sp.b);
+    }
+    c->spans.erase(c->spans.begin(), c->spans.begin() + (std::ptrdiff_t)done);
+}
+
+int32_t cs_stage_h2d(cs_ctx* c, void* dst, const void* src, size_t bytes)
+{
+    if (bytes == 0) return CS_OK;
+    if (bytes > CS_STAGE_MAX) {
+        CS_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+        return CS_OK;
+    }
+    StageSlot& sl = c->stage[c->stage_next];
+    c->stage_next = (c->stage_next + 1) % CS_NSTAGE;
+    if (sl.used) CS_CUDA(cudaEventSynchronize(sl.done));    // its previous copy has long executed in the steady state
+    if (sl.cap < bytes) {
+        if (sl.p) cudaFreeHost(sl.p);
+        sl.p = nullptr;
+        sl.cap = 0;
+        size_t want = std::max<size_t>(bytes + bytes / 2, 4096);
+        CS_CUDA(cudaMallocHost(&sl.p, want));
+        sl.cap = want;
+    }
+    if (!sl.done) CS_CUDA(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+    memcpy(sl.p, src, bytes);
+    CS_CUDA(cudaMemcpyAsync(dst, sl.p, bytes, cudaMemcpyHostToDevice, c->stream));
+    CS_CUDA(cudaEventRecord(sl.done, c->stream));
+    sl.used = true;
+    return CS_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -213,6 +330,7 @@ extern "C" int32_t cs_lines_upload(cs_ctx* ctx, int64_t n, const double* nu, con
     CS_REQUIRE(ctx && out, CS_ERR_ARG, "null argument");
     *out = nullptr;
     CS_REQUIRE(n > 0, CS_ERR_ARG, "no lines");
+    CS_REQUIRE(nu && S && ga && gs && Epp && na && mu && iso, CS_ERR_ARG, "null line-parameter array");
     CS_REQUIRE(niso > 0 && ncheb && cheb && hascheb, CS_ERR_ARG, "missing Qref/Q Chebyshev tables");
     for (int64_t j = 1; j < n; j++)
         CS_REQUIRE(nu[j] >= nu[j - 1], CS_ERR_ARG, "line wavenumbers must be sorted ascending (line %lld)", (long long)j);
@@ -249,8 +367,25 @@ extern "C" int32_t cs_lines_upload(cs_ctx* ctx, int64_t n, const double* nu, con
         cs_lines_free(L);
         return rc;
     }
-    CS_CUDA(cudaStreamSynchronize(st));
+    // the caller's arrays are only valid for the duration of the call: wait for the copies
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) {
+        cs_set_error("cs_lines_upload: %s", cudaGetErrorString(e));
+        cs_lines_free(L);
+        return CS_ERR_CUDA;
+    }
     *out = L;
+    return CS_OK;
+}
+
+extern "C" int32_t cs_lines_set_grid_range(cs_lines* L, double numin, double numax)
+{
+    CS_REQUIRE(L, CS_ERR_ARG, "null argument");
+    CS_REQUIRE(numax >= numin, CS_ERR_ARG, "empty wavenumber range");
+    std::lock_guard<std::recursive_mutex> lk(L->ctx->mtx);
+    L->has_range = true;
+    L->rng_lo = numin;
+    L->rng_hi = numax;
     return CS_OK;
 }
 
@@ -299,7 +434,7 @@ extern "C" int32_t cs_count_evals(cs_lines* L, int64_t nnu, const double* nu, do
     CS_REQUIRE(L && nu && evals, CS_ERR_ARG, "null argument");
     CS_TRY(check_nu(nnu, nu));
     const std::vector<double>& ln = L->h_nu;
-    double numin = nu[0], numax = nu[nnu - 1];
+    double numin = L->has_range ? L->rng_lo : nu[0], numax = L->has_range ? L->rng_hi : nu[nnu - 1];
     int64_t j0 = std::upper_bound(ln.begin(), ln.end(), numin - cut) - ln.begin();
     int64_t j1 = std::lower_bound(ln.begin(), ln.end(), numax + cut) - ln.begin();
     int64_t total = 0, lo = j0, hi = j0;

@@ -72,6 +72,7 @@ extern "C" int32_t cs_group_create(int32_t ndev, const int32_t* devices, cs_grou
         g->dev.push_back(devices[i]);
     }
     g->buf.resize((size_t)ndev);
+    for (int i = 0; i < ndev; i++) g->buf[(size_t)i].st = g->ctx[(size_t)i]->stream;
     if (ndev > 1) {
         int32_t rc = load_nccl(g->nccl);
         if (rc) { cs_group_free(g); return rc; }

@@ -57,19 +57,23 @@ void cs_set_error(const char* fmt, ...);
 
 // ------------------------------------------------------------------------------------------------
 // device buffer that only grows (scratch reused across calls: no cudaMalloc in the RCM loop)
+// Stream-ordered (cudaMallocAsync / cudaFreeAsync on the context stream): growing a buffer neither synchronises the
+// device nor races with kernels already enqueued on the old block.
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
+    cudaStream_t st = nullptr;     // the owning context's stream (set at context creation)
     int32_t reserve(size_t bytes)
     {
         if (bytes <= cap) return CS_OK;
-        if (p) cudaFree(p);
+        if (p) cudaFreeAsync(p, st);
         p = nullptr;
         cap = 0;
         size_t want = bytes + bytes / 8 + 256;
-        cudaError_t e = cudaMalloc(&p, want);
+        cudaError_t e = cudaMallocAsync(&p, want, st);
         if (e != cudaSuccess) {
-            cs_set_error("cudaMalloc(%zu bytes) failed: %s", want, cudaGetErrorString(e));
+            cudaGetLastError();
+            cs_set_error("cudaMallocAsync(%zu bytes) failed: %s", want, cudaGetErrorString(e));
             p = nullptr;
             return CS_ERR_NOMEM;
         }
@@ -78,12 +82,32 @@ struct DevBuf {
     }
     void release()
     {
-        if (p) cudaFree(p);
+        if (p) cudaFreeAsync(p, st);
         p = nullptr;
         cap = 0;
     }
     template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
 };
+
+// one timed span on the context stream: two recorded events whose elapsed time is read LAZILY (cs_spans_collect), so that
+// no compute entry point has to block the host just to fill a timer
+struct TimerSpan {
+    cudaEvent_t a, b;
+    int id;
+    bool assign;   // true: last_kernel_ms[id] = ms ("the last call"), false: += ms
+    bool closed;   // end event recorded
+};
+
+// pinned host staging slot for small host->device parameter blocks (level parameters, per-level tables): the copy is
+// asynchronous with respect to the host, the slot is reused only after its copy has executed
+struct StageSlot {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaEvent_t done = nullptr;
+    bool used = false;
+};
+constexpr int CS_NSTAGE = 16;
+constexpr size_t CS_STAGE_MAX = (size_t)1 << 20;   // larger blocks are copied straight from the caller's buffer
 
 struct cs_ctx {
     int device = 0;
@@ -94,9 +118,16 @@ struct cs_ctx {
     // scratch
     DevBuf s_nu, s_lev, s_rec, s_slow, s_sigma, s_misc, s_part, s_tau, s_planck, s_out0, s_out1, s_out2;
     DevBuf s_w;
-    // kernel timing of the last call (ms), measured with CUDA events on ctx->stream
+    // kernel timing (ms), measured with CUDA events on ctx->stream and read lazily
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
-    double last_kernel_ms[CS_NTIMERS] = {0};
+    std::vector<TimerSpan> spans;          // recorded, not yet read
+    std::vector<cudaEvent_t> ev_free;      // recycled events
+    double last_kernel_ms[CS_NTIMERS] = {0};    // timers of the most recent call (cs_ctx_timers)
+    double total_kernel_ms[CS_NTIMERS] = {0};   // never reset (cs_ctx_timers_total)
+    StageSlot stage[CS_NSTAGE];
+    int stage_next = 0;
+    bool ff_no_moments = false;            // CS_FARFIELD_NO_MOMENTS, read once at context creation
+    bool table_no_mma = false;             // CS_TABLE_EVAL_NO_MMA, likewise
     int64_t launches = 0;   // number of kernels of this library launched on this context
     int32_t farfield = CS_FARFIELD_DIRECT;   // K2 far-wing treatment (cs_ctx_set_farfield)
     double tau_floor = 1e-6;                 // K6 floor on the vertical layer depth (cs_ctx_set_tau_floor)
@@ -114,6 +145,10 @@ struct cs_lines {
     std::vector<double> h_nu;  // host copy of line positions (window searches, eval counting)
     double mu_min;             // lightest isotopologue present (bounds the Doppler width)
     double g_max, na_min, na_max;   // max(gamma_a, gamma_s) and the range of the temperature exponent (bound gamma per level)
+    // nu-sharded runs: first/last point of the GLOBAL grid, so that the strict includedlines prefilter
+    // (line_shapes.jl:18-22) is applied to the grid the reference would see, not to a slice of it
+    bool has_range = false;
+    double rng_lo = 0.0, rng_hi = 0.0;
 };
 
 struct cs_sigma {
@@ -311,6 +346,13 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_
 
 // internal entry points implemented across the .cu files
 void cs_reset_timers(cs_ctx* c);
+// lazy timers: cs_span_begin records the start event and returns the span index, cs_span_end the end event;
+// cs_spans_collect folds finished spans into the timer arrays (block = wait for all of them)
+int cs_span_begin(cs_ctx* c, int id, bool assign);
+void cs_span_end(cs_ctx* c, int span);
+void cs_spans_collect(cs_ctx* c, bool block);
+// asynchronous host->device copy of a small parameter block through the context's pinned staging ring
+int32_t cs_stage_h2d(cs_ctx* c, void* dst, const void* src, size_t bytes);
 int32_t cs_lines_accumulate(cs_lines* L, int32_t shape, int64_t nnu, const double* d_nu,
                             const double* h_nu, int64_t nlev, const double* h_T, const double* h_P,
                             const double* h_Pp, const double* h_scale, double cut, double* d_out,

@@ -1165,8 +1165,7 @@ template <int SHAPE, int R> int32_t launch_line_sum(cs_ctx* ctx, LineSumArgs a, 
     auto al256 = [](size_t b) { return ((b + 255) / 256) * 256; };
     const size_t off = al256(sizeof(int64_t) * a.nr * (size_t)a.ntiles);
     const bool want_chix = SHAPE == CS_PHCO2 && a.mp_theta > 0.0 && a.nl > 0 && 0.0232 * 0.5 * (a.nul_hi - a.nul_lo) < 600.0;
-    const bool want_ff = (SHAPE == CS_VOIGT || SHAPE == CS_LORENTZ) && a.mp_theta > 0.0 && a.nl > 0 &&
-                         getenv("CS_FARFIELD_NO_MOMENTS") == nullptr;
+    const bool want_ff = (SHAPE == CS_VOIGT || SHAPE == CS_LORENTZ) && a.mp_theta > 0.0 && a.nl > 0 && !ctx->ff_no_moments;
     const int64_t ncl = a.nl / 32;
     const size_t off_ffc = off + al256(sizeof(double) * FF_REC * (size_t)ncl * nlev);
     const size_t total = want_chix ? off + sizeof(double2) * (size_t)a.nl
@@ -1287,8 +1286,10 @@ int32_t cs_lines_accumulate(cs_lines* L, int32_t shape, int64_t nnu, const doubl
         CS_REQUIRE(h_T[k] >= CS_TMIN && h_T[k] <= CS_TMAX, CS_ERR_DOMAIN,
                    "temperature outside of Qref/Q interpolation range [%g, %g]: T = %g", CS_TMIN, CS_TMAX, h_T[k]);
     }
-    // includedlines(nu::Vector, ...) strict prefilter (line_shapes.jl:18-22)
-    double numin = h_nu[0], numax = h_nu[nnu - 1];
+    // includedlines(nu::Vector, ...) strict prefilter (line_shapes.jl:18-22) on the grid the reference would see: the
+    // caller's own grid, or the global one a nu slice belongs to (cs_lines_set_grid_range) -- interior slice edges are
+    // then decided by the inclusive per-point rule alone, exactly like in the unsharded run
+    double numin = L->has_range ? L->rng_lo : h_nu[0], numax = L->has_range ? L->rng_hi : h_nu[nnu - 1];
     const std::vector<double>& ln = L->h_nu;
     int64_t j0 = std::upper_bound(ln.begin(), ln.end(), numin - cut) - ln.begin();     // first nul > numin-cut
     int64_t j1 = std::lower_bound(ln.begin(), ln.end(), numax + cut) - ln.begin();     // first nul >= numax+cut
@@ -1316,7 +1317,6 @@ int32_t cs_lines_accumulate(cs_lines* L, int32_t shape, int64_t nnu, const doubl
     CS_TRY(ctx->s_lev.reserve(sizeof(LevelParams) * (size_t)nb));
 
     std::vector<LevelParams> hl((size_t)nb);
-    float ms;
     for (int64_t k0 = 0; k0 < nlev; k0 += nb) {
         int64_t kb = std::min(nb, nlev - k0);
         for (int64_t k = 0; k < kb; k++) {
@@ -1345,9 +1345,8 @@ int32_t cs_lines_accumulate(cs_lines* L, int32_t shape, int64_t nnu, const doubl
                 lp.pexp_ok = (e * e < 1e-4) ? 1.0 : 0.0;
             }
         }
-        // pageable H2D of a few KB; synchronous with respect to the host buffer
-        CS_CUDA(cudaMemcpyAsync(ctx->s_lev.p, hl.data(), sizeof(LevelParams) * (size_t)kb, cudaMemcpyHostToDevice, st));
-        CS_CUDA(cudaStreamSynchronize(st));
+        // a few KB through the pinned staging ring: no host synchronisation
+        CS_TRY(cs_stage_h2d(ctx, ctx->s_lev.p, hl.data(), sizeof(LevelParams) * (size_t)kb));
 
         PrepArgs pa;
         pa.nu = L->nu; pa.S = L->S; pa.ga = L->ga; pa.gs = L->gs; pa.Epp = L->Epp; pa.na = L->na; pa.mu = L->mu;
@@ -1356,12 +1355,13 @@ int32_t cs_lines_accumulate(cs_lines* L, int32_t shape, int64_t nnu, const doubl
         pa.rec = ctx->s_rec.as<double4>();
         pa.slow = need_slow ? ctx->s_slow.as<double4>() : nullptr;
         pa.shape = shape;
-        CS_CUDA(cudaEventRecord(ctx->ev0, st));
+        const int sp_prep = cs_span_begin(ctx, CS_T_PREP, false);
         dim3 pg((unsigned)((nl + 255) / 256), (unsigned)kb);
         prep_kernel<<<pg, 256, 0, st>>>(pa);
         CS_CUDA(cudaGetLastError());
         cs_count_launch(ctx);
-        CS_CUDA(cudaEventRecord(ctx->ev1, st));
+        cs_span_end(ctx, sp_prep);
+        const int sp_sum = cs_span_begin(ctx, CS_T_LINESUM, false);
 
         LineSumArgs la;
         la.nu = d_nu; la.nnu = nnu; la.nul = L->nu + j0; la.nl = nl;
@@ -1377,12 +1377,8 @@ int32_t cs_lines_accumulate(cs_lines* L, int32_t shape, int64_t nnu, const doubl
         case CS_VOIGT:   CS_TRY((launch_line_sum<CS_VOIGT, 4>(ctx, la, (int)kb, cn))); break;
         default:         CS_TRY((launch_line_sum<CS_PHCO2, 4>(ctx, la, (int)kb, cn))); break;
         }
-        CS_CUDA(cudaEventRecord(ctx->ev2, st));
-        CS_CUDA(cudaEventSynchronize(ctx->ev2));
-        CS_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
-        ctx->last_kernel_ms[CS_T_PREP] += ms;
-        CS_CUDA(cudaEventElapsedTime(&ms, ctx->ev1, ctx->ev2));
-        ctx->last_kernel_ms[CS_T_LINESUM] += ms;
+        cs_span_end(ctx, sp_sum);
     }
+    cs_spans_collect(ctx, false);
     return CS_OK;
 }

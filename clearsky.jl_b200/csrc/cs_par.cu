@@ -166,14 +166,14 @@ extern "C" int32_t cs_par_parse(cs_ctx* ctx, int64_t nbytes, const char* text, i
     a.na = d + 6 * nrec; a.da = d + 7 * nrec;
     a.M = (int16_t*)(base + off_i); a.I = a.M + nrec;
     a.flags = (uint8_t*)(base + off_f);
-    CS_CUDA(cudaEventRecord(ctx->ev0, st));
+    const int sp_parse = cs_span_begin(ctx, CS_T_TOTAL, true);     // parse kernel time (ms)
     int64_t nblk = (nrec + PAR_WARPS * 32 - 1) / (PAR_WARPS * 32);
     // the text buffer is padded to a multiple of 256 bytes, so the last aligned 16-byte load stays inside it
     size_t smem = (size_t)PAR_WARPS * ((((size_t)32 * reclen + 16 + 15) & ~(size_t)15));
     par_parse_kernel<<<(unsigned)nblk, PAR_WARPS * 32, smem, st>>>(a);
     CS_CUDA(cudaGetLastError());
     cs_count_launch(ctx);
-    CS_CUDA(cudaEventRecord(ctx->ev1, st));
+    cs_span_end(ctx, sp_parse);
     double* outs[8] = {nu, S, A, ga, gs, Epp, na, da};
     for (int k = 0; k < 8; k++)
         CS_CUDA(cudaMemcpyAsync(outs[k], d + (size_t)k * nrec, sizeof(double) * (size_t)nrec, cudaMemcpyDeviceToHost, st));
@@ -181,8 +181,6 @@ extern "C" int32_t cs_par_parse(cs_ctx* ctx, int64_t nbytes, const char* text, i
     CS_CUDA(cudaMemcpyAsync(I, a.I, sizeof(int16_t) * (size_t)nrec, cudaMemcpyDeviceToHost, st));
     CS_CUDA(cudaMemcpyAsync(flags, a.flags, (size_t)nrec, cudaMemcpyDeviceToHost, st));
     CS_CUDA(cudaStreamSynchronize(st));
-    float ms;
-    CS_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
-    ctx->last_kernel_ms[CS_T_TOTAL] = ms;     // parse kernel time (ms)
+    cs_spans_collect(ctx, false);
     return CS_OK;
 }

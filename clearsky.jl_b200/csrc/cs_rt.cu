@@ -452,7 +452,7 @@ int32_t fluxes_impl(cs_sigma* s, int64_t np, const double* P, int32_t nlob, cons
     size_t total = off_F + sizeof(double) * 2 * (size_t)np;
     CS_TRY(ctx->s_misc.reserve(total));
     char* base = ctx->s_misc.as<char>();
-    CS_CUDA(cudaMemcpyAsync(base + off_small, small.data(), small.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    CS_TRY(cs_stage_h2d(ctx, base + off_small, small.data(), small.size() * sizeof(double)));
     if (wsrc) CS_CUDA(cudaMemcpyAsync(base + off_w, wsrc, sizeof(double) * (size_t)nnu, cudaMemcpyHostToDevice, st));
     if (fS) CS_CUDA(cudaMemcpyAsync(base + off_fS, fS, sizeof(double) * (size_t)nnu, cudaMemcpyHostToDevice, st));
     if (fa) CS_CUDA(cudaMemcpyAsync(base + off_fa, fa, sizeof(double) * (size_t)nnu, cudaMemcpyHostToDevice, st));
@@ -480,7 +480,7 @@ int32_t fluxes_impl(cs_sigma* s, int64_t np, const double* P, int32_t nlob, cons
     size_t smem = sizeof(double) * (small.size() + (size_t)2 * np * RT_WARPS);
     CS_REQUIRE(smem <= 200 * 1024, CS_ERR_ARG, "too many pressure levels for one flux call (%lld): per-CTA tables need %zu bytes", (long long)np, smem);
 
-    CS_CUDA(cudaEventRecord(ctx->ev0, st));
+    const int sp_rt = cs_span_begin(ctx, CS_T_RT, true);
     switch (nstream) {
     case 1: CS_TRY(launch_rt<1>(ctx, a, nblocks, smem)); break;
     case 2: CS_TRY(launch_rt<2>(ctx, a, nblocks, smem)); break;
@@ -492,25 +492,26 @@ int32_t fluxes_impl(cs_sigma* s, int64_t np, const double* P, int32_t nlob, cons
     case 8: CS_TRY(launch_rt<8>(ctx, a, nblocks, smem)); break;
     default: CS_TRY(launch_rt<0>(ctx, a, nblocks, smem)); break;
     }
-    CS_CUDA(cudaEventRecord(ctx->ev1, st));
+    cs_span_end(ctx, sp_rt);
+    const int sp_red = cs_span_begin(ctx, CS_T_REDUCE, true);
     double* dF = d_F ? d_F : (double*)(base + off_F);
     flux_reduce_kernel<<<(2 * (int)np + 3) / 4, 128, 0, st>>>(a.part, nblocks, 2 * (int)np, dF);
     CS_CUDA(cudaGetLastError());
     cs_count_launch(ctx);
-    CS_CUDA(cudaEventRecord(ctx->ev2, st));
+    cs_span_end(ctx, sp_red);
 
-    std::vector<double> F(2 * (size_t)np);
-    if (h_F) CS_CUDA(cudaMemcpyAsync(F.data(), dF, sizeof(double) * 2 * (size_t)np, cudaMemcpyDeviceToHost, st));
+    if (!h_F && !tau && !Mup && !Mdn) {
+        // device-side result only (cs_fluxes_device): nothing to wait for -- the caller's collective or read-back is
+        // stream-ordered behind the reduction
+        cs_spans_collect(ctx, false);
+        return CS_OK;
+    }
+    if (h_F) CS_CUDA(cudaMemcpyAsync(h_F, dF, sizeof(double) * 2 * (size_t)np, cudaMemcpyDeviceToHost, st));
     if (tau) CS_CUDA(cudaMemcpyAsync(tau, a.tau_out, sizeof(double) * (size_t)L * nnu, cudaMemcpyDeviceToHost, st));
     if (Mup) CS_CUDA(cudaMemcpyAsync(Mup, a.Mup_out, sizeof(double) * (size_t)np * nnu, cudaMemcpyDeviceToHost, st));
     if (Mdn) CS_CUDA(cudaMemcpyAsync(Mdn, a.Mdn_out, sizeof(double) * (size_t)np * nnu, cudaMemcpyDeviceToHost, st));
     CS_CUDA(cudaStreamSynchronize(st));
-    float ms;
-    CS_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
-    ctx->last_kernel_ms[CS_T_RT] = ms;
-    CS_CUDA(cudaEventElapsedTime(&ms, ctx->ev1, ctx->ev2));
-    ctx->last_kernel_ms[CS_T_REDUCE] = ms;
-    if (h_F) std::copy(F.begin(), F.end(), h_F);
+    cs_spans_collect(ctx, false);
     return CS_OK;
 }
 
@@ -582,11 +583,11 @@ extern "C" int32_t cs_fluxes_batch(cs_sigma* s, int64_t np, const double* P, int
     const size_t off_F = off_kT + al(rkT.size() * sizeof(double));
     CS_TRY(ctx->s_misc.reserve(off_F + sizeof(double) * 2 * (size_t)np * RTB_NB));
     char* base = ctx->s_misc.as<char>();
-    CS_CUDA(cudaMemcpyAsync(base, small.data(), small.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    CS_TRY(cs_stage_h2d(ctx, base, small.data(), small.size() * sizeof(double)));
     if (nu_weights) CS_CUDA(cudaMemcpyAsync(base + off_w, nu_weights, sizeof(double) * (size_t)nnu, cudaMemcpyHostToDevice, st));
     if (fS) CS_CUDA(cudaMemcpyAsync(base + off_fS, fS, sizeof(double) * (size_t)nnu, cudaMemcpyHostToDevice, st));
     if (fa) CS_CUDA(cudaMemcpyAsync(base + off_fa, fa, sizeof(double) * (size_t)nnu, cudaMemcpyHostToDevice, st));
-    CS_CUDA(cudaMemcpyAsync(base + off_kT, rkT.data(), rkT.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    CS_TRY(cs_stage_h2d(ctx, base + off_kT, rkT.data(), rkT.size() * sizeof(double)));
     CS_TRY(ctx->s_tau.reserve(sizeof(double) * (size_t)L * nnu));
     CS_TRY(ctx->s_planck.reserve(sizeof(double) * (size_t)RTB_NB * np * nnu));
     CS_TRY(ctx->s_part.reserve(sizeof(double) * (size_t)nblocks * RTB_NB * 2 * np));
@@ -610,7 +611,7 @@ extern "C" int32_t cs_fluxes_batch(cs_sigma* s, int64_t np, const double* P, int
                (long long)np, smem);
     CS_CUDA(cudaFuncSetAttribute(rt_batch_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CS_CUDA(cudaFuncSetAttribute(rt_batch_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CS_CUDA(cudaEventRecord(ctx->ev0, st));
+    const int sp_rt = cs_span_begin(ctx, CS_T_RT, true);
     double* dF = (double*)(base + off_F);
     for (int64_t b0 = 0; b0 < nbatch; b0 += RTB_NB) {
         ba.nb = (int)std::min<int64_t>(RTB_NB, nbatch - b0);
@@ -625,11 +626,8 @@ extern "C" int32_t cs_fluxes_batch(cs_sigma* s, int64_t np, const double* P, int
         CS_CUDA(cudaMemcpyAsync(F + (size_t)b0 * 2 * np, dF, sizeof(double) * (size_t)n2, cudaMemcpyDeviceToHost, st));
         CS_CUDA(cudaStreamSynchronize(st));       // dF and the scratch are reused by the next chunk
     }
-    CS_CUDA(cudaEventRecord(ctx->ev1, st));
-    CS_CUDA(cudaEventSynchronize(ctx->ev1));
-    float ms;
-    CS_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
-    ctx->last_kernel_ms[CS_T_RT] = ms;
+    cs_span_end(ctx, sp_rt);
+    cs_spans_collect(ctx, false);
     return CS_OK;
 }
 
@@ -651,7 +649,7 @@ extern "C" int32_t cs_opticaldepth(cs_sigma* s, int64_t np, const double* P, int
     size_t off_out = ((small.size() * sizeof(double) + 255) / 256) * 256;
     CS_TRY(ctx->s_misc.reserve(off_out + sizeof(double) * (size_t)s->nnu));
     char* base = ctx->s_misc.as<char>();
-    CS_CUDA(cudaMemcpyAsync(base, small.data(), small.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    CS_TRY(cs_stage_h2d(ctx, base, small.data(), small.size() * sizeof(double)));
     int nblocks = (int)((s->nnu + RT_THREADS - 1) / RT_THREADS);
     const size_t dsm = small.size() * sizeof(double);
     CS_REQUIRE(dsm <= 200 * 1024, CS_ERR_ARG, "too many pressure levels for one optical-depth call (%lld): per-CTA tables need %zu bytes",
@@ -663,5 +661,635 @@ extern "C" int32_t cs_opticaldepth(cs_sigma* s, int64_t np, const double* P, int
     cs_count_launch(ctx);
     CS_CUDA(cudaMemcpyAsync(tau_total, base + off_out, sizeof(double) * (size_t)s->nnu, cudaMemcpyDeviceToHost, st));
     CS_CUDA(cudaStreamSynchronize(st));
+    return CS_OK;
+}
+
+// ================================================================================================
+// Device-resident radiative-convective loop.
+//
+// Replaces the per-step body of the reference's RCM (src/radiative_convective.jl): heating! :109-144 = radiate! on the
+// radiative levels Pr with the AcceleratedAbsorber, Fnet interpolated to the cell edges (:123-124), cell and surface
+// heating rates (:129-140); step! :147-151 = T += dt*H.  The reference never calls update!(A, T) inside heating!, so
+// Sigma -- an AcceleratedAbsorber ignores T (absorbers.jl:203) -- is the same at every step, and with it every layer
+// optical depth, every stream transmittance exp(-tau*m_k) and the whole stellar beam.  cs_rcm_create computes those once
+// (rcm_static_kernel); a step then only evaluates Planck at the new level temperatures and runs the stream recurrences
+// on stored transmittances (rcm_rt_kernel: HBM-bound, (NS+1) doubles per (layer, nu) and sweep, instead of
+// (2 NS + 1) exponentials per (layer, nu)), reduces spectrally (flux_reduce_kernel) and updates the column
+// (rcm_update_kernel).  The three kernels of a step are captured in ONE CUDA graph; the host sees the temperatures only
+// when it asks (cs_rcm_state).
+namespace {
+
+struct RcmStaticArgs {
+    const double* sig;     // [nnode][nnu]
+    const double* w;       // [nnu]
+    const double* fS;      // [nnu] or null
+    const double* small;   // packed: P[np], mu[nlob*(np-1)], wl[nlob], m[ns]
+    int64_t nnu;
+    int np, nlob, ns;
+    double Cg, cos_s, tau_floor;
+    double* tau;           // [np-1][nnu]
+    double* tr;            // [np-1][ns][nnu]
+    double* beam_surf;     // [nnu] stellar beam at the surface (or null)
+    double* part;          // [nblocks][np] partial sums of w*beam per level (or null)
+};
+
+__global__ void __launch_bounds__(RT_THREADS) rcm_static_kernel(RcmStaticArgs a)
+{
+    extern __shared__ double sm[];
+    const int np = a.np, L = np - 1, nlob = a.nlob, ns = a.ns;
+    const int nsmall = np + nlob * L + nlob + ns;
+    double* sP = sm;
+    double* smu = sP + np;
+    double* swl = smu + nlob * L;
+    double* sm_m = swl + nlob;
+    double* red = sm + nsmall;      // [np][RT_WARPS]
+    for (int t = threadIdx.x; t < nsmall; t += RT_THREADS) sm[t] = a.small[t];
+    for (int t = threadIdx.x; t < np * RT_WARPS; t += RT_THREADS) red[t] = 0.0;
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t jraw = (int64_t)blockIdx.x * RT_THREADS + threadIdx.x;
+    const bool live = jraw < a.nnu;
+    const int64_t j = live ? jraw : a.nnu - 1;
+    const int64_t nnu = a.nnu;
+    const double wj = live ? a.w[j] : 0.0;
+    const double Cg = a.Cg, rc = 1.0 / a.cos_s;
+    // same operations, in the same order, as the downward loop of rt_kernel (d-depth!, discretized.jl:136-177)
+    double beta1 = Cg * (a.sig[j] / smu[0]);
+    double beam = a.cos_s * (a.fS ? a.fS[j] : 0.0);        // M-[1] = c*fS(nu)   (discretized.jl:299)
+    if (a.part) {
+        double r = warp_sum(wj * beam);
+        if (lane == 0) red[0 * RT_WARPS + warp] += r;
+    }
+    for (int i = 0; i < L; i++) {
+        double dP = sP[i + 1] - sP[i];
+        double ti = 0.0;
+        ti += (dP * swl[0]) * beta1;
+        for (int n = 1; n < nlob - 1; n++) {
+            double bn = Cg * (a.sig[(size_t)(n + (nlob - 1) * i) * nnu + j] / smu[n + nlob * i]);
+            ti += (dP * swl[n]) * bn;
+        }
+        double bn = Cg * (a.sig[(size_t)((nlob - 1) * (i + 1)) * nnu + j] / smu[(nlob - 1) + nlob * i]);
+        ti += (dP * swl[nlob - 1]) * bn;
+        beta1 = bn;
+        double tau = fmax(ti, a.tau_floor);
+        if (live) a.tau[(size_t)i * nnu + j] = tau;
+        for (int k = 0; k < ns; k++) {
+            double tk = tau * sm_m[k];
+            if (live) a.tr[((size_t)i * ns + k) * nnu + j] = exp(-tk);
+        }
+        beam *= exp(-tau * rc);                              // discretized.jl:302
+        if (a.part) {
+            double r = warp_sum(wj * beam);
+            if (lane == 0) red[(i + 1) * RT_WARPS + warp] += r;
+        }
+    }
+    if (a.beam_surf && live) a.beam_surf[j] = beam;
+    if (a.part) {
+        __syncthreads();
+        for (int t = threadIdx.x; t < np; t += RT_THREADS) {
+            double s = 0.0;
+#pragma unroll
+            for (int q = 0; q < RT_WARPS; q++) s += red[t * RT_WARPS + q];
+            a.part[(size_t)blockIdx.x * np + t] = s;
+        }
+    }
+}
+
+struct RcmRtArgs {
+    const double* nu;          // [nnu]
+    const double* w;           // [nnu]
+    const double* fa;          // [nnu] or null
+    const double* beam_surf;   // [nnu] or null
+    const double* tau;         // [L][nnu]
+    const double* tr;          // [L][ns][nnu]
+    const double* rkT;         // [np] 1/(k T) at the radiative levels (device, rewritten every step)
+    const double* stream;      // W[ns], 1/m[ns]
+    int64_t nnu;
+    int np, ns;
+    double* B_s;               // scratch [np][nnu]
+    double* part;              // [nblocks][2][np]
+};
+
+template <int NS>
+__global__ void __launch_bounds__(RT_THREADS) rcm_rt_kernel(RcmRtArgs a)
+{
+    extern __shared__ double sm[];
+    const int np = a.np, L = np - 1;
+    const int ns = (NS > 0) ? NS : a.ns;
+    double* skT = sm;                    // [np]
+    double* sW = skT + np;               // [ns]
+    double* srm = sW + ns;               // [ns]
+    double* red = srm + ns;              // [2][np][RT_WARPS]
+    for (int t = threadIdx.x; t < np; t += RT_THREADS) skT[t] = a.rkT[t];
+    for (int t = threadIdx.x; t < 2 * ns; t += RT_THREADS) sW[t] = a.stream[t];
+    for (int t = threadIdx.x; t < 2 * np * RT_WARPS; t += RT_THREADS) red[t] = 0.0;
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t jraw = (int64_t)blockIdx.x * RT_THREADS + threadIdx.x;
+    const bool live = jraw < a.nnu;
+    const int64_t j = live ? jraw : a.nnu - 1;
+    const int64_t nnu = a.nnu;
+    const double wj = live ? a.w[j] : 0.0;
+    const double nuj = a.nu[j];
+    const double num = 100.0 * nuj;
+    const double hcn = CS_H * CS_C * num;
+    const double pref = 2 * CS_H * (CS_C * CS_C) * (num * num * num);
+    constexpr int NSMAX = (NS > 0) ? NS : CS_MAX_STREAMS;
+    double I[NSMAX], tk[NSMAX], tn[NSMAX];
+#pragma unroll
+    for (int k = 0; k < NSMAX; k++) I[k] = 0.0;
+    // ---- downward (diffuse part; the stellar beam is static and added by rcm_update_kernel)
+    double Bprev = 100.0 * pref / (exp(hcn * skT[0]) - 1.0);
+    a.B_s[j] = Bprev;
+    double tau_n = a.tau[j];
+#pragma unroll
+    for (int k = 0; k < NSMAX; k++) tn[k] = (k < ns) ? a.tr[(size_t)k * nnu + j] : 0.0;
+    double Msum = 0.0;
+    for (int i = 0; i < L; i++) {
+        const double tau = tau_n;
+#pragma unroll
+        for (int k = 0; k < NSMAX; k++) tk[k] = tn[k];
+        if (i + 1 < L) {      // next layer's operands, one iteration ahead
+            tau_n = a.tau[(size_t)(i + 1) * nnu + j];
+#pragma unroll
+            for (int k = 0; k < NSMAX; k++)
+                if (k < ns) tn[k] = a.tr[((size_t)(i + 1) * ns + k) * nnu + j];
+        }
+        const double Bnext = 100.0 * pref / (exp(hcn * skT[i + 1]) - 1.0);
+        a.B_s[(size_t)(i + 1) * nnu + j] = Bnext;
+        const double rtau = cs_rcp(tau);
+        Msum = 0.0;
+#pragma unroll
+        for (int k = 0; k < NSMAX; k++) {
+            if (k < ns) {
+                double Be = layerplanck(Bprev, Bnext, rtau * srm[k], tk[k]);
+                I[k] = I[k] * tk[k] + Be;
+                Msum += sW[k] * I[k];
+            }
+        }
+        double r = warp_sum(wj * Msum);
+        if (lane == 0) red[(np + i + 1) * RT_WARPS + warp] += r;
+        Bprev = Bnext;
+    }
+    // ---- surface (discretized.jl:309-310): M-[end] = diffuse + beam
+    const double Mdn_s = Msum + (a.beam_surf ? a.beam_surf[j] : 0.0);
+    const double Is = Mdn_s * (a.fa ? a.fa[j] : 0.0) / CS_PI + Bprev;
+    {
+        double r = warp_sum(wj * (Is * CS_PI));
+        if (lane == 0) red[L * RT_WARPS + warp] += r;
+    }
+    // ---- upward
+#pragma unroll
+    for (int k = 0; k < NSMAX; k++) I[k] = Is;
+    double B1 = Bprev;
+    tau_n = a.tau[(size_t)(L - 1) * nnu + j];
+    double B_n = a.B_s[(size_t)(L - 1) * nnu + j];
+#pragma unroll
+    for (int k = 0; k < NSMAX; k++) tn[k] = (k < ns) ? a.tr[((size_t)(L - 1) * ns + k) * nnu + j] : 0.0;
+    for (int i = L - 1; i >= 0; i--) {
+        const double tau = tau_n, B2 = B_n;
+#pragma unroll
+        for (int k = 0; k < NSMAX; k++) tk[k] = tn[k];
+        if (i > 0) {
+            tau_n = a.tau[(size_t)(i - 1) * nnu + j];
+            B_n = a.B_s[(size_t)(i - 1) * nnu + j];
+#pragma unroll
+            for (int k = 0; k < NSMAX; k++)
+                if (k < ns) tn[k] = a.tr[((size_t)(i - 1) * ns + k) * nnu + j];
+        }
+        const double rtau = cs_rcp(tau);
+        double Ms = 0.0;
+#pragma unroll
+        for (int k = 0; k < NSMAX; k++) {
+            if (k < ns) {
+                double Be = layerplanck(B1, B2, rtau * srm[k], tk[k]);
+                I[k] = I[k] * tk[k] + Be;
+                Ms += sW[k] * I[k];
+            }
+        }
+        double r = warp_sum(wj * Ms);
+        if (lane == 0) red[i * RT_WARPS + warp] += r;
+        B1 = B2;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < 2 * np; t += RT_THREADS) {
+        double s = 0.0;
+#pragma unroll
+        for (int q = 0; q < RT_WARPS; q++) s += red[t * RT_WARPS + q];
+        a.part[(size_t)blockIdx.x * 2 * np + t] = s;
+    }
+}
+
+// column update: everything of heating!/step! that is O(np) (radiative_convective.jl:123-150), in the reference's
+// operation order and WITHOUT fused multiply-adds (Julia does not contract a*b+c), then the level temperatures of the
+// next step (AtmosphericProfile(P, T) at Pr: linear in ln P with end-cell extrapolation, atmospherics.jl:16-26).
+struct RcmColArgs {
+    int np, nrad;
+    const double* F;         // [2*nrad] spectrally integrated diffuse F+ then F- (all ranks summed)
+    const double* beamF;     // [nrad] static stellar-beam part of F- (all ranks summed) or null
+    const double* lnPr;      // [nrad]
+    const double* lnPe;      // [np]
+    const int* ecell;        // [np] cell of ln Pe in lnPr
+    const double* dPe;       // [np-1] Pe[i+1] - Pe[i]
+    const double* gcp;       // [np-1] g / cp_i
+    double cs_surf;
+    const double* lnP;       // [np] ln of cell-centre pressures (+ surface)
+    const int* rcell;        // [nrad] cell of ln Pr in lnP
+    const double* dt;        // device scalar
+    double* T;               // [np]
+    double* H;               // [np]
+    double* R;               // [np]
+    double* Fout;            // [3*nrad] F+, F-, Fnet of this step (beam included)
+    double* rkT;             // [nrad] 1/(k T(Pr)) for the next step
+    double* Tlev;            // [nrad]
+};
+
+__device__ __forceinline__ double rcm_lin(const double* x, const double* y, int i, double q)
+{
+    // LinearInterpolator: (q - x[i]) * (y[i+1] - y[i]) / (x[i+1] - x[i]) + y[i]
+    return __dadd_rn(__ddiv_rn(__dmul_rn(q - x[i], y[i + 1] - y[i]), x[i + 1] - x[i]), y[i]);
+}
+
+__global__ void __launch_bounds__(256) rcm_update_kernel(RcmColArgs a)
+{
+    extern __shared__ double sm[];
+    double* sFnet = sm;                  // [nrad]
+    double* sR = sFnet + a.nrad;         // [np]
+    double* sT = sR + a.np;              // [np]
+    const int np = a.np, nrad = a.nrad;
+    if (a.F) {
+        for (int r = threadIdx.x; r < nrad; r += blockDim.x) {
+            const double up = a.F[r], dn = a.F[nrad + r] + (a.beamF ? a.beamF[r] : 0.0);
+            const double net = up - dn;                                  // fluxes.jl:380
+            sFnet[r] = net;
+            a.Fout[r] = up; a.Fout[nrad + r] = dn; a.Fout[2 * nrad + r] = net;
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < np; e += blockDim.x) {
+            const double Rn = -rcm_lin(a.lnPr, sFnet, a.ecell[e], a.lnPe[e]);   // R = -fFnet(Pe)  (:124)
+            sR[e] = Rn;
+            a.R[e] = Rn;
+        }
+        __syncthreads();
+        const double dt = *a.dt;
+        for (int i = threadIdx.x; i < np; i += blockDim.x) {
+            double H;
+            if (i < np - 1) H = __ddiv_rn(__dmul_rn(a.gcp[i], sR[i] - sR[i + 1]), a.dPe[i]);   // (g/cp)*dR/dP  (:137)
+            else H = __ddiv_rn(sR[np - 1], a.cs_surf);                                          // (:140)
+            a.H[i] = H;
+            const double Tn = __dadd_rn(a.T[i], __dmul_rn(dt, H));                              // step! (:149)
+            a.T[i] = Tn;
+            sT[i] = Tn;
+        }
+    } else {
+        for (int i = threadIdx.x; i < np; i += blockDim.x) sT[i] = a.T[i];
+    }
+    __syncthreads();
+    for (int r = threadIdx.x; r < nrad; r += blockDim.x) {
+        const double Tl = rcm_lin(a.lnP, sT, a.rcell[r], a.lnPr[r]);
+        a.Tlev[r] = Tl;
+        a.rkT[r] = 1.0 / (CS_KB * Tl);
+    }
+}
+
+int findcell_host(const std::vector<double>& x, double q)
+{
+    const int n = (int)x.size();
+    if (q <= x[0]) return 0;
+    if (q >= x[(size_t)n - 1]) return n - 2;
+    return (int)(std::upper_bound(x.begin(), x.end(), q) - x.begin()) - 1;
+}
+
+}  // namespace
+
+struct cs_rcm {
+    cs_ctx* ctx = nullptr;
+    int64_t nnu = 0;
+    int np = 0, nrad = 0, ns = 0;
+    int nblocks = 0;
+    bool has_beam = false, has_albedo = false;
+    // owned device memory (one allocation each, stream-ordered)
+    double *tau = nullptr, *tr = nullptr, *B_s = nullptr, *part = nullptr, *beam_surf = nullptr, *fa = nullptr;
+    double *nu = nullptr, *w = nullptr;
+    char* col = nullptr;      // packed column block (see offsets below)
+    size_t col_bytes = 0;
+    // pointers into col
+    double *F = nullptr, *beamF = nullptr, *lnPr = nullptr, *lnPe = nullptr, *dPe = nullptr, *gcp = nullptr, *lnP = nullptr;
+    double *dt = nullptr, *T = nullptr, *H = nullptr, *R = nullptr, *Fout = nullptr, *rkT = nullptr, *Tlev = nullptr, *stream = nullptr;
+    int *ecell = nullptr, *rcell = nullptr;
+    double cs_surf = 1.0;
+    double dt_host = -1.0;    // value currently in *dt (graph replays read it from device memory)
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    bool graph_tried = false;
+};
+
+namespace {
+
+template <int NS> int32_t rcm_launch_rt(cs_rcm* r, cudaStream_t st, const RcmRtArgs& a, size_t smem)
+{
+    rcm_rt_kernel<NS><<<r->nblocks, RT_THREADS, smem, st>>>(a);
+    CS_CUDA(cudaGetLastError());
+    return CS_OK;
+}
+
+size_t rcm_rt_smem(const cs_rcm* r) { return sizeof(double) * ((size_t)r->nrad + 2 * r->ns + (size_t)2 * r->nrad * RT_WARPS); }
+
+// partial fluxes of this device: rt + spectral reduction into dF (2*nrad doubles, device)
+int32_t rcm_enqueue_fluxes(cs_rcm* r, double* dF)
+{
+    cs_ctx* ctx = r->ctx;
+    cudaStream_t st = ctx->stream;
+    RcmRtArgs a;
+    a.nu = r->nu; a.w = r->w; a.fa = r->has_albedo ? r->fa : nullptr; a.beam_surf = r->has_beam ? r->beam_surf : nullptr;
+    a.tau = r->tau; a.tr = r->tr; a.rkT = r->rkT; a.stream = r->stream;
+    a.nnu = r->nnu; a.np = r->nrad; a.ns = r->ns; a.B_s = r->B_s; a.part = r->part;
+    const size_t smem = rcm_rt_smem(r);
+    switch (r->ns) {
+    case 3: CS_TRY(rcm_launch_rt<3>(r, st, a, smem)); break;
+    case 4: CS_TRY(rcm_launch_rt<4>(r, st, a, smem)); break;
+    case 5: CS_TRY(rcm_launch_rt<5>(r, st, a, smem)); break;
+    case 6: CS_TRY(rcm_launch_rt<6>(r, st, a, smem)); break;
+    case 8: CS_TRY(rcm_launch_rt<8>(r, st, a, smem)); break;
+    default: CS_TRY(rcm_launch_rt<0>(r, st, a, smem)); break;
+    }
+    flux_reduce_kernel<<<(2 * r->nrad + 3) / 4, 128, 0, st>>>(r->part, r->nblocks, 2 * r->nrad, dF);
+    CS_CUDA(cudaGetLastError());
+    cs_count_launch(ctx, 2);
+    return CS_OK;
+}
+
+// column update from summed fluxes dF (null: only recompute the level temperatures from T)
+int32_t rcm_enqueue_update(cs_rcm* r, const double* dF)
+{
+    cudaStream_t st = r->ctx->stream;
+    RcmColArgs a;
+    a.np = r->np; a.nrad = r->nrad; a.F = dF; a.beamF = r->has_beam ? r->beamF : nullptr;
+    a.lnPr = r->lnPr; a.lnPe = r->lnPe; a.ecell = r->ecell; a.dPe = r->dPe; a.gcp = r->gcp; a.cs_surf = r->cs_surf;
+    a.lnP = r->lnP; a.rcell = r->rcell; a.dt = r->dt; a.T = r->T; a.H = r->H; a.R = r->R; a.Fout = r->Fout;
+    a.rkT = r->rkT; a.Tlev = r->Tlev;
+    const size_t smem = sizeof(double) * ((size_t)r->nrad + 2 * (size_t)r->np);
+    rcm_update_kernel<<<1, 256, smem, st>>>(a);
+    CS_CUDA(cudaGetLastError());
+    cs_count_launch(r->ctx, 1);
+    return CS_OK;
+}
+
+int32_t rcm_set_dt(cs_rcm* r, double dt)
+{
+    if (dt == r->dt_host) return CS_OK;
+    CS_TRY(cs_stage_h2d(r->ctx, r->dt, &dt, sizeof(double)));
+    r->dt_host = dt;
+    return CS_OK;
+}
+
+}  // namespace
+
+extern "C" int32_t cs_rcm_free(cs_rcm* r)
+{
+    if (!r) return CS_OK;
+    cudaSetDevice(r->ctx->device);
+    cudaStream_t st = r->ctx->stream;
+    if (r->exec) cudaGraphExecDestroy(r->exec);
+    if (r->graph) cudaGraphDestroy(r->graph);
+    cs_free(r->tau, st); cs_free(r->tr, st); cs_free(r->B_s, st); cs_free(r->part, st); cs_free(r->beam_surf, st);
+    cs_free(r->fa, st); cs_free(r->nu, st); cs_free(r->w, st); cs_free(r->col, st);
+    delete r;
+    return CS_OK;
+}
+
+extern "C" int32_t cs_rcm_create(cs_sigma* s, int64_t np, const double* Pe, const double* P, const double* T0,
+                                 const double* cp, double c_surf, int64_t nrad, const double* Pr, int32_t nlob,
+                                 const double* wlob, const double* mu, double g, const double* fS, const double* fa,
+                                 double theta_s, int32_t nstream, const double* m, const double* W,
+                                 const double* nu_weights, cs_rcm** out)
+{
+    CS_REQUIRE(s && Pe && P && T0 && cp && Pr && wlob && mu && m && W && out, CS_ERR_ARG, "null argument");
+    *out = nullptr;
+    CS_REQUIRE(np >= 2 && nrad >= 2, CS_ERR_ARG, "need at least two cells and two radiative levels");
+    CS_TRY(check_profile_args(s, nrad, Pr, nlob));
+    CS_REQUIRE(nstream >= 1 && nstream <= CS_MAX_STREAMS, CS_ERR_ARG, "nstream must be in [1,%d]", CS_MAX_STREAMS);
+    CS_REQUIRE(theta_s >= 0 && theta_s < CS_PI / 2, CS_ERR_ARG, "azimuth angle theta must be in [0,pi/2)");
+    CS_REQUIRE(g > 0 && c_surf > 0, CS_ERR_ARG, "gravity and surface heat capacity must be positive");
+    for (int64_t i = 1; i < np; i++) {
+        CS_REQUIRE(Pe[i] > Pe[i - 1], CS_ERR_ARG, "cell-edge pressures must ascend (radiative_convective.jl:55-57)");
+        CS_REQUIRE(P[i] > P[i - 1], CS_ERR_ARG, "cell-centre pressures must ascend");
+    }
+    for (int64_t i = 1; i < nrad; i++) CS_REQUIRE(Pr[i] > Pr[i - 1], CS_ERR_ARG, "radiative levels must ascend strictly");
+    for (int64_t i = 0; i + 1 < np; i++) CS_REQUIRE(cp[i] > 0, CS_ERR_ARG, "heat capacities must be positive");
+    cs_ctx* ctx = s->ctx;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mtx);
+    CS_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int64_t nnu = s->nnu;
+    const int L = (int)nrad - 1;
+    cs_rcm* r = new cs_rcm();
+    r->ctx = ctx; r->nnu = nnu; r->np = (int)np; r->nrad = (int)nrad; r->ns = nstream;
+    r->nblocks = (int)((nnu + RT_THREADS - 1) / RT_THREADS);
+    r->has_beam = fS != nullptr; r->has_albedo = fa != nullptr;
+    r->cs_surf = c_surf;
+    const size_t smem_rt = rcm_rt_smem(r);
+    if (smem_rt > 200 * 1024) {
+        delete r;
+        cs_set_error("too many radiative levels for the device-resident RCM (%lld)", (long long)nrad);
+        return CS_ERR_ARG;
+    }
+    // ---- packed column block
+    std::vector<double> lnPr((size_t)nrad), lnPe((size_t)np), lnP((size_t)np), dPe((size_t)np - 1), gcp((size_t)np - 1);
+    for (int64_t i = 0; i < nrad; i++) lnPr[(size_t)i] = log(Pr[i]);
+    for (int64_t i = 0; i < np; i++) { lnPe[(size_t)i] = log(Pe[i]); lnP[(size_t)i] = log(P[i]); }
+    for (int64_t i = 0; i + 1 < np; i++) { dPe[(size_t)i] = Pe[i + 1] - Pe[i]; gcp[(size_t)i] = g / cp[i]; }
+    std::vector<int> ecell((size_t)np), rcell((size_t)nrad);
+    for (int64_t i = 0; i < np; i++) ecell[(size_t)i] = findcell_host(lnPr, lnPe[(size_t)i]);
+    for (int64_t i = 0; i < nrad; i++) rcell[(size_t)i] = findcell_host(lnP, lnPr[(size_t)i]);
+    std::vector<double> stream;
+    stream.insert(stream.end(), W, W + nstream);
+    for (int k = 0; k < nstream; k++) stream.push_back(1.0 / m[k]);
+    // layout (doubles): F[2nrad] beamF[nrad] lnPr[nrad] lnPe[np] dPe[np-1] gcp[np-1] lnP[np] dt[1] T[np] H[np] R[np]
+    //                   Fout[3nrad] rkT[nrad] Tlev[nrad] stream[2ns], then ints ecell[np] rcell[nrad]
+    std::vector<double> host;
+    auto put = [&](const double* p, size_t n) { size_t o = host.size(); if (p) host.insert(host.end(), p, p + n); else host.insert(host.end(), n, 0.0); return o; };
+    const size_t oF = put(nullptr, 2 * (size_t)nrad), obF = put(nullptr, (size_t)nrad), olnPr = put(lnPr.data(), (size_t)nrad);
+    const size_t olnPe = put(lnPe.data(), (size_t)np), odPe = put(dPe.data(), (size_t)np - 1), ogcp = put(gcp.data(), (size_t)np - 1);
+    const size_t olnP = put(lnP.data(), (size_t)np), odt = put(nullptr, 1), oT = put(T0, (size_t)np), oH = put(nullptr, (size_t)np);
+    const size_t oR = put(nullptr, (size_t)np), oFout = put(nullptr, 3 * (size_t)nrad), orkT = put(nullptr, (size_t)nrad);
+    const size_t oTlev = put(nullptr, (size_t)nrad), ostream = put(stream.data(), stream.size());
+    const size_t nd = host.size();
+    r->col_bytes = nd * sizeof(double) + sizeof(int) * ((size_t)np + (size_t)nrad);
+    int32_t rc = CS_OK;
+    auto fail = [&](int32_t code) { cs_rcm_free(r); return code; };
+    if (cs_malloc((void**)&r->col, r->col_bytes, st) != cudaSuccess) { cs_set_error("cudaMalloc(RCM column block) failed"); return fail(CS_ERR_NOMEM); }
+    double* cd = (double*)r->col;
+    r->F = cd + oF; r->beamF = cd + obF; r->lnPr = cd + olnPr; r->lnPe = cd + olnPe; r->dPe = cd + odPe; r->gcp = cd + ogcp;
+    r->lnP = cd + olnP; r->dt = cd + odt; r->T = cd + oT; r->H = cd + oH; r->R = cd + oR; r->Fout = cd + oFout;
+    r->rkT = cd + orkT; r->Tlev = cd + oTlev; r->stream = cd + ostream;
+    r->ecell = (int*)(cd + nd); r->rcell = r->ecell + np;
+    if ((rc = cs_stage_h2d(ctx, cd, host.data(), nd * sizeof(double))) || (rc = cs_stage_h2d(ctx, r->ecell, ecell.data(), sizeof(int) * (size_t)np)) ||
+        (rc = cs_stage_h2d(ctx, r->rcell, rcell.data(), sizeof(int) * (size_t)nrad)))
+        return fail(rc);
+    r->dt_host = 0.0;
+    // ---- per-wavenumber arrays
+    const size_t bnu = sizeof(double) * (size_t)nnu;
+    if (cs_malloc((void**)&r->tau, bnu * L, st) != cudaSuccess || cs_malloc((void**)&r->tr, bnu * L * nstream, st) != cudaSuccess ||
+        cs_malloc((void**)&r->B_s, bnu * nrad, st) != cudaSuccess ||
+        cs_malloc((void**)&r->part, sizeof(double) * (size_t)r->nblocks * 2 * nrad, st) != cudaSuccess ||
+        cs_malloc((void**)&r->nu, bnu, st) != cudaSuccess || cs_malloc((void**)&r->w, bnu, st) != cudaSuccess ||
+        (fS && cs_malloc((void**)&r->beam_surf, bnu, st) != cudaSuccess) || (fa && cs_malloc((void**)&r->fa, bnu, st) != cudaSuccess)) {
+        cudaGetLastError();
+        cs_set_error("cudaMalloc(RCM transmittance tables, %zu bytes) failed", bnu * L * (nstream + 1));
+        return fail(CS_ERR_NOMEM);
+    }
+    CS_CUDA(cudaMemcpyAsync(r->nu, s->nu, bnu, cudaMemcpyDeviceToDevice, st));
+    if (nu_weights) CS_CUDA(cudaMemcpyAsync(r->w, nu_weights, bnu, cudaMemcpyHostToDevice, st));
+    else CS_CUDA(cudaMemcpyAsync(r->w, s->w, bnu, cudaMemcpyDeviceToDevice, st));
+    if (fa) CS_CUDA(cudaMemcpyAsync(r->fa, fa, bnu, cudaMemcpyHostToDevice, st));
+    // ---- static pass: optical depths, transmittances, stellar beam
+    {
+        std::vector<double> small;
+        small.insert(small.end(), Pr, Pr + nrad);
+        small.insert(small.end(), mu, mu + (size_t)nlob * L);
+        small.insert(small.end(), wlob, wlob + nlob);
+        small.insert(small.end(), m, m + nstream);
+        auto al = [](size_t b) { return ((b + 255) / 256) * 256; };
+        const size_t off_fS = al(small.size() * sizeof(double));
+        if ((rc = ctx->s_misc.reserve(off_fS + bnu))) return fail(rc);
+        char* base = ctx->s_misc.as<char>();
+        if ((rc = cs_stage_h2d(ctx, base, small.data(), small.size() * sizeof(double)))) return fail(rc);
+        if (fS) CS_CUDA(cudaMemcpyAsync(base + off_fS, fS, bnu, cudaMemcpyHostToDevice, st));
+        RcmStaticArgs a;
+        a.sig = s->sig; a.w = r->w; a.fS = fS ? (const double*)(base + off_fS) : nullptr; a.small = (const double*)base;
+        a.nnu = nnu; a.np = (int)nrad; a.nlob = nlob; a.ns = nstream;
+        a.Cg = 1e-4 * CS_NA / g; a.cos_s = cos(theta_s); a.tau_floor = ctx->tau_floor;
+        a.tau = r->tau; a.tr = r->tr; a.beam_surf = fS ? r->beam_surf : nullptr; a.part = fS ? r->part : nullptr;
+        const size_t smem = sizeof(double) * (small.size() + (size_t)nrad * RT_WARPS);
+        if (smem > 48 * 1024) CS_CUDA(cudaFuncSetAttribute(rcm_static_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        rcm_static_kernel<<<r->nblocks, RT_THREADS, smem, st>>>(a);
+        CS_CUDA(cudaGetLastError());
+        cs_count_launch(ctx, 1);
+        if (fS) {
+            flux_reduce_kernel<<<((int)nrad + 3) / 4, 128, 0, st>>>(r->part, r->nblocks, (int)nrad, r->beamF);
+            CS_CUDA(cudaGetLastError());
+            cs_count_launch(ctx, 1);
+        }
+    }
+    if (smem_rt > 48 * 1024) {
+        CS_CUDA(cudaFuncSetAttribute(rcm_rt_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rt));
+        CS_CUDA(cudaFuncSetAttribute(rcm_rt_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rt));
+        CS_CUDA(cudaFuncSetAttribute(rcm_rt_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rt));
+        CS_CUDA(cudaFuncSetAttribute(rcm_rt_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rt));
+        CS_CUDA(cudaFuncSetAttribute(rcm_rt_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rt));
+        CS_CUDA(cudaFuncSetAttribute(rcm_rt_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rt));
+    }
+    // level temperatures of the first step
+    if ((rc = rcm_enqueue_update(r, nullptr))) return fail(rc);
+    cudaError_t e = cudaStreamSynchronize(st);      // the caller's host arrays are only valid during the call
+    if (e != cudaSuccess) { cs_set_error("cs_rcm_create: %s", cudaGetErrorString(e)); return fail(CS_ERR_CUDA); }
+    *out = r;
+    return CS_OK;
+}
+
+extern "C" int32_t cs_rcm_enqueue_fluxes(cs_rcm* r, double* d_F)
+{
+    CS_REQUIRE(r, CS_ERR_ARG, "null argument");
+    std::lock_guard<std::recursive_mutex> lk(r->ctx->mtx);
+    CS_CUDA(cudaSetDevice(r->ctx->device));
+    return rcm_enqueue_fluxes(r, d_F ? d_F : r->F);
+}
+
+extern "C" int32_t cs_rcm_enqueue_update(cs_rcm* r, const double* d_F, double dt)
+{
+    CS_REQUIRE(r, CS_ERR_ARG, "null argument");
+    std::lock_guard<std::recursive_mutex> lk(r->ctx->mtx);
+    CS_CUDA(cudaSetDevice(r->ctx->device));
+    CS_TRY(rcm_set_dt(r, dt));
+    return rcm_enqueue_update(r, d_F ? d_F : r->F);
+}
+
+extern "C" int32_t cs_rcm_step(cs_rcm* r, double dt, int64_t nsteps)
+{
+    CS_REQUIRE(r && nsteps >= 0, CS_ERR_ARG, "bad arguments");
+    cs_ctx* ctx = r->ctx;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mtx);
+    CS_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    CS_TRY(rcm_set_dt(r, dt));
+    if (!r->graph_tried) {
+        // one step = rt + spectral reduction + column update, captured once; dt is read from device memory so the same
+        // executable graph serves every time step
+        r->graph_tried = true;
+        const int64_t l0 = ctx->launches;
+        if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            int32_t rc = rcm_enqueue_fluxes(r, r->F);
+            if (!rc) rc = rcm_enqueue_update(r, r->F);
+            cudaGraph_t gph = nullptr;
+            cudaError_t e = cudaStreamEndCapture(st, &gph);
+            if (!rc && e == cudaSuccess && gph && cudaGraphInstantiate(&r->exec, gph, 0) == cudaSuccess) {
+                r->graph = gph;
+            } else {
+                if (gph) cudaGraphDestroy(gph);
+                r->exec = nullptr;
+                cudaGetLastError();
+            }
+        } else {
+            cudaGetLastError();
+        }
+        ctx->launches = l0;      // capturing launched nothing
+    }
+    const int sp = cs_span_begin(ctx, CS_T_RT, true);
+    for (int64_t k = 0; k < nsteps; k++) {
+        if (r->exec) {
+            CS_CUDA(cudaGraphLaunch(r->exec, st));
+            cs_count_launch(ctx, 3);
+        } else {
+            CS_TRY(rcm_enqueue_fluxes(r, r->F));
+            CS_TRY(rcm_enqueue_update(r, r->F));
+        }
+    }
+    cs_span_end(ctx, sp);
+    CS_CUDA(cudaStreamSynchronize(st));
+    cs_spans_collect(ctx, false);
+    return CS_OK;
+}
+
+extern "C" int32_t cs_rcm_set_temperature(cs_rcm* r, const double* T)
+{
+    CS_REQUIRE(r && T, CS_ERR_ARG, "null argument");
+    cs_ctx* ctx = r->ctx;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mtx);
+    CS_CUDA(cudaSetDevice(ctx->device));
+    CS_TRY(cs_stage_h2d(ctx, r->T, T, sizeof(double) * (size_t)r->np));
+    CS_TRY(rcm_enqueue_update(r, nullptr));
+    return CS_OK;
+}
+
+extern "C" int32_t cs_rcm_state(cs_rcm* r, double* T, double* H, double* R, double* Fup, double* Fdn, double* Fnet)
+{
+    CS_REQUIRE(r, CS_ERR_ARG, "null argument");
+    cs_ctx* ctx = r->ctx;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mtx);
+    CS_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const size_t bn = sizeof(double) * (size_t)r->np, br = sizeof(double) * (size_t)r->nrad;
+    if (T) CS_CUDA(cudaMemcpyAsync(T, r->T, bn, cudaMemcpyDeviceToHost, st));
+    if (H) CS_CUDA(cudaMemcpyAsync(H, r->H, bn, cudaMemcpyDeviceToHost, st));
+    if (R) CS_CUDA(cudaMemcpyAsync(R, r->R, bn, cudaMemcpyDeviceToHost, st));
+    if (Fup) CS_CUDA(cudaMemcpyAsync(Fup, r->Fout, br, cudaMemcpyDeviceToHost, st));
+    if (Fdn) CS_CUDA(cudaMemcpyAsync(Fdn, r->Fout + r->nrad, br, cudaMemcpyDeviceToHost, st));
+    if (Fnet) CS_CUDA(cudaMemcpyAsync(Fnet, r->Fout + 2 * r->nrad, br, cudaMemcpyDeviceToHost, st));
+    CS_CUDA(cudaStreamSynchronize(st));
+    return CS_OK;
+}
+
+extern "C" int32_t cs_rcm_ctx(cs_rcm* r, cs_ctx** ctx)
+{
+    CS_REQUIRE(r && ctx, CS_ERR_ARG, "null argument");
+    *ctx = r->ctx;
+    return CS_OK;
+}
+
+extern "C" int32_t cs_rcm_flux_buffer(cs_rcm* r, double** d_F)
+{
+    CS_REQUIRE(r && d_F, CS_ERR_ARG, "null argument");
+    *d_F = r->F;
     return CS_OK;
 }

@@ -493,13 +493,13 @@ int32_t fit_table(cs_ctx* ctx, cs_table* tb, double* d_block)
     CS_CUDA(cudaMemcpyAsync(base + offxt, MxT.data(), MxT.size() * sizeof(double), cudaMemcpyHostToDevice, st));
     CS_CUDA(cudaMemcpyAsync(base + offyt, MyT.data(), MyT.size() * sizeof(double), cudaMemcpyHostToDevice, st));
     CS_CUDA(cudaMemsetAsync(base + offc, 0, 8, st));
-    CS_CUDA(cudaEventRecord(ctx->ev0, st));
+    const int sp_fit = cs_span_begin(ctx, CS_T_TABLE_FIT, false);
     unsigned nb = (unsigned)((nnu + 255) / 256);
     table_log_kernel<<<nb, 256, 0, st>>>(d_block, nnu, nk, (unsigned long long*)(base + offc));
     CS_CUDA(cudaGetLastError());
     // pass along T in place (a thread / CTA reads its whole line of nT rows before it writes any), then the pass along
     // ln P from the block into coef: the block is read twice and written once, coef written once
-    if (nnu % 2 == 0 && getenv("CS_TABLE_EVAL_NO_MMA") == nullptr) {
+    if (nnu % 2 == 0 && !ctx->table_no_mma) {
         // tensor-core passes: per (128-wavenumber tile, index of the other axis) an [128 x n] = [128 x n] . [n x n] product
         const size_t sm2 = sizeof(double) * GM_STAGES * 2 * GM_BK * GM_LD;
         CS_CUDA(cudaFuncSetAttribute(table_eval_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
@@ -522,13 +522,11 @@ int32_t fit_table(cs_ctx* ctx, cs_table* tb, double* d_block)
         CS_CUDA(cudaGetLastError());
     }
     cs_count_launch(ctx, 3);
-    CS_CUDA(cudaEventRecord(ctx->ev1, st));
+    cs_span_end(ctx, sp_fit);
     unsigned long long nz = 0;
     CS_CUDA(cudaMemcpyAsync(&nz, base + offc, 8, cudaMemcpyDeviceToHost, st));
     CS_CUDA(cudaStreamSynchronize(st));
-    float ms;
-    CS_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
-    ctx->last_kernel_ms[CS_T_TABLE_FIT] += ms;
+    cs_spans_collect(ctx, false);
     tb->nzeroed = (int64_t)nz;
     return CS_OK;
 }
@@ -577,15 +575,15 @@ int32_t eval_table(cs_table* tb, int64_t nlev, const double* T, const double* P,
     const int nby = (int)((nlev + 127) / 128);
     const int lpb = (int)((nlev + nby - 1) / nby);
     // the tensor-core kernel needs 16-byte aligned coefficient rows: nnu even (coef itself is 256-byte aligned)
-    const bool mma = (tb->nnu % 2 == 0) && getenv("CS_TABLE_EVAL_NO_MMA") == nullptr;
+    const bool mma = (tb->nnu % 2 == 0) && !ctx->table_no_mma;
     const size_t offP = sizeof(double) * (size_t)nlev * nT;
     const size_t offC = ((basis.size() * sizeof(double) + 255) / 256) * 256;
     const size_t offB = offC + ((sizeof(double) * (size_t)nlev + 255) / 256) * 256;
     CS_TRY(ctx->s_misc.reserve(offB + (mma ? sizeof(double) * (size_t)nby * nk * GM_BN : 0)));
     char* base = ctx->s_misc.as<char>();
-    CS_CUDA(cudaMemcpyAsync(base, basis.data(), basis.size() * sizeof(double), cudaMemcpyHostToDevice, st));
-    if (C) CS_CUDA(cudaMemcpyAsync(base + offC, C, sizeof(double) * (size_t)nlev, cudaMemcpyHostToDevice, st));
-    CS_CUDA(cudaEventRecord(ctx->ev0, st));
+    CS_TRY(cs_stage_h2d(ctx, base, basis.data(), basis.size() * sizeof(double)));
+    if (C) CS_TRY(cs_stage_h2d(ctx, base + offC, C, sizeof(double) * (size_t)nlev));
+    const int sp_ev = cs_span_begin(ctx, CS_T_TABLE_EVAL, false);
     const double* dTt = (const double*)base;
     const double* dTp = (const double*)(base + offP);
     const double* dC = (const double*)(base + offC);
@@ -623,11 +621,8 @@ int32_t eval_table(cs_table* tb, int64_t nlev, const double* T, const double* P,
 #undef CS_TE_LAUNCH
     CS_CUDA(cudaGetLastError());
     cs_count_launch(ctx);
-    CS_CUDA(cudaEventRecord(ctx->ev1, st));
-    CS_CUDA(cudaStreamSynchronize(st));
-    float ms;
-    CS_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
-    ctx->last_kernel_ms[CS_T_TABLE_EVAL] += ms;
+    cs_span_end(ctx, sp_ev);
+    cs_spans_collect(ctx, false);
     return CS_OK;
 }
 
@@ -844,15 +839,14 @@ extern "C" int32_t cs_sigma_add_accel(cs_sigma* s, cs_accel* A, const double* P)
     size_t offc = offq + (((size_t)nn * sizeof(double) + 255) / 256) * 256;
     CS_TRY(ctx->s_misc.reserve(offc + sizeof(int) * (size_t)nn));
     char* base = ctx->s_misc.as<char>();
-    CS_CUDA(cudaMemcpyAsync(base, x.data(), sizeof(double) * (size_t)nl, cudaMemcpyHostToDevice, st));
-    CS_CUDA(cudaMemcpyAsync(base + offq, q.data(), sizeof(double) * (size_t)nn, cudaMemcpyHostToDevice, st));
-    CS_CUDA(cudaMemcpyAsync(base + offc, cell.data(), sizeof(int) * (size_t)nn, cudaMemcpyHostToDevice, st));
+    CS_TRY(cs_stage_h2d(ctx, base, x.data(), sizeof(double) * (size_t)nl));
+    CS_TRY(cs_stage_h2d(ctx, base + offq, q.data(), sizeof(double) * (size_t)nn));
+    CS_TRY(cs_stage_h2d(ctx, base + offc, cell.data(), sizeof(int) * (size_t)nn));
     dim3 grid((unsigned)((s->nnu + 255) / 256), (unsigned)nn);
     accel_eval_kernel<<<grid, 256, 0, st>>>(A->lnsig, s->nnu, (const double*)base, (const int*)(base + offc),
                                             (const double*)(base + offq), (int)nn, s->sig);
     CS_CUDA(cudaGetLastError());
     cs_count_launch(ctx);
-    CS_CUDA(cudaStreamSynchronize(st));
     return CS_OK;
 }
 
@@ -955,18 +949,15 @@ extern "C" int32_t cs_sigma_add_cia(cs_sigma* s, cs_cia* c, const double* T, con
     size_t offg = ((nodes.size() * sizeof(CiaNode) + 255) / 256) * 256;
     CS_TRY(ctx->s_misc.reserve(offg + gn.size() * sizeof(CiaGridNode)));
     char* base = ctx->s_misc.as<char>();
-    CS_CUDA(cudaMemcpyAsync(base, nodes.data(), nodes.size() * sizeof(CiaNode), cudaMemcpyHostToDevice, st));
-    CS_CUDA(cudaMemcpyAsync(base + offg, gn.data(), gn.size() * sizeof(CiaGridNode), cudaMemcpyHostToDevice, st));
-    CS_CUDA(cudaEventRecord(ctx->ev0, st));
+    CS_TRY(cs_stage_h2d(ctx, base, nodes.data(), nodes.size() * sizeof(CiaNode)));
+    CS_TRY(cs_stage_h2d(ctx, base + offg, gn.data(), gn.size() * sizeof(CiaGridNode)));
+    const int sp_cia = cs_span_begin(ctx, CS_T_CIA, false);
     cia_kernel<<<(unsigned)((s->nnu + 127) / 128), 128, 0, st>>>(
         s->nu, s->nnu, c->ngrid, c->d_desc, c->d_nu, c->d_T, c->d_lnk, c->nsingle, c->d_desc + 5 * c->ngrid, c->d_snu,
         c->d_slnk, c->singles, (const CiaNode*)base, (const CiaGridNode*)(base + offg), (int)nn, s->sig);
     CS_CUDA(cudaGetLastError());
     cs_count_launch(ctx);
-    CS_CUDA(cudaEventRecord(ctx->ev1, st));
-    CS_CUDA(cudaStreamSynchronize(st));
-    float ms;
-    CS_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
-    ctx->last_kernel_ms[CS_T_CIA] += ms;
+    cs_span_end(ctx, sp_cia);
+    cs_spans_collect(ctx, false);
     return CS_OK;
 }

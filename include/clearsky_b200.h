@@ -68,6 +68,10 @@ int32_t cs_ctx_free(cs_ctx* ctx);
 int32_t cs_ctx_synchronize(cs_ctx* ctx);
 /* timers[CS_NTIMERS] of the last compute call; launches = kernels launched so far on this context */
 int32_t cs_ctx_timers(cs_ctx* ctx, double* timers_ms);
+/* same timers accumulated since the context was created (never reset): take differences around a region.  Timers are
+ * CUDA-event pairs recorded on the context stream and read lazily, so compute calls never block the host for them;
+ * both cs_ctx_timers and cs_ctx_timers_total wait for the spans still in flight. */
+int32_t cs_ctx_timers_total(cs_ctx* ctx, double* timers_ms);
 int32_t cs_ctx_launches(cs_ctx* ctx, int64_t* launches);
 /* Far-wing treatment of the windowed line sum (Voigt, Lorentz, PHCO2; Doppler far lines contribute exactly 0).
  *   CS_FARFIELD_DIRECT (default): every (nu, line) pair inside the cut-off is evaluated, as surf! does
@@ -106,6 +110,11 @@ int32_t cs_lines_upload(cs_ctx* ctx, int64_t n, const double* nu, const double* 
                         const int16_t* iso, int32_t niso, const int32_t* ncheb, const double* cheb,
                         const uint8_t* hascheb, cs_lines** out);
 int32_t cs_lines_free(cs_lines* lines);
+/* nu-sharded runs: tell a (sliced) line list the first and last point of the GLOBAL wavenumber grid.  The strict
+ * includedlines prefilter (line_shapes.jl:18-22: nul > min(nu) - cut && nul < max(nu) + cut) is then applied to that grid,
+ * as the reference would, instead of to the slice a call happens to see; at interior slice edges only the inclusive
+ * per-point rule |nu - nul| <= cut (line_shapes.jl:10) decides, so a sharded run keeps exactly the unsharded run's lines. */
+int32_t cs_lines_set_grid_range(cs_lines* lines, double numin, double numax);
 
 /* vector forms of scaleintensity(sl, i, T) (line_shapes.jl:125-132), alpha-doppler(sl, i, T) (:146-148) and
  * gamma-lorentz(sl, i, T, P, Pp) (:259-261) for ALL lines at one (T, P, Pp): outputs [n] each (NULL = skip) */
