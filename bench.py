@@ -548,23 +548,333 @@ def run_ours(args):
         sys.exit(3)
 
 
+# ------------------------------------------------------------------------------------------------
+# BASELINE configs[4]: radiative-convective loop -- `--workload c5`
+C5_METRIC, C5_UNIT = "radiative-convective steps/s", "steps/s"
+C5_DT = 600.0
+
+
+def make_c5(cs, small=False):
+    """C2 atmosphere and line lists, 12 x 24 opacity tables on C2's ν grid, 51 cell edges, radmul = 2 -> 101 radiative levels"""
+    n, nν = (20_000, 30_000) if small else (250_000, 300_000)
+    ν = 0.01 * np.arange(1, nν + 1) * (300_000 / nν)
+    Pe = cs.pressuregrid(10.0, 1e5, 51)
+    Te = cs.DryAdiabat(288.0, 1e5, 1040.0, 0.029, Ptropo=1e4)(Pe)
+    return dict(name="c5small" if small else "c5", n=n, ν=ν, Pe=Pe, Te=Te, g=9.8, μ=0.029, cp=1040.0, cs=1e7, nstream=5, nlob=2,
+                radmul=2, domain=((140, 320), 12, (5, 1.1e5), 24),
+                gases=[(20261018, 2, (0.06, 0.13), 400e-6), (20261019, 1, (0.10, 0.50), 1e-3)])
+
+
+def c5_config(wl, world, nrad):
+    return {"workload": wl["name"], "lines": 2 * wl["n"], "n_nu": len(wl["ν"]), "cells": len(wl["Pe"]), "radiative_levels": int(nrad),
+            "table_nodes": "12x24", "nstream": wl["nstream"], "nlobatto": wl["nlob"], "dt_s": C5_DT,
+            "absorber": "AcceleratedAbsorber (frozen, as in the reference's heating!)", "parallelism": f"nu-slices x{world}",
+            "l2": "per-step working set (stored transmittances 1.45 GB + Planck scratch 0.24 GB) exceeds the 126 MB L2"}
+
+
+def c5_cpu_sample(cs, orc, wl, Pr, P, T0, lnσe, i0, n, nthreads):
+    """one heating!/step! on the host cores: the oracle's AcceleratedAbsorber evaluation at the radiative levels is static,
+    a step is orc.fluxes on the ν sample + the O(np) column arithmetic"""
+    ν = np.ascontiguousarray(wl["ν"][i0:i0 + n])
+    σr = orc.accel_nodes(np.log(wl["Pe"]), np.ascontiguousarray(lnσe[:, i0:i0 + n]), Pr)
+    m, W = cs.streamnodes(wl["nstream"])
+    _, w = cs.lobattonodes(wl["nlob"])
+    μn = np.full((len(Pr) - 1, wl["nlob"]), wl["μ"])
+    Pe = wl["Pe"]
+
+    def step(T, wts=None):
+        Tlev = cs.AtmosphericProfile(P, T)(Pr)
+        f = orc.fluxes(ν, Pr, wl["nlob"], w, μn, Tlev, σr, wl["g"], None, None, 0.841, wl["nstream"], m, W, nthreads=nthreads, full=False)
+        R = -cs.AtmosphericProfile(Pr, f["Fnet"])(Pe)
+        H = np.empty(len(Pe))
+        H[:-1] = (wl["g"] / wl["cp"]) * (R[:-1] - R[1:]) / (Pe[1:] - Pe[:-1])
+        H[-1] = R[-1] / wl["cs"]
+        return T + C5_DT * H, H, f
+
+    return step
+
+
+def run_c5_reference(args):
+    import clearsky_b200 as cs
+    from oracle import oracle as orc
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    orc.build()
+    wl = make_c5(cs, args.workload == "c5small")
+    nth = host_threads()
+    # any smooth positive ln sigma serves the timing: the oracle's cost per step does not depend on the values
+    rng = np.random.default_rng(1)
+    n = min(len(wl["ν"]), 30_000)
+    i0 = (len(wl["ν"]) - n) // 2
+    lnσe = np.full((len(wl["Pe"]), len(wl["ν"])), -60.0)
+    lnσe[:, i0:i0 + n] += rng.uniform(-3, 3, (1, n))
+    rcm = _HostColumn(cs, wl)
+    step = c5_cpu_sample(cs, orc, wl, rcm.Pr, rcm.P, rcm.T, lnσe, i0, n, nth)
+    T = rcm.T.copy()
+    for _ in range(args.warmup):
+        T, _, _ = step(T)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        T, _, _ = step(T)
+    dt = (time.perf_counter() - t0) / args.steps * (len(wl["ν"]) / n)      # scaled to the full ν grid
+    sample = f"ν slice of {n} points of {len(wl['ν'])} x {len(rcm.Pr)} radiative levels, time scaled by the point count"
+    cfg = c5_config(wl, args.gpus, len(rcm.Pr))
+    cfg["sample"] = sample
+    line = {"impl": "reference", "metric": C5_METRIC, "value": 1.0 / dt, "unit": C5_UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": cfg,
+            "cpu_baseline": {"value": 1.0 / dt, "unit": C5_UNIT, "cores": nth, "kind": "port", "sample": sample},
+            "e2e": {"value": 1.0 / dt, "unit": C5_UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line, ensure_ascii=False))
+
+
+class _HostColumn:
+    """grid bookkeeping of RCM(...) (radiative_convective.jl:42-103) without any device object"""
+
+    def __init__(self, cs, wl):
+        Pe, Te, radmul = wl["Pe"], wl["Te"], wl["radmul"]
+        n = len(Pe)
+        self.P, self.T = np.empty(n), np.empty(n)
+        self.P[:-1], self.T[:-1] = (Pe[:-1] + Pe[1:]) / 2, (Te[:-1] + Te[1:]) / 2
+        self.P[-1], self.T[-1] = Pe[-1], Te[-1]
+        Pr = np.empty(radmul * (n - 1) + 1)
+        Pr[: n - 1] = Pe[:-1]
+        i = n - 1
+        for j in range(2, radmul + 1):
+            Pr[i: i + n - 1] = ((j - 1) * Pe[:-1] + (radmul - j + 1) * Pe[1:]) / radmul
+            i += n - 1
+        Pr[-1] = Pe[-1]
+        self.Pr = np.sort(Pr)
+
+
+def run_c5(args):
+    import ctypes as C
+
+    import torch
+    import torch.distributed as dist
+
+    import clearsky_b200 as cs
+    from clearsky_b200 import sharding
+    from clearsky_b200._lib import check, f64, lib, ptr
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    if world > 1:
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.all_reduce(torch.zeros(1, device=dev))
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
+    stream = torch.cuda.Stream(device=local)
+    torch.cuda.set_stream(stream)
+    ctx = cs.Context(local, stream=stream.cuda_stream)
+    wl = make_c5(cs, args.workload == "c5small")
+    ν, Pe, Te = wl["ν"], wl["Pe"], wl["Te"]
+    edges = balanced_slices(np.ones(len(ν)), world)          # a step costs the same at every wavenumber
+    i0, i1 = edges[rank], edges[rank + 1]
+    νs = np.ascontiguousarray(ν[i0:i1])
+    wts = f64(trapz_weights(ν)[i0:i1])
+    Ω = cs.AtmosphericDomain(*wl["domain"])
+    t0 = time.perf_counter()
+    gases = []
+    for seed, M, rng, Cg in wl["gases"]:
+        sl = sharding.slice_lines(synthetic_lines(cs, wl["n"], seed, M, rng), νs[0], νs[-1], 25.0, grid=(ν[0], ν[-1]))
+        gases.append(cs.Gas(sl, Cg, νs, Ω, ctx=ctx))
+    A = cs.AcceleratedAbsorber(Te, Pe, *gases, ctx=ctx)
+    ctx.synchronize()
+    t_setup = time.perf_counter() - t0
+    col = _HostColumn(cs, wl)
+    Pr, nrad, npc = f64(col.Pr), len(col.Pr), len(Pe)
+    m, W = (f64(x) for x in cs.streamnodes(wl["nstream"]))
+    wl_w = f64(cs.lobattonodes(wl["nlob"])[1])
+    ws = cs.SigmaWorkspace(νs, nrad, ctx)
+    A.sigma_nodes(ws, f64(np.full(nrad, 250.0)), Pr)
+    μn = f64(np.full((nrad - 1, wl["nlob"]), wl["μ"]))
+    cp = f64(np.full(npc - 1, wl["cp"]))
+    h = C.c_void_p()
+    check(lib().cs_rcm_create(ws.h, npc, ptr(f64(Pe)), ptr(f64(col.P)), ptr(f64(col.T)), ptr(cp), wl["cs"], nrad, ptr(Pr), wl["nlob"],
+                              ptr(wl_w), ptr(μn), wl["g"], None, None, 0.841, wl["nstream"], ptr(m), ptr(W), ptr(wts), C.byref(h)))
+    dF = torch.zeros(2 * nrad, dtype=torch.float64, device=dev)
+    T0 = f64(col.T)
+
+    def enqueue_step():
+        check(lib().cs_rcm_enqueue_fluxes(h, dF.data_ptr()))
+        if world > 1:
+            dist.all_reduce(dF)
+        check(lib().cs_rcm_enqueue_update(h, dF.data_ptr(), C5_DT))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def state():
+        T, H = np.empty(npc), np.empty(npc)
+        Fup, Fdn = np.empty(nrad), np.empty(nrad)
+        check(lib().cs_rcm_state(h, ptr(T), ptr(H), None, ptr(Fup), ptr(Fdn), None))
+        return T, H, Fup, Fdn
+
+    # one CUDA graph per step: flux kernels + (NCCL all-reduce) + column update; falls back to plain launches
+    graph = None
+    for _ in range(max(args.warmup, 3)):
+        enqueue_step()
+    barrier()
+    if not args.no_graph:
+        try:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=stream):
+                enqueue_step()
+            graph = g
+        except Exception as e:          # capture is an optimisation, never a requirement
+            print(f"bench.py: CUDA-graph capture of the step failed ({e!r}); plain launches", file=sys.stderr)
+            graph = None
+            torch.cuda.synchronize()
+    run_step = (lambda: graph.replay()) if graph is not None else enqueue_step
+    check(lib().cs_rcm_set_temperature(h, ptr(T0)))
+    for _ in range(3):
+        run_step()
+    check(lib().cs_rcm_set_temperature(h, ptr(T0)))
+    barrier()
+    l0 = ctx.launches()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        ev0.record()
+        for _ in range(args.steps):
+            run_step()
+        ev1.record()
+        barrier()
+        dt = ev0.elapsed_time(ev1) * 1e-3
+    tmax = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    dt = float(tmax.item()) / args.steps
+    Tend, Hend, Fup, Fdn = state()
+
+    # kernel-only time of the dominant kernel (rcm_rt_kernel), events on the launching stream around it alone
+    ke0, ke1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kms = []
+    for _ in range(5):
+        ke0.record()
+        check(lib().cs_rcm_enqueue_fluxes(h, dF.data_ptr()))
+        ke1.record()
+        torch.cuda.synchronize()
+        kms.append(ke0.elapsed_time(ke1))
+    k_ms = float(np.median(kms))
+    L, ns = nrad - 1, wl["nstream"]
+    alg_bytes = (2 * (ns + 1) * L + 2 * nrad) * 8.0 * len(νs)       # stored tau + transmittances on both sweeps, Planck scratch w+r
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6458.4))
+
+    # ---- end to end through the host API: temperatures in from pinned host memory, state out, every step
+    Tpin = torch.from_numpy(T0.copy()).pin_memory()
+    check(lib().cs_rcm_set_temperature(h, ptr(T0)))
+    barrier()
+    t0 = time.perf_counter()
+    Th = T0.copy()
+    for _ in range(args.steps):
+        Tpin.numpy()[:] = Th
+        check(lib().cs_rcm_set_temperature(h, Tpin.numpy().ctypes.data_as(C.POINTER(C.c_double))))
+        enqueue_step()
+        Th, _, _, _ = state()
+    barrier()
+    dte = time.perf_counter() - t0
+    te = torch.tensor([dte], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    dte = float(te.item()) / args.steps
+
+    line = {"metric": C5_METRIC, "value": 1.0 / dt, "unit": C5_UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": c5_config(wl, world, nrad),
+            "olr_w_m2": float(Fup[0]), "T_surface_K": float(Tend[-1]), "setup_s": t_setup,
+            "step_launch": "cuda-graph replay (flux kernels + all-reduce + column update)" if graph is not None else "plain launches",
+            "e2e": {"value": 1.0 / dte, "unit": C5_UNIT, "h2d_bytes_per_step": int(npc * 8), "d2h_bytes_per_step": int((2 * npc + 2 * nrad) * 8),
+                    "ms_per_step": dte * 1e3, "steps": args.steps, "host_memory": "pinned",
+                    "max_rel_diff_T_vs_resident": float(np.max(np.abs(Th - Tend) / Tend))},
+            "gpu_launches": int(ctx.launches() - l0) if graph is None else int(3 * args.steps),
+            "clocks": clk.summary(),
+            "roofline": {"bound": "hbm", "kernel": "rcm_rt_kernel<5>", "achieved": alg_bytes / (k_ms * 1e-3) / 1e9, "peak": hbm_peak,
+                         "unit": "GB/s", "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6458.4 GB/s (MEASURED_PEAKS.json absent)",
+                         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k_ms,
+                         "kernel_share_of_step": k_ms / (dt * 1e3), "note": "kernel_ms includes the 2 us spectral reduction launched with it"}}
+
+    parity_fail = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        # FULL-size parity of the step against the oracle-driven host twin: the GPU's own ln sigma at the cell edges is the
+        # input of both (the tables behind it are checked against the oracle on a slice by tools/config_parity.py c5)
+        from oracle import oracle as orc
+        orc.build()
+        nth = host_threads()
+        wse = cs.SigmaWorkspace(νs, npc, ctx)
+        A.sigma_nodes(wse, f64(Te), f64(Pe))
+        lnσe = np.maximum(np.log(wse.read()), np.log(np.finfo(float).tiny))
+        step = c5_cpu_sample(cs, orc, wl, col.Pr, col.P, col.T, lnσe, 0, len(ν), nth)
+        check(lib().cs_rcm_set_temperature(h, ptr(T0)))
+        T = T0.copy()
+        eT = eH = eF = 0.0
+        tc = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            T, H, f = step(T)
+            tc.append(time.perf_counter() - t0)
+            enqueue_step()
+            Tg, Hg, Fu, Fd = state()
+            eT = max(eT, float(np.max(np.abs(Tg - T) / T)))
+            eH = max(eH, float(np.max(np.abs(Hg - H)) / np.max(np.abs(H))))
+            eF = max(eF, float(np.max(np.abs(Fu - f["Fup"]) / f["Fup"])), float(np.max(np.abs(Fd[1:] - f["Fdn"][1:]) / f["Fdn"][1:])))
+        ps = {"n_nu": len(ν), "levels": nrad, "steps": 3, "sample": "full workload (flux solve + column update; Sigma taken from the GPU)",
+              "max_rel_T": eT, "max_rel_heating": eH, "max_rel_flux": eF, "tol_flux": 1e-8, "ok": bool(max(eT, eH, eF) <= 1e-8)}
+        line["parity_sample"] = ps
+        line["cpu_baseline"] = {"value": 1.0 / min(tc), "unit": C5_UNIT, "cores": nth, "kind": "port",
+                                "sample": "full workload: orc.fluxes over all ν at the 101 radiative levels + column update", "seconds": min(tc)}
+        if not ps["ok"]:
+            parity_fail = ps
+    if rank == 0:
+        print(json.dumps(line, ensure_ascii=False))
+    lib().cs_rcm_free(h)
+    if world > 1:
+        dist.destroy_process_group()
+    if parity_fail is not None:
+        print(f"bench.py: PARITY FAILURE against the oracle: {parity_fail}", file=sys.stderr)
+        sys.exit(3)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "c2small"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c2small", "c5", "c5small"])
     ap.add_argument("--cpu-evals", type=float, default=0.0,
                     help="size of the bounded CPU sample [evals]; 0 = 2e10 for the cpu_baseline leg, and for --impl reference "
                          "a size calibrated so that warm-up + steps take about 150 s")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-expansion", action="store_true", help="skip the extra far-field-expansion measurement")
+    ap.add_argument("--no-graph", action="store_true", help="c5: plain launches instead of a CUDA graph per step")
     args = ap.parse_args()
+    c5 = args.workload.startswith("c5")
     if args.impl == "reference":
-        run_reference(args)
+        (run_c5_reference if c5 else run_reference)(args)
     else:
-        run_ours(args)
+        (run_c5 if c5 else run_ours)(args)
 
 
 if __name__ == "__main__":

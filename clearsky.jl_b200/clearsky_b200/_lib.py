@@ -56,6 +56,7 @@ SIGNATURES = {
                       C.c_int32, C.POINTER(_vp)],
     "cs_cia_free": [_vp],
     "cs_accel_from_sigma": [_vp, _dp, C.POINTER(_vp)],
+    "cs_accel_upload": [_vp, C.c_int64, C.c_int64, _dp, _dp, C.POINTER(_vp)],
     "cs_accel_free": [_vp],
     "cs_sigma_create": [_vp, C.c_int64, _dp, C.c_int64, C.POINTER(_vp)],
     "cs_sigma_zero": [_vp],
@@ -83,6 +84,18 @@ SIGNATURES = {
     "cs_group_buffer": [_vp, C.c_int32, C.c_int64, C.POINTER(_vp)],
     "cs_group_allreduce_sum": [_vp, C.c_int64],
     "cs_group_read": [_vp, C.c_int32, C.c_int64, _dp],
+    "cs_group_rcm_step": [_vp, C.POINTER(_vp), C.c_double, C.c_int64],
+    "cs_rcm_create": [_vp, C.c_int64, _dp, _dp, _dp, _dp, C.c_double, C.c_int64, _dp, C.c_int32, _dp, _dp, C.c_double, _dp, _dp,
+                      C.c_double, C.c_int32, _dp, _dp, _dp, C.POINTER(_vp)],
+    "cs_rcm_free": [_vp],
+    "cs_rcm_step": [_vp, C.c_double, C.c_int64],
+    "cs_rcm_set_temperature": [_vp, _dp],
+    "cs_rcm_state": [_vp, _dp, _dp, _dp, _dp, _dp, _dp],
+    "cs_rcm_info": [_vp, _i64p, _i64p, _i64p],
+    "cs_rcm_ctx": [_vp, C.POINTER(_vp)],
+    "cs_rcm_enqueue_fluxes": [_vp, _vp],
+    "cs_rcm_enqueue_update": [_vp, _vp, C.c_double],
+    "cs_rcm_flux_buffer": [_vp, C.POINTER(_vp)],
 }
 
 _lib = None

@@ -5,11 +5,15 @@ The arithmetic outside `radiate!` is O(np) and stays on the host exactly as in t
 `heating!` is one GPU flux solve with the AcceleratedAbsorber (which, like the reference, is NOT updated
 between steps: heating! never calls update!, radiative_convective.jl:109-144).
 """
+import ctypes as C
+
 import numpy as np
 
-from .absorbers import AcceleratedAbsorber, unifyabsorbers
+from ._lib import check, f64, lib, ptr
+from .absorbers import AcceleratedAbsorber, SigmaWorkspace, unifyabsorbers
 from .core import Discretized, FluxPack
-from .fluxes import fluxes_batch, radiate_
+from .fluxes import _eval_spectral, _prepare, _unique_nodes, _vec, fluxes_batch, formprofile, lobattoevaluations, radiate_
+from .quadrature import lobattonodes, streamnodes
 from .sharding import ShardedAbsorber
 from .util import AtmosphericProfile
 
@@ -86,6 +90,84 @@ class RCM:
         self.heating_()
         self.T += Δt * self.H
         return None
+
+    # ---- device-resident loop (cs_rcm_*): the AcceleratedAbsorber is frozen during an RCM run (heating! never calls
+    # update!), so Σ, the layer depths and the stream transmittances are computed once and every step is three kernels
+    # replayed from a CUDA graph; T, H, R and the fluxes come back to the host when the call returns
+    def _device_handles(self):
+        h = self.__dict__.get("_dev")
+        if h is not None:
+            return h
+        core = self.core
+        assert isinstance(core, Discretized), "the device-resident loop runs on the Discretized core"
+        fT = AtmosphericProfile(self.P, self.T)
+        fμ = formprofile(self.Pr, self.fμ)
+        m, W = (f64(x) for x in streamnodes(core.nstream))
+        wl = f64(lobattonodes(core.nlobatto)[1])
+        cp = f64([self.fcp(self.T[i], self.P[i]) if callable(self.fcp) else float(self.fcp) for i in range(self.np - 1)])
+        Pr = f64(self.Pr)
+
+        def create(A, ν, ctx, ν_weights, fSν, faν):
+            Tl, μl, Pn = lobattoevaluations(Pr, fT, fμ, core.nlobatto)
+            Tn, Pq = _unique_nodes(Pr, Tl, Pn, core.nlobatto)
+            ws = SigmaWorkspace(ν, len(Tn), ctx)
+            A.sigma_nodes(ws, f64(Tn), f64(Pq))
+            r = C.c_void_p()
+            check(lib().cs_rcm_create(ws.h, self.np, ptr(f64(self.Pe)), ptr(f64(self.P)), ptr(f64(self.T)), ptr(cp), self.cs,
+                                      len(Pr), ptr(Pr), core.nlobatto, ptr(wl), ptr(f64(μl)), self.g, ptr(fSν), ptr(faν),
+                                      0.841, core.nstream, ptr(m), ptr(W), ptr(ν_weights) if ν_weights is not None else None,
+                                      C.byref(r)))
+            return r
+
+        self.A.checkpressures(Pr[-1], Pr[0])
+        if self.sharded:
+            grp = self.A.group
+            fSν, faν = _eval_spectral(self.fS, self.A.ν), _eval_spectral(self.fa, self.A.ν)
+            hs = []
+            for i, part in enumerate(self.A.parts):
+                assert part is not None, "every device of the group needs a non-empty ν slice"
+                a, b = part["a"], part["b"]
+                hs.append(create(part["A"], part["ν"], grp.ctx[i], part["w"],
+                                 None if fSν is None else f64(fSν[a:b]), None if faν is None else f64(faν[a:b])))
+            h = dict(handles=hs, group=grp)
+        else:
+            ctx = self.A._ws.ctx
+            h = dict(handles=[create(self.A, self.ν, ctx, None, _eval_spectral(self.fS, self.ν), _eval_spectral(self.fa, self.ν))],
+                     group=None)
+        self._dev = h
+        return h
+
+    def steps_(self, Δt, nsteps=1):
+        """nsteps × step!(ℛ, Δt) without leaving the device (cs_rcm_step / cs_group_rcm_step).  The heat capacities
+        𝒻cₚ(T, P) and the molar masses 𝒻μ are evaluated once, at the temperatures of the first call."""
+        h = self._device_handles()
+        T = f64(self.T)
+        for r in h["handles"]:
+            check(lib().cs_rcm_set_temperature(r, ptr(T)))
+        if h["group"] is None:
+            check(lib().cs_rcm_step(h["handles"][0], float(Δt), int(nsteps)))
+        else:
+            arr = (C.c_void_p * len(h["handles"]))(*[r.value for r in h["handles"]])
+            check(lib().cs_group_rcm_step(h["group"].h, arr, float(Δt), int(nsteps)))
+        Tn, H, R = np.empty(self.np), np.empty(self.np), np.empty(self.np)
+        nr = len(self.Pr)
+        Fup, Fdn, Fnet = np.empty(nr), np.empty(nr), np.empty(nr)
+        check(lib().cs_rcm_state(h["handles"][0], ptr(Tn), ptr(H), ptr(R), ptr(Fup), ptr(Fdn), ptr(Fnet)))
+        self.T[:], self.H[:], self.R[:] = Tn, H, R
+        self.F.Fup[:], self.F.Fdn[:], self.F.Fnet[:] = Fup, Fdn, Fnet
+        return None
+
+    def close(self):
+        h = self.__dict__.pop("_dev", None)
+        if h is not None:
+            for r in h["handles"]:
+                lib().cs_rcm_free(r)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def _heating_from(self, Fnet):
         """the O(np) tail of heating! (radiative_convective.jl:123-143) for a given net-flux profile -> H"""

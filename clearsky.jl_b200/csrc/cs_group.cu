@@ -160,3 +160,49 @@ extern "C" int32_t cs_group_read(cs_group* g, int32_t i, int64_t count, double* 
     CS_CUDA(cudaStreamSynchronize(st));
     return CS_OK;
 }
+
+// radiative-convective steps on a nu-sharded column: every device holds the same column state and its own slice of the
+// spectrum.  Per step and device: partial fluxes (2 kernels) -> ONE ncclAllReduce of 2*nrad doubles -> column update
+// (1 kernel), all enqueued from this one host thread without any synchronisation until the last step; the devices then
+// hold bit-identical temperatures (same summed fluxes, same arithmetic).
+extern "C" int32_t cs_group_rcm_step(cs_group* g, cs_rcm* const* rcm, double dt, int64_t nsteps)
+{
+    CS_REQUIRE(g && rcm && nsteps >= 0, CS_ERR_ARG, "bad arguments");
+    const int n = (int)g->ctx.size();
+    int64_t nrad = 0;
+    for (int i = 0; i < n; i++) {
+        CS_REQUIRE(rcm[i], CS_ERR_ARG, "null RCM handle for device %d", i);
+        cs_ctx* c = nullptr;
+        int64_t nr = 0;
+        CS_TRY(cs_rcm_ctx(rcm[i], &c));
+        CS_REQUIRE(c == g->ctx[(size_t)i], CS_ERR_ARG, "RCM handle %d does not live on group member %d", i, i);
+        CS_TRY(cs_rcm_info(rcm[i], nullptr, &nr, nullptr));
+        CS_REQUIRE(i == 0 || nr == nrad, CS_ERR_ARG, "RCM handles disagree on the number of radiative levels");
+        nrad = nr;
+    }
+    std::lock_guard<std::mutex> lk(g->mtx);
+    std::vector<double*> buf((size_t)n);
+    for (int i = 0; i < n; i++) {
+        CS_CUDA(cudaSetDevice(g->dev[(size_t)i]));
+        CS_TRY(g->buf[(size_t)i].reserve(sizeof(double) * 2 * (size_t)nrad));
+        buf[(size_t)i] = g->buf[(size_t)i].as<double>();
+    }
+    for (int64_t k = 0; k < nsteps; k++) {
+        for (int i = 0; i < n; i++) CS_TRY(cs_rcm_enqueue_fluxes(rcm[i], buf[(size_t)i]));
+        if (n > 1) {
+            ncclResult_t r = g->nccl.GroupStart();
+            for (int i = 0; i < n && r == 0; i++)
+                r = g->nccl.AllReduce(buf[(size_t)i], buf[(size_t)i], 2 * (size_t)nrad, NCCL_DOUBLE, NCCL_SUM, g->comm[(size_t)i],
+                                      g->ctx[(size_t)i]->stream);
+            ncclResult_t r2 = g->nccl.GroupEnd();
+            if (r == 0) r = r2;
+            CS_REQUIRE(r == 0, CS_ERR_CUDA, "ncclAllReduce: %s", g->nccl.GetErrorString(r));
+        }
+        for (int i = 0; i < n; i++) CS_TRY(cs_rcm_enqueue_update(rcm[i], buf[(size_t)i], dt));
+    }
+    for (int i = 0; i < n; i++) {
+        CS_CUDA(cudaSetDevice(g->dev[(size_t)i]));
+        CS_CUDA(cudaStreamSynchronize(g->ctx[(size_t)i]->stream));
+    }
+    return CS_OK;
+}

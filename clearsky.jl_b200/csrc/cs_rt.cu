@@ -1287,6 +1287,15 @@ extern "C" int32_t cs_rcm_ctx(cs_rcm* r, cs_ctx** ctx)
     return CS_OK;
 }
 
+extern "C" int32_t cs_rcm_info(cs_rcm* r, int64_t* np, int64_t* nrad, int64_t* nnu)
+{
+    CS_REQUIRE(r, CS_ERR_ARG, "null argument");
+    if (np) *np = r->np;
+    if (nrad) *nrad = r->nrad;
+    if (nnu) *nnu = r->nnu;
+    return CS_OK;
+}
+
 extern "C" int32_t cs_rcm_flux_buffer(cs_rcm* r, double** d_F)
 {
     CS_REQUIRE(r && d_F, CS_ERR_ARG, "null argument");

@@ -805,6 +805,33 @@ extern "C" int32_t cs_accel_from_sigma(cs_sigma* s, const double* P, cs_accel** 
     return CS_OK;
 }
 
+extern "C" int32_t cs_accel_upload(cs_ctx* ctx, int64_t nnu, int64_t nlev, const double* P, const double* lnsig, cs_accel** out)
+{
+    CS_REQUIRE(ctx && P && lnsig && out, CS_ERR_ARG, "null argument");
+    *out = nullptr;
+    CS_REQUIRE(nnu > 0 && nlev >= 2, CS_ERR_ARG, "need at least one wavenumber and two pressure levels");
+    for (int64_t i = 1; i < nlev; i++)
+        CS_REQUIRE(P[i] > P[i - 1], CS_ERR_ARG, "AcceleratedAbsorber pressure levels must ascend (absorbers.jl:141-143)");
+    std::lock_guard<std::recursive_mutex> lk(ctx->mtx);
+    CS_CUDA(cudaSetDevice(ctx->device));
+    cs_accel* A = new cs_accel();
+    A->ctx = ctx;
+    A->nnu = nnu;
+    A->nlev = nlev;
+    A->h_lnP.resize((size_t)nlev);
+    for (int64_t i = 0; i < nlev; i++) A->h_lnP[(size_t)i] = log(P[i]);
+    int32_t rc = upload_d(&A->lnsig, lnsig, (size_t)nnu * nlev, ctx->stream);
+    if (rc) { delete A; return rc; }
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        cs_set_error("cs_accel_upload: %s", cudaGetErrorString(e));
+        cs_accel_free(A);
+        return CS_ERR_CUDA;
+    }
+    *out = A;
+    return CS_OK;
+}
+
 extern "C" int32_t cs_accel_free(cs_accel* A)
 {
     if (!A) return CS_OK;

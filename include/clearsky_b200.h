@@ -162,6 +162,9 @@ int32_t cs_cia_free(cs_cia* cia);
 /* snapshot max(log(Sigma), log(floatmin)) of a sigma workspace whose nodes are the nlev levels P
  * (ascending) -> update!(A, T) (:173-200) */
 int32_t cs_accel_from_sigma(cs_sigma* sig, const double* P, cs_accel** out);
+/* the same object from host values: lnsig[nlev][nnu] = the phi_i[k] of a stock AcceleratedAbsorber (Julia matrix [nnu, nlev]),
+ * already floored at log(floatmin) by update! (:193-195); P[nlev] ascending (:141-143) */
+int32_t cs_accel_upload(cs_ctx* ctx, int64_t nnu, int64_t nlev, const double* P, const double* lnsig, cs_accel** out);
 int32_t cs_accel_free(cs_accel* accel);
 
 /* ---- sigma workspace: Sigma(A, idx, T, P) = sum of absorbers at the Lobatto nodes ---------------
@@ -218,6 +221,41 @@ int32_t cs_fluxes_batch(cs_sigma* sig, int64_t np, const double* P, int32_t nlob
 int32_t cs_opticaldepth(cs_sigma* sig, int64_t np, const double* P, int32_t nlob, const double* wlob,
                         const double* mu, double g, double theta, double* tau_total);
 
+/* ---- device-resident radiative-convective loop  (src/radiative_convective.jl:6-151) ------------------------------
+ * heating!(R) (:109-144) = radiate! on the radiative levels Pr with the AcceleratedAbsorber, Fnet interpolated to the
+ * cell edges Pe (AtmosphericProfile(Pr, Fnet), :123-124), cell heating rates H[i] = (g/cp_i) (R[i]-R[i+1]) / (Pe[i+1]-Pe[i])
+ * and surface heating H[end] = R[end]/c_surf (:129-140); step!(R, dt) (:147-151) = T += dt*H.  The reference never calls
+ * update!(A, T) inside heating!, and an AcceleratedAbsorber ignores T (absorbers.jl:203), so Sigma is the same at every
+ * step: cs_rcm_create takes a sigma workspace already filled at the nodes of Pr ((nrad-1)*(nlob-1)+1 nodes), computes all
+ * layer optical depths, stream transmittances and the stellar beam ONCE, and a step only evaluates Planck at the new level
+ * temperatures (AtmosphericProfile(P, T) at Pr, :112), runs the stream recurrences on the stored transmittances, reduces
+ * spectrally and updates the column -- three kernels captured in one CUDA graph; nothing crosses PCIe until cs_rcm_state.
+ *   Pe[np] cell edges (ascending), P[np] cell centres + surface (:62-69), T0[np] initial cell temperatures,
+ *   cp[np-1] = fcp(T_i, P_i) (held fixed), c_surf surface heat capacity, Pr[nrad] radiative levels (:71-85),
+ *   mu[nlob][nrad-1] at the Lobatto nodes, the rest as in cs_fluxes.  The workspace is only read during the call. */
+typedef struct cs_rcm cs_rcm;
+int32_t cs_rcm_create(cs_sigma* sig, int64_t np, const double* Pe, const double* P, const double* T0, const double* cp,
+                      double c_surf, int64_t nrad, const double* Pr, int32_t nlob, const double* wlob, const double* mu,
+                      double g, const double* fS, const double* fa, double theta_s, int32_t nstream, const double* m,
+                      const double* W, const double* nu_weights, cs_rcm** out);
+int32_t cs_rcm_free(cs_rcm* rcm);
+/* nsteps x step!(R, dt) on the device (graph replays), synchronised on return; dt = 0 evaluates heating! without moving T */
+int32_t cs_rcm_step(cs_rcm* rcm, double dt, int64_t nsteps);
+/* overwrite the cell temperatures (e.g. after a convective adjustment on the host) */
+int32_t cs_rcm_set_temperature(cs_rcm* rcm, const double* T);
+/* copy the column state to the host: T, H, R [np]; F+, F-, Fnet [nrad] of the last step; NULL = skip */
+int32_t cs_rcm_state(cs_rcm* rcm, double* T, double* H, double* R, double* Fup, double* Fdn, double* Fnet);
+int32_t cs_rcm_info(cs_rcm* rcm, int64_t* np, int64_t* nrad, int64_t* nnu);
+int32_t cs_rcm_ctx(cs_rcm* rcm, cs_ctx** ctx);
+/* nu-sharded columns (one cs_rcm per slice, global trapezoid weights): the two halves of a step around the caller's
+ * all-reduce.  cs_rcm_enqueue_fluxes launches the flux kernels and leaves this slice's partial F+ then F- (2*nrad doubles)
+ * in DEVICE memory d_F (NULL: the handle's own buffer, cs_rcm_flux_buffer); cs_rcm_enqueue_update consumes the summed
+ * fluxes.  Both only enqueue work on the context stream (no host synchronisation), so a caller can capture
+ * fluxes -> all-reduce -> update in its own CUDA graph. */
+int32_t cs_rcm_enqueue_fluxes(cs_rcm* rcm, double* d_F);
+int32_t cs_rcm_enqueue_update(cs_rcm* rcm, const double* d_F, double dt);
+int32_t cs_rcm_flux_buffer(cs_rcm* rcm, double** d_F);
+
 /* ---- HITRAN .par ingestion on the GPU (the step BEFORE the path; readpar's parse loop, src/hitran/par.jl:127-152) ----
  * text = the file's bytes, nrec fixed-width records of reclen bytes each (160 columns + line terminator), column map
  * of par.jl:131-140.  Outputs (host, nrec each, FILE order -- filtering/sorting stay with the caller exactly like
@@ -245,6 +283,10 @@ int32_t cs_group_buffer(cs_group* grp, int32_t i, int64_t count, double** d_ptr)
 int32_t cs_group_allreduce_sum(cs_group* grp, int64_t count);
 /* copy the first `count` doubles of device i's group buffer to the host */
 int32_t cs_group_read(cs_group* grp, int32_t i, int64_t count, double* host);
+/* nsteps radiative-convective steps of a nu-sharded column: rcm[i] lives on group member i; per step every device computes
+ * its partial fluxes, ONE ncclAllReduce sums the 2*nrad values, every device applies the same column update.  Everything is
+ * enqueued from the calling thread; the call returns when all devices have finished the last step. */
+int32_t cs_group_rcm_step(cs_group* grp, cs_rcm* const* rcm, double dt, int64_t nsteps);
 
 #ifdef __cplusplus
 }

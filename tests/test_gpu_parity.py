@@ -516,6 +516,52 @@ def test_rcm_heating_and_step(cs, orc, co2):
         scale = np.max(np.abs(Href))
         assert np.max(np.abs(rcm.H - Href)) < 1e-8 * scale
         assert np.max(np.abs(rcm.T - T)) < 1e-9 * np.max(T)
+    # ---- device-resident loop (cs_rcm_step: Fnet -> edges, heating rates, T += dt*H and the level temperatures on the
+    # device, three kernels per step replayed from a CUDA graph) against the same oracle-driven twin, continuing the run
+    for nsteps in (1, 4):
+        for _ in range(nsteps):
+            Href = heating(T)
+            T = T + 3600.0 * Href
+        rcm.steps_(3600.0, nsteps)
+        assert np.max(np.abs(rcm.H - Href)) < 1e-8 * np.max(np.abs(Href))
+        assert np.max(np.abs(rcm.T - T)) < 1e-9 * np.max(T)
+    # heating! without moving T (dt = 0), and the fluxes of the last step against a plain flux call
+    Tb = rcm.T.copy()
+    rcm.steps_(0.0, 1)
+    assert np.array_equal(rcm.T, Tb)
+    Fup, Fdn = cs.fluxes(rcm.Pr, 9.8, cs.AtmosphericProfile(rcm.P, rcm.T), 0.029, fS, 0.25, rcm.A)
+    assert relerr(rcm.F.Fup, Fup) < 1e-12 and relerr(rcm.F.Fdn, Fdn, 1e-3) < 1e-12
+    # host loop and device loop are interchangeable step by step
+    rcm2 = cs.RCM(Pe, Te, 9.8, 0.029, fS, 0.25, 1040.0, 1e7, gas, radmul=2)
+    rcm3 = cs.RCM(Pe, Te, 9.8, 0.029, fS, 0.25, 1040.0, 1e7, gas, radmul=2)
+    for _ in range(6):
+        rcm2.step_(1800.0)
+    rcm3.steps_(1800.0, 6)
+    assert relerr(rcm2.T, rcm3.T) < 1e-13 and np.max(np.abs(rcm2.H - rcm3.H)) < 1e-9 * np.max(np.abs(rcm2.H))
+    rcm.close(); rcm3.close()
+
+
+def test_rcm_device_loop_variants(cs, co2):
+    """cs_rcm_step against the host loop for the other kernel variants: no sun / no albedo (null pointers), nlobatto = 3
+    (intermediate quadrature nodes), generic stream count, radmul = 4"""
+    ν = np.linspace(50.0, 2000.0, 333)
+    Pe = cs.pressuregrid(50.0, 1e5, 9)
+    Te = cs.DryAdiabat(288.0, 1e5, 1040.0, 0.029, Ptropo=1.5e4)(Pe)
+    Ω = cs.AtmosphericDomain((120, 330), 8, (20, 1.1e5), 12)
+    gas = cs.Gas(co2, 400e-6, ν, Ω)
+    fS = lambda x: 0.3 * np.exp(-((x - 1200.0) / 500.0) ** 2)
+    for core, sun, alb, radmul in ((cs.Discretized(5, 2), None, None, 2), (cs.Discretized(4, 3), fS, 0.1, 2),
+                                   (cs.Discretized(7, 2), fS, None, 4)):
+        a = cs.RCM(Pe, Te, 9.8, 0.029, sun, alb, lambda T, P: 1000.0 + 0.1 * (T - 250.0), 1e7, gas, radmul=radmul, core=core)
+        b = cs.RCM(Pe, Te, 9.8, 0.029, sun, alb, 1.0, 1e7, gas, radmul=radmul, core=core)
+        cp0 = np.array([1000.0 + 0.1 * (a.T[i] - 250.0) for i in range(a.np - 1)])     # held at the first call's T
+        b.fcp = lambda T, P, _c=cp0, _P=b.P: float(_c[int(np.argmin(np.abs(_P[:-1] - P)))])
+        a.steps_(900.0, 5)
+        for _ in range(5):
+            b.step_(900.0)
+        assert relerr(a.T, b.T) < 1e-13 and np.max(np.abs(a.H - b.H)) < 1e-9 * np.max(np.abs(b.H))
+        assert np.max(np.abs(a.F.Fnet - b.F.Fnet)) < 1e-10 * np.max(np.abs(b.F.Fnet))
+        a.close()
 
 
 def test_rcm_jacobian_batched(cs, co2):
@@ -731,6 +777,12 @@ def test_sharded_tables_and_rcm(cs, co2, h2o):
     b.A.update(b.Te + 1.0)
     a.heating_(); b.heating_()
     assert relerr(a.H, b.H, 1e-30) < 1e-9
+    # device-resident loop over the group (cs_group_rcm_step: partial fluxes -> ncclAllReduce -> column update per step)
+    a.steps_(1800.0, 4)
+    for _ in range(4):
+        b.step_(1800.0)
+    assert relerr(a.T, b.T) < 1e-12 and np.max(np.abs(a.H - b.H)) < 1e-9 * np.max(np.abs(b.H))
+    a.close()
     del a, sh
     grp.close()
 
