@@ -77,6 +77,9 @@ SIGNATURES = {
     "cs_opticaldepth": [_vp, C.c_int64, _dp, C.c_int32, _dp, _dp, C.c_double, C.c_double, _dp],
     "cs_par_parse": [_vp, C.c_int64, C.c_char_p, C.c_int32, C.c_int64, C.POINTER(C.c_int16), C.POINTER(C.c_int16),
                      _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, C.POINTER(C.c_uint8)],
+    "cs_par_read": [_vp, C.c_int64, C.c_char_p, C.c_int32, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_int32,
+                    C.POINTER(C.c_int16), C.c_int64, C.POINTER(C.c_int16), C.POINTER(C.c_int16), _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp,
+                    _i64p, _i64p, _i64p],
     "cs_group_create": [C.c_int32, C.POINTER(C.c_int32), C.POINTER(_vp)],
     "cs_group_free": [_vp],
     "cs_group_size": [_vp, C.POINTER(C.c_int32)],

@@ -148,12 +148,7 @@ def parse_records_b200(buf, ctx=None):
     from . import _lib
     from ._lib import check, lib, ptr
     ctx = ctx or _lib.default_context()
-    nl = buf.find(b"\n")
-    reclen = nl + 1 if nl >= 0 else len(buf)
-    assert reclen >= 161 or (nl < 0 and reclen >= 160), "expected 160-column HITRAN records"
-    nrec = (len(buf) + reclen - 1) // reclen if len(buf) % reclen else len(buf) // reclen
-    if len(buf) % reclen and len(buf) - (nrec - 1) * reclen < 67:
-        nrec -= 1                       # trailing blank line
+    reclen, nrec = _record_geometry(buf)
     M, I = np.empty(nrec, np.int16), np.empty(nrec, np.int16)
     cols = {k: np.empty(nrec) for k in ("ν", "S", "A", "γa", "γs", "Epp", "na", "δa")}
     flags = np.empty(nrec, np.uint8)
@@ -165,38 +160,56 @@ def parse_records_b200(buf, ctx=None):
     return par, flags, reclen
 
 
-def readpar_b200(filename, νmin=0, νmax=np.inf, Scut=0, I=(), maxlines=-1, ctx=None):
-    """readpar (par.jl:91-193) with the parse loop on the GPU.  "I" is returned as the isotopologue character like
-    readpar does; every numeric column is bit-identical to the host parser."""
+def _record_geometry(buf):
+    """(reclen, nrec) of a buffer of fixed-width records (a trailing blank line is not a record)"""
+    nl = buf.find(b"\n")
+    reclen = nl + 1 if nl >= 0 else len(buf)
+    assert reclen >= 161 or (nl < 0 and reclen >= 160), "expected 160-column HITRAN records"
+    nrec = (len(buf) + reclen - 1) // reclen if len(buf) % reclen else len(buf) // reclen
+    if len(buf) % reclen and len(buf) - (nrec - 1) * reclen < 67:
+        nrec -= 1
+    return reclen, nrec
+
+
+def readpar_b200(filename, νmin=0, νmax=np.inf, Scut=0, I=(), maxlines=-1, ctx=None, index=False):
+    """readpar (par.jl:91-193) in one device call (cs_par_read): parse loop (:127-152), filters (:154-170), the
+    maxlines truncation (:178-185) and the final sort by ν (:187-191) all run on the GPU, so only the surviving records
+    cross PCIe, already in output order.  "I" is returned as the isotopologue character like readpar does; every
+    numeric column is bit-identical to the host parser.  index=True adds "record" = 0-based file record of each row
+    (to gather the quantum-number string columns)."""
+    import ctypes as C
+
+    from . import _lib
+    from ._lib import check, lib, ptr
     base = filename[:-3] if filename.endswith(".gz") else filename
     assert base.endswith(".par"), "expected file with .par extension, downloaded from https://hitran.org/lbl/"
     op = gzip.open if filename.endswith(".gz") else open
     with op(filename, "rb") as f:
         buf = f.read()
-    par, flags, reclen = parse_records_b200(buf, ctx)
-    if flags.any():
-        raise ValueError(f"{int(flags.sum())} malformed record(s) in {filename}, first at line {int(np.argmax(flags)) + 1}")
-    N = len(par["ν"])
+    ctx = ctx or _lib.default_context()
+    reclen, nrec = _record_geometry(buf)
+    Ilist = np.array([ISOINDEX[i] if isinstance(i, str) else int(i) for i in I], dtype=np.int16)
+    M, Iv = np.empty(nrec, np.int16), np.empty(nrec, np.int16)
+    keys = ("ν", "S", "A", "γa", "γs", "Epp", "na", "δa")
+    cols = {k: np.empty(nrec) for k in keys}
+    idx = np.empty(nrec, np.int64)
+    nout, nbad = C.c_int64(0), C.c_int64(0)
+    i16 = lambda a: a.ctypes.data_as(C.POINTER(C.c_int16))
+    rc = lib().cs_par_read(ctx.h, len(buf), buf, reclen, nrec, float(νmin), float(νmax), float(Scut), len(Ilist),
+                           i16(Ilist) if len(Ilist) else None, int(maxlines), i16(M), i16(Iv), *[ptr(cols[k]) for k in keys],
+                           idx.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(nout), C.byref(nbad))
+    if rc != 0 and b"filtered to nothing" in lib().cs_last_error():
+        raise AssertionError("par information has been filtered to nothing!")          # par.jl:172 is an @assert
+    check(rc)
+    if nbad.value:
+        raise ValueError(f"{nbad.value} malformed record(s) in {filename}")
+    n = nout.value
     inv = {v: k for k, v in ISOINDEX.items()}
-    par["I"] = np.array([inv[int(i)] for i in par["I"]], dtype="U1")
-    mask = np.ones(N, dtype=bool)
-    mask &= par["ν"] >= νmin
-    mask &= par["ν"] <= νmax
-    mask &= par["S"] >= Scut
-    if len(I) > 0:
-        Iset = set(I)
-        keep = np.array([(ch in Iset) or (ISOINDEX[ch] in Iset) for ch in par["I"]])
-        mask &= keep
-    assert mask.any(), "par information has been filtered to nothing!"
-    for key in par:
-        par[key] = par[key][mask]
-    if maxlines > 0 and N > maxlines:
-        idx = np.argsort(par["S"], kind="stable")[::-1][:maxlines]
-        for key in par:
-            par[key] = par[key][idx]
-    idx = np.argsort(par["ν"], kind="stable")
-    for key in par:
-        par[key] = par[key][idx]
+    par = {"M": M[:n].copy(), "I": np.array([inv[int(i)] for i in Iv[:n]], dtype="U1")}
+    for k in keys:
+        par[k] = cols[k][:n].copy()
+    if index:
+        par["record"] = idx[:n].copy()
     return par
 
 

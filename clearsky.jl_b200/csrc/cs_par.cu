@@ -6,6 +6,11 @@
 // the correctly rounded result (Clinger's fast path); larger exponents (line intensities ~1e-30) go through a
 // double-double division by two exact powers of ten, whose 106-bit intermediate is rounded once.
 #include "cs_internal.cuh"
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
+#include <cstring>
+#include <limits>
 
 namespace {
 
@@ -182,5 +187,215 @@ extern "C" int32_t cs_par_parse(cs_ctx* ctx, int64_t nbytes, const char* text, i
     CS_CUDA(cudaMemcpyAsync(flags, a.flags, (size_t)nrec, cudaMemcpyDeviceToHost, st));
     CS_CUDA(cudaStreamSynchronize(st));
     cs_spans_collect(ctx, false);
+    return CS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// readpar's vector operations on the device (src/hitran/par.jl:154-191): filters, the maxlines truncation and the final
+// sort by wavenumber, so that only the surviving records cross PCIe, already in output order.
+namespace {
+
+// order-preserving map double -> uint64 (isless order: -0.0 before +0.0, as Julia's sortperm uses)
+__device__ __forceinline__ unsigned long long ord_key(double x)
+{
+    unsigned long long b = (unsigned long long)__double_as_longlong(x);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ULL);
+}
+
+__global__ void par_mask_kernel(int64_t n, const double* __restrict__ nu, const double* __restrict__ S,
+                                const int16_t* __restrict__ I, double numin, double numax, double Scut, int nI,
+                                const int16_t* __restrict__ Ilist, uint8_t* __restrict__ keep)
+{
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    bool k = (nu[j] >= numin) && (nu[j] <= numax) && (S[j] >= Scut);     // par.jl:155-157
+    if (nI > 0) {                                                        // :158-169
+        bool in = false;
+        for (int q = 0; q < nI; q++) in |= (Ilist[q] == I[j]);
+        k &= in;
+    }
+    keep[j] = k ? 1 : 0;
+}
+
+__global__ void par_keys_kernel(int64_t n, const int64_t* __restrict__ idx, const double* __restrict__ col,
+                                unsigned long long* __restrict__ keys)
+{
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) keys[k] = ord_key(col[idx[k]]);
+}
+
+// reverse(sortperm(S))[1:m]: the last m entries of the ascending stable order, reversed (par.jl:181)
+__global__ void par_reverse_tail_kernel(const int64_t* __restrict__ asc, int64_t nf, int64_t m, int64_t* __restrict__ q)
+{
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < m) q[k] = asc[nf - 1 - k];
+}
+
+struct ParGather {
+    const int64_t* order;
+    int64_t n;
+    const double* in[8];
+    double* out[8];
+    const int16_t *Min, *Iin;
+    int16_t *Mout, *Iout;
+};
+__global__ void par_gather_kernel(ParGather g)
+{
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= g.n) return;
+    const int64_t j = g.order[k];
+#pragma unroll
+    for (int c = 0; c < 8; c++) g.out[c][k] = g.in[c][j];
+    g.Mout[k] = g.Min[j];
+    g.Iout[k] = g.Iin[j];
+}
+
+__global__ void par_count_bad_kernel(int64_t n, const uint8_t* __restrict__ flags, unsigned long long* nbad)
+{
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned bad = (j < n && flags[j]) ? 1u : 0u;
+    unsigned m = __ballot_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(nbad, (unsigned long long)__popc(m));
+}
+
+// host text -> device through two pinned staging buffers: the host memcpy of chunk c+1 overlaps the DMA of chunk c (a
+// pageable cudaMemcpy of the whole file serialises the two)
+int32_t staged_text_h2d(cs_ctx* ctx, char* dst, const char* src, size_t bytes)
+{
+    constexpr size_t CHUNK = (size_t)4 << 20;
+    static thread_local void* pin[2] = {nullptr, nullptr};
+    static thread_local cudaEvent_t done[2] = {nullptr, nullptr};
+    for (int b = 0; b < 2; b++) {
+        if (!pin[b]) CS_CUDA(cudaMallocHost(&pin[b], CHUNK));
+        if (!done[b]) CS_CUDA(cudaEventCreateWithFlags(&done[b], cudaEventDisableTiming));
+    }
+    int b = 0;
+    for (size_t off = 0; off < bytes; off += CHUNK, b ^= 1) {
+        const size_t n = std::min(CHUNK, bytes - off);
+        CS_CUDA(cudaEventSynchronize(done[b]));        // an event never recorded is complete
+        memcpy(pin[b], src + off, n);
+        CS_CUDA(cudaMemcpyAsync(dst + off, pin[b], n, cudaMemcpyHostToDevice, ctx->stream));
+        CS_CUDA(cudaEventRecord(done[b], ctx->stream));
+    }
+    return CS_OK;
+}
+
+}  // namespace
+
+extern "C" int32_t cs_par_read(cs_ctx* ctx, int64_t nbytes, const char* text, int32_t reclen, int64_t nrec, double numin,
+                               double numax, double Scut, int32_t nI, const int16_t* Ilist, int64_t maxlines, int16_t* M,
+                               int16_t* I, double* nu, double* S, double* A, double* ga, double* gs, double* Epp, double* na,
+                               double* da, int64_t* index, int64_t* nout, int64_t* nbad)
+{
+    CS_REQUIRE(ctx && text && M && I && nu && S && A && ga && gs && Epp && na && da && nout, CS_ERR_ARG, "null argument");
+    CS_REQUIRE(reclen >= PAR_COLS && reclen <= 512, CS_ERR_ARG, "record length %d outside [%d, 512]", reclen, PAR_COLS);
+    CS_REQUIRE(nrec > 0 && nbytes >= (nrec - 1) * (int64_t)reclen + PAR_COLS, CS_ERR_ARG, "buffer shorter than nrec records");
+    CS_REQUIRE(nI >= 0 && (nI == 0 || Ilist), CS_ERR_ARG, "bad isotopologue filter");
+    CS_REQUIRE(nrec < ((int64_t)1 << 31), CS_ERR_ARG, "too many records for one call");
+    *nout = 0;
+    if (nbad) *nbad = 0;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mtx);
+    CS_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    auto al = [](size_t b) { return ((b + 255) / 256) * 256; };
+    const size_t n = (size_t)nrec;
+    // device layout: text | 8 parsed columns | M, I | parse flags | keep | Ilist | counters | idx a/b | keys a/b | 8 output columns | M, I out
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += al(bytes); return o; };
+    const size_t o_text = take(n * reclen + 256), o_col = take(8 * n * sizeof(double)), o_mi = take(2 * n * sizeof(int16_t));
+    const size_t o_flags = take(n), o_keep = take(n), o_il = take(sizeof(int16_t) * (size_t)std::max(nI, 1)), o_cnt = take(64);
+    const size_t o_ia = take(n * 8), o_ib = take(n * 8), o_ka = take(n * 8), o_kb = take(n * 8);
+    const size_t o_out = take(8 * n * sizeof(double)), o_mio = take(2 * n * sizeof(int16_t));
+    size_t tmp_sel = 0, tmp_sort = 0;
+    {
+        cub::CountingInputIterator<int64_t> it(0);
+        cub::DeviceSelect::Flagged((void*)nullptr, tmp_sel, it, (const uint8_t*)nullptr, (int64_t*)nullptr, (int64_t*)nullptr, (int)nrec, st);
+        cub::DeviceRadixSort::SortPairs((void*)nullptr, tmp_sort, (const unsigned long long*)nullptr, (unsigned long long*)nullptr,
+                                        (const int64_t*)nullptr, (int64_t*)nullptr, (int)nrec, 0, 64, st);
+    }
+    const size_t tmp_bytes = std::max(tmp_sel, tmp_sort);
+    const size_t o_tmp = take(tmp_bytes + 256);
+    CS_TRY(ctx->s_sigma.reserve(off));
+    char* base = ctx->s_sigma.as<char>();
+    const size_t ncopy = std::min<size_t>((size_t)nbytes, n * reclen);
+    if (ncopy < n * reclen) CS_CUDA(cudaMemsetAsync(base + o_text, ' ', n * reclen, st));
+    CS_TRY(staged_text_h2d(ctx, base + o_text, text, ncopy));
+    ParArgs a;
+    a.text = base + o_text; a.nrec = nrec; a.reclen = reclen;
+    double* d = (double*)(base + o_col);
+    a.nu = d; a.S = d + n; a.A = d + 2 * n; a.ga = d + 3 * n; a.gs = d + 4 * n; a.Epp = d + 5 * n; a.na = d + 6 * n; a.da = d + 7 * n;
+    a.M = (int16_t*)(base + o_mi); a.I = a.M + n;
+    a.flags = (uint8_t*)(base + o_flags);
+    const int sp = cs_span_begin(ctx, CS_T_TOTAL, true);
+    const int64_t nblk = (nrec + PAR_WARPS * 32 - 1) / (PAR_WARPS * 32);
+    const size_t smem = (size_t)PAR_WARPS * ((((size_t)32 * reclen + 16 + 15) & ~(size_t)15));
+    par_parse_kernel<<<(unsigned)nblk, PAR_WARPS * 32, smem, st>>>(a);
+    CS_CUDA(cudaGetLastError());
+    // ---- filters (par.jl:154-170)
+    int16_t* dIl = (int16_t*)(base + o_il);
+    if (nI > 0) CS_TRY(cs_stage_h2d(ctx, dIl, Ilist, sizeof(int16_t) * (size_t)nI));
+    uint8_t* keep = (uint8_t*)(base + o_keep);
+    unsigned long long* cnt = (unsigned long long*)(base + o_cnt);      // [0] selected, [1] malformed
+    CS_CUDA(cudaMemsetAsync(cnt, 0, 64, st));
+    const unsigned g256 = (unsigned)((nrec + 255) / 256);
+    par_mask_kernel<<<g256, 256, 0, st>>>(nrec, a.nu, a.S, a.I, numin, numax, Scut, nI, dIl, keep);
+    par_count_bad_kernel<<<g256, 256, 0, st>>>(nrec, a.flags, cnt + 1);
+    int64_t *ia = (int64_t*)(base + o_ia), *ib = (int64_t*)(base + o_ib);
+    unsigned long long *ka = (unsigned long long*)(base + o_ka), *kb = (unsigned long long*)(base + o_kb);
+    {
+        cub::CountingInputIterator<int64_t> it(0);
+        size_t tb = tmp_bytes;
+        CS_CUDA(cub::DeviceSelect::Flagged(base + o_tmp, tb, it, keep, ia, (int64_t*)cnt, (int)nrec, st));
+    }
+    unsigned long long hc[2] = {0, 0};
+    CS_CUDA(cudaMemcpyAsync(hc, cnt, sizeof(hc), cudaMemcpyDeviceToHost, st));
+    CS_CUDA(cudaStreamSynchronize(st));
+    cs_count_launch(ctx, 4);
+    int64_t nf = (int64_t)hc[0];
+    if (nbad) *nbad = (int64_t)hc[1];
+    CS_REQUIRE(nf > 0, CS_ERR_ARG, "par information has been filtered to nothing!");      // par.jl:172
+    int64_t* cur = ia;
+    int64_t* other = ib;
+    // ---- strongest maxlines lines (par.jl:178-185; the comparison is against the PRE-filter count, as in the reference)
+    if (maxlines > 0 && nrec > maxlines) {
+        CS_REQUIRE(nf >= maxlines, CS_ERR_ARG,
+                   "maxlines = %lld exceeds the %lld lines left after filtering (the reference raises a BoundsError here)",
+                   (long long)maxlines, (long long)nf);
+        const unsigned gf = (unsigned)((nf + 255) / 256);
+        par_keys_kernel<<<gf, 256, 0, st>>>(nf, cur, a.S, ka);
+        size_t tb = tmp_bytes;
+        CS_CUDA(cub::DeviceRadixSort::SortPairs(base + o_tmp, tb, ka, kb, cur, other, (int)nf, 0, 64, st));     // stable, ascending
+        par_reverse_tail_kernel<<<(unsigned)((maxlines + 255) / 256), 256, 0, st>>>(other, nf, maxlines, cur);
+        CS_CUDA(cudaGetLastError());
+        cs_count_launch(ctx, 3);
+        nf = maxlines;
+    }
+    // ---- sort by wavenumber, stable on the current order (par.jl:187-191)
+    {
+        const unsigned gf = (unsigned)((nf + 255) / 256);
+        par_keys_kernel<<<gf, 256, 0, st>>>(nf, cur, a.nu, ka);
+        size_t tb = tmp_bytes;
+        CS_CUDA(cub::DeviceRadixSort::SortPairs(base + o_tmp, tb, ka, kb, cur, other, (int)nf, 0, 64, st));
+        std::swap(cur, other);
+        ParGather g;
+        g.order = cur; g.n = nf;
+        double* od = (double*)(base + o_out);
+        for (int c = 0; c < 8; c++) { g.in[c] = d + (size_t)c * n; g.out[c] = od + (size_t)c * n; }
+        g.Min = a.M; g.Iin = a.I;
+        g.Mout = (int16_t*)(base + o_mio); g.Iout = g.Mout + n;
+        par_gather_kernel<<<gf, 256, 0, st>>>(g);
+        CS_CUDA(cudaGetLastError());
+        cs_count_launch(ctx, 3);
+        cs_span_end(ctx, sp);
+        double* outs[8] = {nu, S, A, ga, gs, Epp, na, da};
+        const size_t bo = sizeof(double) * (size_t)nf;
+        for (int c = 0; c < 8; c++) CS_CUDA(cudaMemcpyAsync(outs[c], od + (size_t)c * n, bo, cudaMemcpyDeviceToHost, st));
+        CS_CUDA(cudaMemcpyAsync(M, g.Mout, sizeof(int16_t) * (size_t)nf, cudaMemcpyDeviceToHost, st));
+        CS_CUDA(cudaMemcpyAsync(I, g.Iout, sizeof(int16_t) * (size_t)nf, cudaMemcpyDeviceToHost, st));
+        if (index) CS_CUDA(cudaMemcpyAsync(index, cur, sizeof(int64_t) * (size_t)nf, cudaMemcpyDeviceToHost, st));
+        CS_CUDA(cudaStreamSynchronize(st));
+    }
+    cs_spans_collect(ctx, false);
+    *nout = nf;
     return CS_OK;
 }

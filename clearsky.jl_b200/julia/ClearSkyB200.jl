@@ -161,11 +161,12 @@ cs_par_parse(ctx, nbytes, text, reclen, nrec, M, I, ν, S, A, γa, γs, Epp, na,
           (Ptr{Cvoid}, Int64, Ptr{UInt8}, Int32, Int64, Ptr{Int16}, Ptr{Int16}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
            Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{UInt8}),
           ctx, nbytes, text, reclen, nrec, M, I, ν, S, A, γa, γs, Epp, na, δa, flags)
-cs_par_select(ctx, nrec, M, I, ν, S, νmin, νmax, Scut, nI, Ilist, maxlines, order, nout) =
-    ccall((:cs_par_select, LIB), Int32,
-          (Ptr{Cvoid}, Int64, Ptr{Int16}, Ptr{Int16}, Ptr{Float64}, Ptr{Float64}, Float64, Float64, Float64, Int32, Ptr{Int16},
-           Int64, Ptr{Int64}, Ref{Int64}),
-          ctx, nrec, M, I, ν, S, νmin, νmax, Scut, nI, Ilist, maxlines, order, nout)
+cs_par_read(ctx, nbytes, text, reclen, nrec, νmin, νmax, Scut, nI, Ilist, maxlines, M, I, ν, S, A, γa, γs, Epp, na, δa, index, nout, nbad) =
+    ccall((:cs_par_read, LIB), Int32,
+          (Ptr{Cvoid}, Int64, Ptr{UInt8}, Int32, Int64, Float64, Float64, Float64, Int32, Ptr{Int16}, Int64, Ptr{Int16},
+           Ptr{Int16}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+           Ptr{Float64}, Ptr{Int64}, Ref{Int64}, Ref{Int64}),
+          ctx, nbytes, text, reclen, nrec, νmin, νmax, Scut, nI, Ilist, maxlines, M, I, ν, S, A, γa, γs, Epp, na, δa, index, nout, nbad)
 cs_group_create(ndev, devices, out) =
     ccall((:cs_group_create, LIB), Int32, (Int32, Ptr{Int32}, Ref{Ptr{Cvoid}}), ndev, devices, out)
 cs_group_free(grp) = ccall((:cs_group_free, LIB), Int32, (Ptr{Cvoid},), grp)
@@ -787,20 +788,28 @@ function readpar_b200(filename::String; νmin::Real=0, νmax::Real=Inf, Scut::Re
     M, Iv = zeros(Int16, N), zeros(Int16, N)
     col() = zeros(F64, N)
     ν, S, A, γa, γs, Epp, na, δa = col(), col(), col(), col(), col(), col(), col(), col()
+    index = zeros(Int64, N)
+    nout, nbad = Ref{Int64}(0), Ref{Int64}(0)
+    # readpar's filters (:154-170), the maxlines truncation (:178-185) and the final sort by ν (:187-191) all happen on the
+    # device; only the surviving records come back, in output order
+    Ilist = Int16[i isa Char ? ISOINDEX[i] : Int16(i) for i in I]
+    check(Lib.cs_par_read(ctx.h, Int64(length(text)), text, Int32(reclen), Int64(N), F64(νmin), F64(νmax), F64(Scut),
+                          Int32(length(Ilist)), Ilist, Int64(maxlines), M, Iv, ν, S, A, γa, γs, Epp, na, δa, index, nout, nbad))
+    @assert nbad[] == 0 "malformed numeric field in $filename"
+    k = 1:nout[]
+    # "I" as ISOINDEX numbers; the string columns (Vp, Vpp, ...) can be gathered from `text` with index .+ 1
+    Dict("M" => M[k], "I" => Iv[k], "ν" => ν[k], "S" => S[k], "A" => A[k], "γa" => γa[k], "γs" => γs[k], "Epp" => Epp[k],
+         "na" => na[k], "δa" => δa[k], "record" => index[k] .+ 1)
+end
+# the unfiltered, file-order form (parse loop only, par.jl:127-152)
+function parsepar_b200(text::Vector{UInt8}, reclen::Integer; ctx::Context=context())
+    N = cld(length(text), reclen)
+    M, Iv = zeros(Int16, N), zeros(Int16, N)
+    col() = zeros(F64, N)
+    ν, S, A, γa, γs, Epp, na, δa = col(), col(), col(), col(), col(), col(), col(), col()
     flags = zeros(UInt8, N)
     check(Lib.cs_par_parse(ctx.h, Int64(length(text)), text, Int32(reclen), Int64(N), M, Iv, ν, S, A, γa, γs, Epp, na, δa, flags))
-    @assert !any(!=(0), flags) "malformed numeric field in $filename"
-    # readpar's filters (:154-170), the maxlines truncation (:178-185) and the final sort by ν (:187-191) as one device pass
-    # that returns the surviving records' indices in output order
-    Ilist = Int16[i isa Char ? ISOINDEX[i] : Int16(i) for i in I]
-    order = zeros(Int64, N)
-    nout = Ref{Int64}(0)
-    check(Lib.cs_par_select(ctx.h, Int64(N), M, Iv, ν, S, F64(νmin), F64(νmax), F64(Scut), Int32(length(Ilist)), Ilist,
-                            Int64(maxlines), order, nout))
-    @assert nout[] > 0 "par information has been filtered to nothing!"
-    idx = order[1:nout[]] .+ 1
-    Dict("M" => M[idx], "I" => Iv[idx], "ν" => ν[idx], "S" => S[idx], "A" => A[idx], "γa" => γa[idx], "γs" => γs[idx],
-         "Epp" => Epp[idx], "na" => na[idx], "δa" => δa[idx])
+    (M=M, I=Iv, ν=ν, S=S, A=A, γa=γa, γs=γs, Epp=Epp, na=na, δa=δa, flags=flags)
 end
 
 # =============================================================================================================

@@ -267,6 +267,19 @@ int32_t cs_par_parse(cs_ctx* ctx, int64_t nbytes, const char* text, int32_t recl
                      double* nu, double* S, double* A, double* gamma_a, double* gamma_s, double* Epp, double* na,
                      double* delta_a, uint8_t* flags);
 
+/* readpar(filename; numin, numax, Scut, I, maxlines) (src/hitran/par.jl:91-193) in ONE call: the text goes to the device through
+ * pinned double-buffered staging, is parsed there (as cs_par_parse), filtered (nu in [numin, numax], S >= Scut, isotopologue
+ * in Ilist[nI] given as ISOINDEX numbers; nI = 0 keeps all; :154-170), truncated to the maxlines strongest lines when
+ * maxlines > 0 and nrec > maxlines (reverse(sortperm(S))[1:maxlines], compared against the PRE-filter count like the reference,
+ * :178-185), and sorted by wavenumber with a stable sort on that order (:187-191).  Only the surviving records come back,
+ * in output order: the ten numeric columns (capacity nrec each, *nout valid), index[k] = 0-based file record of output k
+ * (NULL = skip; lets the caller gather the string columns), *nbad = records with a malformed numeric field (NULL = skip).
+ * An empty selection fails with the reference's message (:172). */
+int32_t cs_par_read(cs_ctx* ctx, int64_t nbytes, const char* text, int32_t reclen, int64_t nrec, double numin, double numax,
+                    double Scut, int32_t nI, const int16_t* Ilist, int64_t maxlines, int16_t* M, int16_t* I, double* nu,
+                    double* S, double* A, double* gamma_a, double* gamma_s, double* Epp, double* na, double* delta_a,
+                    int64_t* index, int64_t* nout, int64_t* nbad);
+
 /* ---- single-process multi-GPU: nu-sharded runs from ONE host process --------------------
  * A group owns one context per device and a single-node NCCL communicator (libnccl.so.2 is dlopen'ed on first use).
  * The host shards nu contiguously, drives each device's cs_* calls from its own thread (every call only blocks its

@@ -830,6 +830,19 @@ def test_par_ingestion_bit_exact(cs, tmp_path):
     a, b = cs.readpar(fn, νmin=1000, νmax=3000, Scut=1e-26, I=[1, 2], maxlines=500), \
         cs.readpar_b200(fn, νmin=1000, νmax=3000, Scut=1e-26, I=[1, 2], maxlines=500)
     assert all(np.array_equal(a[k], b[k]) for k in a)
+    # device-side filters / maxlines / sort (cs_par_read) against the host readpar over the keyword combinations, ties in S
+    # and ν included (stable order), and the reference's pre-filter comparison of maxlines
+    for kw in (dict(νmin=600.0, νmax=800.0), dict(Scut=1e-24), dict(I=["1"]), dict(I=[2, "3"], Scut=1e-27),
+               dict(maxlines=100), dict(maxlines=100, νmin=2000.0), dict(maxlines=10**9), dict(νmin=600.0, νmax=2400.0, I=[1], maxlines=7)):
+        for name in ("CO2", "H2O"):
+            fn = os.path.join(DATA, f"{name}.par.gz")
+            a, b = cs.readpar(fn, **kw), cs.readpar_b200(fn, **kw)
+            assert all(a[k].shape == b[k].shape and np.array_equal(a[k], b[k]) for k in a), (name, kw)
+    rec = cs.readpar_b200(fn, νmin=1000.0, maxlines=50, index=True)
+    full, _, _ = cs.parse_records_b200(gzip.open(fn, "rb").read())           # file order
+    assert np.array_equal(full["ν"][rec["record"]], rec["ν"]) and np.array_equal(full["S"][rec["record"]], rec["S"])
+    with pytest.raises(AssertionError, match="filtered to nothing"):
+        cs.readpar_b200(fn, νmin=1e6)
     # exhaustive E10.3 sweep
     recs, vals = [], []
     for e in range(-60, 21):
