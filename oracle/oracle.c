@@ -10,6 +10,10 @@
  * follows the reference source function by function, in the reference's operation order, and is
  * pinned instead by closed-form / high-precision (mpmath) checks, the analytic gray-atmosphere OLR
  * of the reference's disabled test (test/test_gray.jl:15-24), and scipy's wofz (tests/test_oracle*.py).
+ * PIN RECIPE: tools/julia_golden.jl runs the unmodified reference (any machine with Julia) and writes
+ * the .npy files under tests/golden/ref/; tests/test_reference_golden.py then asserts this file against them (faddeyeva
+ * across every region border, the four shapes, bake + OpacityTable, fluxes, CIA, a configs[1] slice)
+ * and reports "PARITY UNPINNED" while that directory is absent -- which it is in this tree.
  *
  * Third-party arithmetic that is NOT in /root/reference and had to be restated from its published
  * algorithm (see DESIGN.md "Oracle"):
@@ -118,7 +122,7 @@ double orc_lorentz(double nu, double nul, double S, double gamma)
  *   3.5  <= |z|^2 (< 107), y^2 < 0.026   Humlicek (1982) w4 region-IV form, exp(u) - t P6(u)/Q7(u)
  *   otherwise                   Hui, Armstrong & Wray (1978) p = 6 rational approximation
  * Each border is where the cheaper form reaches ~1e-4 relative error in the real part (verified
- * against scipy.special.wofz in tests/test_oracle_faddeyeva.py: max rel. err 1.0e-4 over
+ * against scipy.special.wofz in tests/test_oracle_pins.py: max rel. err 1.0e-4 over
  * x in [0,1e5], y in [1e-30,1e5]).  s is formed with an explicit fma so that the CUDA kernel and
  * this oracle take the same branch for the same (x, y).
  */
