@@ -856,6 +856,55 @@ def run_c5(args):
         sys.exit(3)
 
 
+def run_single_process(args):
+    """configs[1] from ONE host process over N GPUs: the host model the Julia wrapper uses.  nu slices
+    balanced by the same cost model, lines uploaded per slice, one thread per device, the library's ncclAllReduce (cs_group.cu)
+    on the 2*np integrated fluxes.  A step is wall-clock timed around sh.fluxes() (the call returns after the reduced fluxes are
+    on the host), so it is an end-to-end number with resident line lists; the kernel times come from the per-context timers."""
+    import clearsky_b200 as cs
+    n = max(1, args.gpus)
+    assert cs.device_count() >= n, f"--gpus {n} but only {cs.device_count()} device(s) visible"
+    wl = make_workload(cs, args.workload)
+    ν, P, T = wl["ν"], wl["P"], wl["T"]
+    # NCCL prints a version banner on stdout when the communicator comes up (first collective); stdout must carry exactly
+    # one JSON line, so file descriptor 1 points at stderr until the warm-up steps are done
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        grp = cs.DeviceGroup(list(range(n)))
+        sh = cs.ShardedLineByLine(grp, [(sl, C, "voigt", wl["cut"]) for sl, C in wl["gases"]], ν)
+        prof = cs.AtmosphericProfile(P, T)
+        total_evals = 0
+        for part in sh.parts:
+            if part is not None:
+                total_evals += sum(g.evals_per_node() for g in part["gases"]) * len(P)
+        for _ in range(max(args.warmup, 3)):
+            Fup, Fdn, Fnet = sh.fluxes(P, wl["g"], prof, wl["μ"])
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+    t0 = [c.timers_total() for c in grp.ctx]
+    with ClockSampler(0) as clk:
+        w0 = time.perf_counter()
+        for _ in range(args.steps):
+            Fup, Fdn, Fnet = sh.fluxes(P, wl["g"], prof, wl["μ"])
+        dt = (time.perf_counter() - w0) / args.steps
+    t1 = [c.timers_total() for c in grp.ctx]
+    ls = [(b["linesum"] - a["linesum"]) / args.steps for a, b in zip(t0, t1)]
+    cfg = workload_config(wl, n, total_evals)
+    cfg["parallelism"] = f"nu-slices x{n}, single process (cs_group: thread per device + library ncclAllReduce)"
+    line = {"metric": METRIC, "value": total_evals / dt, "unit": UNIT, "n_gpus": n, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": cfg, "olr_w_m2": float(Fup[0]), "host_model": "single-process",
+            "timing": "host wall clock around the synchronous group call (includes the all-reduce and the D2H of the fluxes)",
+            "linesum_kernel_ms_per_device": ls, "slice_imbalance_max_over_mean": max(ls) / (sum(ls) / len(ls)),
+            "clocks": clk.summary()}
+    grp.close()
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -869,10 +918,15 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-expansion", action="store_true", help="skip the extra far-field-expansion measurement")
     ap.add_argument("--no-graph", action="store_true", help="c5: plain launches instead of a CUDA graph per step")
+    ap.add_argument("--single-process", action="store_true",
+                    help="c2: drive all --gpus N devices from THIS process through the library's own device group (cs_group_*: one "
+                         "host thread per device, ncclAllReduce inside the library) instead of one torchrun rank per GPU")
     args = ap.parse_args()
     c5 = args.workload.startswith("c5")
     if args.impl == "reference":
         (run_c5_reference if c5 else run_reference)(args)
+    elif args.single_process and not c5:
+        run_single_process(args)
     else:
         (run_c5 if c5 else run_ours)(args)
 

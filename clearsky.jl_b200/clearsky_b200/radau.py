@@ -32,7 +32,8 @@ from .quadrature import lobattonodes, streamnodes
 RADAU_TAU_FLOOR = 1e-9
 REFERENCE_TAU_FLOOR = 1e-6      # discretized.jl:174
 MAX_NODE_BYTES = 6 << 30        # cap on the Σ workspace of one refinement level
-MAX_LEVELS = 1025               # K6 / depth kernel keep per-level tables in shared memory
+MAX_LEVELS = 4097               # K6 keeps (2 + nlobatto)·np doubles of per-level tables in shared memory (its per-warp
+                                # accumulators move to global memory beyond ~600 levels)
 
 
 @dataclass
@@ -52,7 +53,8 @@ def _sigma(A, ν, P, fT, fμ, nlobatto):
 
 
 def _fits(nν, nlev, nlobatto):
-    return nlev <= MAX_LEVELS and nν * ((nlev - 1) * (nlobatto - 1) + 1) * 8 <= MAX_NODE_BYTES
+    return (nlev <= MAX_LEVELS and 8 * ((2 + nlobatto) * nlev + 64) <= 200 * 1024
+            and nν * ((nlev - 1) * (nlobatto - 1) + 1) * 8 <= MAX_NODE_BYTES)
 
 
 def _converged(new, old, tol):

@@ -36,7 +36,8 @@ struct RtArgs {
     double* tau_out;       // optional, Julia tau[i,j] -> i + (np-1)*j
     double* Mup_out;       // optional, Julia M[i,j]  -> i + np*j
     double* Mdn_out;
-    double* part;          // [nblocks][2][np] CTA partial sums (0: up, 1: down)
+    double* part;          // [nblocks][2][np] CTA partial sums (0: up, 1: down); [nblocks*RT_WARPS][2][np] when red_global
+    int red_global;        // 1: per-warp partial sums go straight to `part` (no shared-memory accumulators: lifts the level cap)
 };
 
 __device__ __forceinline__ double warp_sum(double v)
@@ -71,10 +72,20 @@ __global__ void __launch_bounds__(RT_THREADS) rt_kernel(RtArgs a)
     double* srm = sW + ns;      // 1/m_k
     double* red = sm + nsmall;
     for (int t = threadIdx.x; t < nsmall; t += RT_THREADS) sm[t] = a.small[t];
-    for (int t = threadIdx.x; t < 2 * np * RT_WARPS; t += RT_THREADS) red[t] = 0.0;
+    if (!a.red_global)
+        for (int t = threadIdx.x; t < 2 * np * RT_WARPS; t += RT_THREADS) red[t] = 0.0;
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // a warp contributes exactly one partial sum per (direction, level): in shared memory (summed over the warps below) or,
+    // for level counts whose accumulators would not fit, straight in the second stage's input
+    double* gred = a.part + ((size_t)blockIdx.x * RT_WARPS + warp) * 2 * np;
+    auto put = [&](int idx, double r) {
+        if (lane == 0) {
+            if (a.red_global) gred[idx] = r;
+            else red[idx * RT_WARPS + warp] += r;
+        }
+    };
     const int64_t jraw = (int64_t)blockIdx.x * RT_THREADS + threadIdx.x;
     const bool live = jraw < a.nnu;
     const int64_t j = live ? jraw : a.nnu - 1;
@@ -102,8 +113,7 @@ __global__ void __launch_bounds__(RT_THREADS) rt_kernel(RtArgs a)
     double Mdn = beam;                                   // M-[1] = c*fS(nu)   (discretized.jl:299)
     if (a.Mdn_out && live) a.Mdn_out[(size_t)np * j] = Mdn;
     {
-        double r = warp_sum(wj * Mdn);
-        if (lane == 0) red[(np + 0) * RT_WARPS + warp] += r;
+        put(np + 0, warp_sum(wj * Mdn));
     }
     // the end-node cross-section of the NEXT layer is loaded one iteration ahead: the load is the only long-latency
     // operation of the loop and everything after it depends on it
@@ -141,8 +151,7 @@ __global__ void __launch_bounds__(RT_THREADS) rt_kernel(RtArgs a)
         beam *= exp(-tau * rc);                          // discretized.jl:302
         Mdn = Msum + beam;
         if (a.Mdn_out && live) a.Mdn_out[(size_t)np * j + i + 1] = Mdn;
-        double r = warp_sum(wj * Mdn);
-        if (lane == 0) red[(np + i + 1) * RT_WARPS + warp] += r;
+        put(np + i + 1, warp_sum(wj * Mdn));
         Bprev = Bnext;
     }
     // ---- surface: Lambertian reflection + emission (discretized.jl:309-310)
@@ -150,8 +159,7 @@ __global__ void __launch_bounds__(RT_THREADS) rt_kernel(RtArgs a)
     {
         double Mup = Is * CS_PI;
         if (a.Mup_out && live) a.Mup_out[(size_t)np * j + L] = Mup;
-        double r = warp_sum(wj * Mup);
-        if (lane == 0) red[L * RT_WARPS + warp] += r;
+        put(L, warp_sum(wj * Mup));
     }
     // ---- upward
 #pragma unroll
@@ -174,10 +182,10 @@ __global__ void __launch_bounds__(RT_THREADS) rt_kernel(RtArgs a)
             }
         }
         if (a.Mup_out && live) a.Mup_out[(size_t)np * j + i] = Msum;
-        double r = warp_sum(wj * Msum);
-        if (lane == 0) red[i * RT_WARPS + warp] += r;
+        put(i, warp_sum(wj * Msum));
         B1 = B2;
     }
+    if (a.red_global) return;
     __syncthreads();
     for (int t = threadIdx.x; t < 2 * np; t += RT_THREADS) {
         double s = 0.0;
@@ -458,7 +466,12 @@ int32_t fluxes_impl(cs_sigma* s, int64_t np, const double* P, int32_t nlob, cons
     if (fa) CS_CUDA(cudaMemcpyAsync(base + off_fa, fa, sizeof(double) * (size_t)nnu, cudaMemcpyHostToDevice, st));
     CS_TRY(ctx->s_tau.reserve(sizeof(double) * (size_t)L * nnu));
     CS_TRY(ctx->s_planck.reserve(sizeof(double) * (size_t)np * nnu));
-    CS_TRY(ctx->s_part.reserve(sizeof(double) * (size_t)nblocks * 2 * np));
+    // per-CTA tables: the small arrays, plus the per-warp accumulators while they fit; beyond that (Radau-equivalent
+    // refinements with thousands of levels) the warps write their partial sums straight to the second stage's input
+    const size_t smem_small = sizeof(double) * small.size();
+    const bool red_global = smem_small + sizeof(double) * (size_t)2 * np * RT_WARPS > 96 * 1024;
+    const int nparts = red_global ? nblocks * RT_WARPS : nblocks;
+    CS_TRY(ctx->s_part.reserve(sizeof(double) * (size_t)nparts * 2 * np));
     if (tau) CS_TRY(ctx->s_out0.reserve(sizeof(double) * (size_t)L * nnu));
     if (Mup) CS_TRY(ctx->s_out1.reserve(sizeof(double) * (size_t)np * nnu));
     if (Mdn) CS_TRY(ctx->s_out2.reserve(sizeof(double) * (size_t)np * nnu));
@@ -477,7 +490,8 @@ int32_t fluxes_impl(cs_sigma* s, int64_t np, const double* P, int32_t nlob, cons
     a.Mup_out = Mup ? ctx->s_out1.as<double>() : nullptr;
     a.Mdn_out = Mdn ? ctx->s_out2.as<double>() : nullptr;
     a.part = ctx->s_part.as<double>();
-    size_t smem = sizeof(double) * (small.size() + (size_t)2 * np * RT_WARPS);
+    a.red_global = red_global ? 1 : 0;
+    size_t smem = red_global ? smem_small : smem_small + sizeof(double) * (size_t)2 * np * RT_WARPS;
     CS_REQUIRE(smem <= 200 * 1024, CS_ERR_ARG, "too many pressure levels for one flux call (%lld): per-CTA tables need %zu bytes", (long long)np, smem);
 
     const int sp_rt = cs_span_begin(ctx, CS_T_RT, true);
@@ -495,7 +509,7 @@ int32_t fluxes_impl(cs_sigma* s, int64_t np, const double* P, int32_t nlob, cons
     cs_span_end(ctx, sp_rt);
     const int sp_red = cs_span_begin(ctx, CS_T_REDUCE, true);
     double* dF = d_F ? d_F : (double*)(base + off_F);
-    flux_reduce_kernel<<<(2 * (int)np + 3) / 4, 128, 0, st>>>(a.part, nblocks, 2 * (int)np, dF);
+    flux_reduce_kernel<<<(2 * (int)np + 3) / 4, 128, 0, st>>>(a.part, nparts, 2 * (int)np, dF);
     CS_CUDA(cudaGetLastError());
     cs_count_launch(ctx);
     cs_span_end(ctx, sp_red);
@@ -603,7 +617,7 @@ extern "C" int32_t cs_fluxes_batch(cs_sigma* s, int64_t np, const double* P, int
     a.cos_s = cos(theta_s);
     a.tau_floor = ctx->tau_floor;
     a.tau_s = ctx->s_tau.as<double>(); a.B_s = nullptr;
-    a.tau_out = nullptr; a.Mup_out = nullptr; a.Mdn_out = nullptr; a.part = nullptr;
+    a.tau_out = nullptr; a.Mup_out = nullptr; a.Mdn_out = nullptr; a.part = nullptr; a.red_global = 0;
     ba.B_b = ctx->s_planck.as<double>();
     ba.part_b = ctx->s_part.as<double>();
     const size_t smem = sizeof(double) * (small.size() + (size_t)RTB_NB * np + (size_t)RTB_NB * 2 * np * RT_WARPS);

@@ -649,14 +649,29 @@ def test_full_size_properties_c2(cs):
     assert relerr(tot[:nlev], Fu) < 1e-12 and relerr(tot[nlev + 1:], Fd[1:]) < 1e-12
 
 
-def test_table_export_import_roundtrip(cs, co2):
-    """cs_table_block -> cs_table_from_block reproduces the table (persistence path)"""
+def test_table_export_import_roundtrip(cs, orc, co2):
+    """cs_table_block -> cs_table_from_block (persistence path) against the ORACLE, not against
+    itself: the exported block equals orc.bake (what the reference hands to OpacityTable, gases.jl:109-144, zero-mixing
+    repair included), and a table re-imported from that block evaluates like orc.table_fit + orc.gas_nodes on it"""
     import ctypes as C
     from clearsky_b200._lib import check, f64, lib, ptr
     ν, P, Γ = c1_problem(cs, nν=400)
     Ω = cs.AtmosphericDomain((140, 300), 9, (5, 1.1e5), 11)
     gas = cs.Gas(co2, 400e-6, ν, Ω, keep_block=True)
     blk = gas.σblock()
+    oblk, onz = orc.bake(orc.VOIGT, co2, ν, Ω.T, Ω.P, np.full((Ω.nP, Ω.nT), 400e-6), 25.0, nthreads=0)
+    assert np.asarray(blk).reshape(oblk.shape).shape == oblk.shape
+    assert relerr(np.asarray(blk).reshape(oblk.shape), oblk, 1e-290) < XSEC_TOL
+    assert np.array_equal(np.asarray(blk).reshape(oblk.shape) == 0, oblk == 0) and gas.nzeroed == onz
+    Tq, Pq = Γ(P), P
+    want = orc.gas_nodes(orc.table_fit(oblk), Ω.T, Ω.P, Tq, Pq, np.ones(len(Pq)))
+    # a block that did not come from this library at all: the oracle's, handed to cs_table_from_block like a Julia caller would
+    h2 = C.c_void_p()
+    check(lib().cs_table_from_block(gas.ctx.h, len(ν), Ω.nT, ptr(f64(Ω.T)), Ω.nP, ptr(f64(Ω.P)), ptr(f64(oblk)), C.byref(h2)))
+    out2 = np.empty((len(P), len(ν)))
+    check(lib().cs_table_eval(h2, len(P), ptr(f64(Tq)), ptr(f64(Pq)), ptr(out2)))
+    lib().cs_table_free(h2)
+    assert relerr(out2, want, 1e-290) < XSEC_TOL
     h = C.c_void_p()
     check(lib().cs_table_from_block(gas.ctx.h, len(ν), Ω.nT, ptr(f64(Ω.T)), Ω.nP, ptr(f64(Ω.P)), ptr(f64(blk)), C.byref(h)))
     T = Γ(P)
@@ -664,6 +679,7 @@ def test_table_export_import_roundtrip(cs, co2):
     check(lib().cs_table_eval(h, len(P), ptr(f64(T)), ptr(f64(P)), ptr(out)))
     lib().cs_table_free(h)
     assert relerr(out, gas.rawσ(T, P), 1e-300) < 1e-13
+    assert relerr(out, want, 1e-290) < XSEC_TOL
 
 
 def test_phco2_all_chi_classes(cs, orc):
@@ -784,6 +800,30 @@ def test_sharded_tables_and_rcm(cs, co2, h2o):
     assert relerr(a.T, b.T) < 1e-12 and np.max(np.abs(a.H - b.H)) < 1e-9 * np.max(np.abs(b.H))
     a.close()
     del a, sh
+    grp.close()
+
+
+def test_group_spans_distinct_gpus(cs, co2):
+    """driver-visible proof of the library's own NCCL path (cs_group.cu: ncclAllReduce over the group's communicator): needs two
+    DISTINCT devices, so it is skipped on a one-GPU box (`gpurun --gpus 2 -- python -m pytest tests -m gpu -k distinct_gpus`).
+    nu-sharded fluxes through the group equal the one-device run, and after the call EVERY device's buffer holds the same reduced
+    sums (each started from its own slice's partial integrals)."""
+    ndev = cs.device_count()
+    if ndev < 2:
+        pytest.skip("needs >= 2 GPUs")
+    grp = cs.DeviceGroup(list(range(ndev)))
+    assert len(set(grp.devices)) == ndev
+    ν = np.linspace(500.0, 900.0, 4001)
+    P = cs.pressuregrid(10.0, 1e5, 16)
+    Γ = cs.DryAdiabat(288.0, 1e5, 1040.0, 0.029, Ptropo=1e4)
+    Fup, Fdn, Fnet = cs.sharded_fluxes(grp, P, 9.8, Γ, 0.029, None, None, [(co2, 400e-6, "voigt", 25.0)], ν)
+    F = cs.radiate(P, 9.8, Γ, 0.029, None, None, cs.LineGas(co2, 400e-6, ν, "voigt", 25.0))
+    assert relerr(Fup, F.Fup) < 1e-12 and relerr(Fdn[1:], F.Fdn[1:]) < 1e-12
+    # every device's reduced buffer holds the same sums
+    got = [grp.read(i, 2 * len(P)) for i in range(ndev)]
+    for g in got[1:]:
+        assert np.array_equal(g, got[0])
+    assert relerr(got[0][:len(P)], F.Fup) < 1e-12
     grp.close()
 
 
@@ -911,6 +951,35 @@ def test_extreme_cutoffs_and_sizes(cs, orc, co2):
     ref = orc.fluxes(ν2, P4, 2, w, np.full((400, 2), 0.029), Γ(P4), np.full((401, len(ν2)), 3e-26), 9.8, None, None, 0.841, 5, m, W,
                      full=False)
     assert relerr(Fup, ref["Fup"]) < FLUX_TOL and relerr(Fdn[1:], ref["Fdn"][1:]) < FLUX_TOL
+
+
+def test_thousands_of_levels_vs_oracle(cs, orc, co2):
+    """the flux solver beyond the former 1025-level cap (per-warp partial sums in global memory): 2049 levels with 4-point
+    Lobatto layers on a real-gas table, monochromatic and integrated fluxes against the oracle's Discretized solve of the
+    same refined grid (the grid the Radau-equivalent entry points refine to)"""
+    ν = np.linspace(600.0, 760.0, 161)
+    Γ = cs.DryAdiabat(288.0, 1e5, 1040.0, 0.029, Ptropo=1e4)
+    Ω = cs.AtmosphericDomain((140, 300), 8, (5, 1.1e5), 12)
+    gas = cs.Gas(co2, 400e-6, ν, Ω, "voigt", 25.0)
+    P = np.exp(np.linspace(np.log(10.0), np.log(1e5), 2049))
+    fS, fa = (lambda x: 0.05 + 0 * x), 0.2
+    Mup, Mdn = cs.monochromaticfluxes(P, 9.8, Γ, 0.029, fS, fa, gas, core=cs.Discretized(5, 4))
+    Fup, Fdn = cs.fluxes(P, 9.8, Γ, 0.029, fS, fa, gas, core=cs.Discretized(5, 4))
+    m, W = cs.streamnodes(5)
+    x, w = cs.lobattonodes(4)
+    Pn = P[:-1, None] + np.diff(P)[:, None] * x[None, :]
+    nodesP = np.concatenate([Pn[:, :-1].ravel(), P[-1:]])
+    ws = cs.SigmaWorkspace(ν, len(nodesP))
+    cs.UnifiedAbsorber(gas).sigma_nodes(ws, Γ(nodesP), nodesP)
+    ref = orc.fluxes(ν, P, 4, w, np.full((len(P) - 1, 4), 0.029), Γ(P), ws.read(), 9.8, np.full(len(ν), 0.05), np.full(len(ν), 0.2),
+                     0.841, 5, m, W, nthreads=0)
+    assert relerr(Mup, ref["Mup"], 1e-300) < FLUX_TOL and relerr(Mdn, ref["Mdn"], 1e-300) < FLUX_TOL
+    assert relerr(Fup, ref["Fup"]) < FLUX_TOL and relerr(Fdn, ref["Fdn"]) < FLUX_TOL
+    # and the refinement of the Radau-equivalent `outgoing` now reaches its tolerance instead of stopping at the cap
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        cs.outgoing(1e5, 9.8, Γ, 0.029, gas, Ptop=10.0, tol=1e-5)
 
 
 def test_bench_line_contract(cs):
