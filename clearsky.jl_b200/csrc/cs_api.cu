@@ -73,6 +73,7 @@ static int32_t ctx_create(int32_t device, void* stream, bool own, cs_ctx** out)
         c->farfield = (strcmp(ff, "expansion") == 0) ? CS_FARFIELD_EXPANSION : CS_FARFIELD_DIRECT;
     c->ff_no_moments = getenv("CS_FARFIELD_NO_MOMENTS") != nullptr;
     c->table_no_mma = getenv("CS_TABLE_EVAL_NO_MMA") != nullptr;
+    c->table_no_fused = getenv("CS_TABLE_FIT_NO_FUSED") != nullptr;
     {
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {

@@ -128,6 +128,7 @@ struct cs_ctx {
     int stage_next = 0;
     bool ff_no_moments = false;            // CS_FARFIELD_NO_MOMENTS, read once at context creation
     bool table_no_mma = false;             // CS_TABLE_EVAL_NO_MMA, likewise
+    bool table_no_fused = false;           // CS_TABLE_FIT_NO_FUSED: two-pass GEMM fit instead of the fused single sweep
     int64_t launches = 0;   // number of kernels of this library launched on this context
     int32_t farfield = CS_FARFIELD_DIRECT;   // K2 far-wing treatment (cs_ctx_set_farfield)
     double tau_floor = 1e-6;                 // K6 floor on the vertical layer depth (cs_ctx_set_tau_floor)

@@ -183,7 +183,8 @@ struct LineSumArgs {
     const LevelParams* lev;
     double cut;
     double* out;            // [nlev][nnu]
-    int accumulate;         // 0: out = scale*sigma (surf! overwrites), 1: out += scale*sigma
+    int accumulate;         // 0: out = scale*sigma (surf! overwrites), 1: out += scale*sigma, 2: out = log(scale*sigma) (bake: the
+                            // table fit wants ln sigma, gases.jl:75-81, and one log per output point is free here)
     int64_t ntiles;
     int nr;                 // entries per tile in ranges (6, 8 with the far-field expansion, or LS_NR for PHCO2)
     const int64_t* ranges;  // [ntiles][nr], see tile_ranges_kernel
@@ -1505,7 +1506,7 @@ __global__ void __launch_bounds__(LS_THREADS, CS_LS_MINBLK / LS_WARPS) line_sum_
         if (i < a.nnu) {
             size_t o = (size_t)lev * a.nnu + i;
             double v = lp.scale * (acc[r] + w.cacc[32 * r + lane]);
-            a.out[o] = a.accumulate ? a.out[o] + v : v;
+            a.out[o] = a.accumulate == 1 ? a.out[o] + v : (a.accumulate == 2 ? log(v) : v);
         }
     }
 }
@@ -1603,6 +1604,11 @@ __global__ void __launch_bounds__(256) line_params_kernel(PrepArgs a, double* S_
     if (gamma) gamma[j] = (pow(CS_TREF / T, a.na[j])) * (a.ga[j] * (lp.P - lp.Pp) + a.gs[j] * lp.Pp) / CS_ATM;
 }
 
+__global__ void fill_kernel(double* p, size_t n, double v)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
 }  // namespace
 
 extern "C" int32_t cs_line_params(cs_lines* L, double T, double P, double Pp, double* S_T, double* alpha, double* gamma)
@@ -1659,7 +1665,11 @@ int32_t cs_lines_accumulate(cs_lines* L, int32_t shape, int64_t nnu, const doubl
 
     cudaStream_t st = ctx->stream;
     if (nl == 0) {
-        if (!accumulate) CS_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double) * (size_t)nnu * nlev, st));
+        if (accumulate == 0) CS_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double) * (size_t)nnu * nlev, st));
+        if (accumulate == 2) {      // log(0): every byte 0xFF would be a NaN, so fill -inf explicitly
+            fill_kernel<<<1024, 256, 0, st>>>(d_out, (size_t)nnu * nlev, -INFINITY);
+            CS_CUDA(cudaGetLastError());
+        }
         return CS_OK;
     }
     // level batches sized so that the per-level records stay within a fixed HBM budget

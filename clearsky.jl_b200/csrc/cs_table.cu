@@ -334,6 +334,174 @@ __global__ void __launch_bounds__(32 * 17, 1) table_eval_mma_kernel(const double
     }
 }
 
+// ---- K3 fused: the whole table fit of 8 wavenumbers in ONE pass over HBM.
+// The fit is lnsigma[i + nT j][nu] -> coef[i + nT j][nu] = sum_{i', j'} Mx[i][i'] My[j][j'] lnsigma[i' + nT j'][nu] (2-D Chebyshev
+// transform, gases.jl:75-81 via BichebyshevInterpolator), with the zero-mixing repair (gases.jl:131-142) and the all-zero rule
+// (:75-81) applied first.  As two separable GEMM passes over the block it costs 4 sweeps of HBM plus 3 for the log / repair
+// pass (140 GB on configs[3], 61 ms); here a CTA owns 8 wavenumbers, keeps their whole [nT*nP] x 8 slab in shared memory
+// (nP (nT|1) 64 B = 163 KB for 50 x 50), and does log, repair flags, T pass (in place, one j block per warp) and P pass
+// (straight to global memory) on it: the block is read once and the coefficients written once (40 GB).  Both passes run on the
+// FP64 tensor pipe (mma.sync.m8n8k4.f64: M = the 8 wavenumbers, N = output index, K = input index), A fragments from the slab
+// and B fragments from padded copies of Mx^T / My^T.  A 64-bit fragment load is served per half warp (4 k rows x 4 columns), so
+// the four rows must fall in four different bank groups: slab rows are 8 doubles wide and swizzled (columns 0-3 and 4-7 swap in
+// rows with bit 1 set), j blocks are nTp = nT|1 rows apart (the P pass' four rows, nTp apart, are then distinct mod 4), and the
+// matrix rows are padded to a pitch of 8 NT8 + 4 doubles.  2 (nT + nP) nT nP FMAs
+// per wavenumber = 5e11 flop on configs[3]: the kernel is bound by the FP64 tensor pipe, not by HBM.
+constexpr int FF_V = 8;            // wavenumbers per CTA (= M of the MMA)
+constexpr int FF_MAXT = CS_MAX_NODES / 8;
+struct FitArgs {
+    const double* blk;      // [nk][nnu] sigma (is_log = 0) or ln sigma (is_log = 1)
+    double* coef;           // [nk][nnu]
+    const double* MxT;      // [4 KT][8 NT8 + 4] zero padded: MxT[q][o] = Mx[o][q]
+    const double* MyT;      // [4 KP][8 NP8 + 4]
+    unsigned long long* nzeroed;
+    int64_t nnu;
+    int nT, nP, nTp, is_log;
+};
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
+}
+
+__global__ void __launch_bounds__(800, 1) table_fit_fused_kernel(FitArgs a)
+{
+    extern __shared__ __align__(128) double fs[];
+    __shared__ int sflag[2][FF_V];
+    const int nT = a.nT, nP = a.nP, nTp = a.nTp;
+    const int KT = (nT + 3) / 4, KP = (nP + 3) / 4, NT8 = (nT + 7) / 8, NP8 = (nP + 7) / 8;
+    const int ldx = 8 * NT8 + 4, ldy = 8 * NP8 + 4;          // matrix row pitches (= 4 or 12 mod 16 doubles)
+    double* slab = fs;                                       // [nP][nTp][8], row r holds column c at r*8 + (c ^ ((r & 2) << 1))
+    double* sMx = slab + (size_t)nP * nTp * FF_V;            // [4 KT][ldx]
+    double* sMy = sMx + (size_t)4 * KT * ldx;                // [4 KP][ldy]
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int warp = tid >> 5, lane = tid & 31, nwarp = nthr >> 5;
+    const int fr = lane >> 2, fk = lane & 3;
+    const int part = lane & 3;                               // a lane always loads the same pair of wavenumbers
+    const int64_t ntile = (a.nnu + FF_V - 1) / FF_V;
+    const double lt = log(TINY);
+
+    // The CTA is persistent.  A warp owns the T indices i = warp, warp + nwarp, ..: it loads the rows (i, all j) of a tile,
+    // and as soon as its P pass is done with them it loads the same rows of the CTA's NEXT tile into the same place, so the
+    // next tile's HBM reads overlap this tile's P pass and its stores.
+    auto load_rows = [&](int i, int64_t tile) {
+        const int64_t v0 = tile * FF_V;
+        const int nv = (int)min((int64_t)FF_V, a.nnu - v0);
+        for (int c = lane; c < 4 * nP; c += 32) {
+            const int j = c >> 2, r = j * nTp + i;
+            double* dst = slab + ((size_t)r * FF_V + ((2 * part) ^ ((r & 2) << 1)));
+            if (2 * part < nv) cp_async16(dst, a.blk + ((size_t)i + (size_t)nT * j) * a.nnu + v0 + 2 * part);
+            else { dst[0] = 0.0; dst[1] = 0.0; }
+        }
+    };
+    if (tid < 2 * FF_V) (&sflag[0][0])[tid] = 0;
+    int64_t tile = blockIdx.x;
+    if (tile < ntile)
+        for (int i = warp; i < nT; i += nwarp) load_rows(i, tile);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    for (int c = tid; c < 4 * KT * ldx; c += nthr) sMx[c] = a.MxT[c];
+    for (int c = tid; c < 4 * KP * ldy; c += nthr) sMy[c] = a.MyT[c];
+    __syncthreads();
+
+    for (int it = 0; tile < ntile; tile += gridDim.x, it ^= 1) {
+        const int64_t v0 = tile * FF_V;
+        const int nv = (int)min((int64_t)FF_V, a.nnu - v0);   // even (nnu is even), >= 2
+        int* flg = sflag[it];
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        // ---- log + repair flags on the lane's own chunks (bit 0: a zero, bit 1: a positive value, bit 2: a value > floatmin)
+        if (2 * part < nv) {
+            int f0 = 0, f1 = 0;
+            for (int i = warp; i < nT; i += nwarp) {
+                for (int c = lane; c < 4 * nP; c += 32) {
+                    const int j = c >> 2, r = j * nTp + i;
+                    double2* q = reinterpret_cast<double2*>(slab + ((size_t)r * FF_V + ((2 * part) ^ ((r & 2) << 1))));
+                    double2 x = *q;
+                    if (a.is_log) {
+                        f0 |= (x.x == -INFINITY ? 1 : 2) | (x.x > lt ? 4 : 0);
+                        f1 |= (x.y == -INFINITY ? 1 : 2) | (x.y > lt ? 4 : 0);
+                    } else {
+                        f0 |= (x.x == 0.0 ? 1 : 0) | (x.x > 0.0 ? 2 : 0) | (x.x > TINY ? 4 : 0);
+                        f1 |= (x.y == 0.0 ? 1 : 0) | (x.y > 0.0 ? 2 : 0) | (x.y > TINY ? 4 : 0);
+                        x.x = log(x.x);
+                        x.y = log(x.y);
+                        *q = x;
+                    }
+                }
+            }
+            atomicOr(&flg[2 * part], f0);
+            atomicOr(&flg[2 * part + 1], f1);
+        }
+        __syncthreads();
+        if (tid < FF_V) {
+            sflag[it ^ 1][tid] = 0;                          // the other buffer was last read in the previous tile's P pass
+            if (tid < nv && (flg[tid] & 3) == 3) atomicAdd(a.nzeroed, 1ULL);     // min == 0 < max: zero-mixing (gases.jl:131-142)
+        }
+        // ---- T pass, in place: one j block per warp at a time (nobody else touches the block)
+        for (int j = warp; j < nP; j += nwarp) {
+            const int r0 = j * nTp;
+            double acc[FF_MAXT][2];
+#pragma unroll
+            for (int t = 0; t < FF_MAXT; t++) acc[t][0] = acc[t][1] = 0.0;
+            for (int ks = 0; ks < KT; ks++) {
+                const int k = 4 * ks + fk;
+                const int r = r0 + k;
+                const double av = (k < nT) ? slab[(size_t)r * FF_V + (fr ^ ((r & 2) << 1))] : 0.0;
+                const double* brow = sMx + (size_t)k * ldx + fr;
+#pragma unroll
+                for (int t = 0; t < FF_MAXT; t++)
+                    if (t < NT8) dmma884(acc[t][0], acc[t][1], av, brow[8 * t]);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int t = 0; t < FF_MAXT; t++) {
+                if (t < NT8) {
+                    const int o = 8 * t + 2 * fk;
+                    const int r = r0 + o;
+                    if (o < nT) slab[(size_t)r * FF_V + (fr ^ ((r & 2) << 1))] = acc[t][0];
+                    if (o + 1 < nT) slab[(size_t)(r + 1) * FF_V + (fr ^ (((r + 1) & 2) << 1))] = acc[t][1];
+                }
+            }
+        }
+        __syncthreads();
+        // ---- P pass: unit = T index i; output straight to the coefficient block, with the repaired columns replaced by the
+        // transform of the constant log(floatmin): c00 = log(floatmin), everything else 0
+        const int fl = flg[fr];
+        const bool repaired = ((fl & 3) == 3) || !(fl & 4);
+        const bool vok = v0 + fr < a.nnu;
+        const int64_t next = tile + gridDim.x;
+        for (int i = warp; i < nT; i += nwarp) {
+            double acc[FF_MAXT][2];
+#pragma unroll
+            for (int t = 0; t < FF_MAXT; t++) acc[t][0] = acc[t][1] = 0.0;
+            for (int ks = 0; ks < KP; ks++) {
+                const int k = 4 * ks + fk;
+                const int r = k * nTp + i;
+                const double av = (k < nP) ? slab[(size_t)r * FF_V + (fr ^ ((r & 2) << 1))] : 0.0;
+                const double* brow = sMy + (size_t)k * ldy + fr;
+#pragma unroll
+                for (int t = 0; t < FF_MAXT; t++)
+                    if (t < NP8) dmma884(acc[t][0], acc[t][1], av, brow[8 * t]);
+            }
+            __syncwarp();                                    // every lane has read the rows (i, .): they can be overwritten
+            if (next < ntile) load_rows(i, next);
+#pragma unroll
+            for (int t = 0; t < FF_MAXT; t++) {
+                if (t < NP8) {
+#pragma unroll
+                    for (int c = 0; c < 2; c++) {
+                        const int o = 8 * t + 2 * fk + c;
+                        if (o < nP && vok) {
+                            const double val = repaired ? ((i == 0 && o == 0) ? lt : 0.0) : acc[t][c];
+                            a.coef[((size_t)i + (size_t)nT * o) * a.nnu + v0 + fr] = val;
+                        }
+                    }
+                }
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+}
+
 // ---- accelerated absorber
 __global__ void accel_snapshot_kernel(const double* sig, double* lnsig, size_t n)
 {
@@ -466,8 +634,19 @@ int32_t check_grid(int32_t nT, const double* Tg, int32_t nP, const double* Pg)
     return CS_OK;
 }
 
-// fit coefficients from a device sigma block [nk][nnu] (destroyed: becomes ln sigma)
-int32_t fit_table(cs_ctx* ctx, cs_table* tb, double* d_block)
+// does the single-sweep fused fit apply?  (even nnu for 16-byte row alignment, slab of 8 wavenumbers within shared memory)
+size_t fused_fit_smem(int nT, int nP)
+{
+    const int KT = (nT + 3) / 4, KP = (nP + 3) / 4, NT8 = (nT + 7) / 8, NP8 = (nP + 7) / 8, nTp = nT | 1;
+    return sizeof(double) * ((size_t)nP * nTp * FF_V + (size_t)4 * KT * (8 * NT8 + 4) + (size_t)4 * KP * (8 * NP8 + 4));
+}
+bool fit_is_fused(const cs_ctx* ctx, int64_t nnu, int nT, int nP)
+{
+    return nnu % 2 == 0 && !ctx->table_no_mma && !ctx->table_no_fused && fused_fit_smem(nT, nP) <= 227 * 1024 - 256;
+}
+
+// fit coefficients from a device block [nk][nnu] of sigma, or of ln sigma when block_is_log (destroyed either way)
+int32_t fit_table(cs_ctx* ctx, cs_table* tb, double* d_block, bool block_is_log = false)
 {
     cudaStream_t st = ctx->stream;
     const int nT = tb->nT, nP = tb->nP, nk = nT * nP;
@@ -494,6 +673,41 @@ int32_t fit_table(cs_ctx* ctx, cs_table* tb, double* d_block)
     CS_CUDA(cudaMemcpyAsync(base + offyt, MyT.data(), MyT.size() * sizeof(double), cudaMemcpyHostToDevice, st));
     CS_CUDA(cudaMemsetAsync(base + offc, 0, 8, st));
     const int sp_fit = cs_span_begin(ctx, CS_T_TABLE_FIT, false);
+    // fused single-sweep fit when the slab of 8 wavenumbers fits in shared memory (any grid up to about 56 x 56)
+    {
+        const int KT = (nT + 3) / 4, KP = (nP + 3) / 4, NT8 = (nT + 7) / 8, NP8 = (nP + 7) / 8, nTp = nT | 1;
+        const int ldx = 8 * NT8 + 4, ldy = 8 * NP8 + 4;
+        const size_t nMx = (size_t)4 * KT * ldx, nMy = (size_t)4 * KP * ldy;
+        const size_t smf = fused_fit_smem(nT, nP);
+        if (fit_is_fused(ctx, nnu, nT, nP)) {
+            std::vector<double> pad(nMx + nMy, 0.0);
+            for (int o = 0; o < nT; o++)
+                for (int q = 0; q < nT; q++) pad[(size_t)q * ldx + o] = Mx[(size_t)o * nT + q];
+            for (int o = 0; o < nP; o++)
+                for (int q = 0; q < nP; q++) pad[nMx + (size_t)q * ldy + o] = My[(size_t)o * nP + q];
+            CS_TRY(ctx->s_w.reserve(pad.size() * sizeof(double)));
+            CS_CUDA(cudaMemcpyAsync(ctx->s_w.p, pad.data(), pad.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+            FitArgs fa;
+            fa.blk = d_block; fa.coef = tb->coef; fa.MxT = ctx->s_w.as<double>(); fa.MyT = ctx->s_w.as<double>() + nMx;
+            fa.nzeroed = (unsigned long long*)(base + offc); fa.nnu = nnu; fa.nT = nT; fa.nP = nP; fa.nTp = nTp;
+            fa.is_log = block_is_log ? 1 : 0;
+            CS_CUDA(cudaFuncSetAttribute(table_fit_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smf));
+            int nsm = 0;
+            CS_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device));
+            const int64_t ntile = (nnu + FF_V - 1) / FF_V;
+            table_fit_fused_kernel<<<(unsigned)std::min<int64_t>(ntile, nsm), 800, smf, st>>>(fa);   // persistent: 1 CTA per SM
+            CS_CUDA(cudaGetLastError());
+            cs_count_launch(ctx, 1);
+            cs_span_end(ctx, sp_fit);
+            unsigned long long nzf = 0;
+            CS_CUDA(cudaMemcpyAsync(&nzf, base + offc, 8, cudaMemcpyDeviceToHost, st));
+            CS_CUDA(cudaStreamSynchronize(st));
+            cs_spans_collect(ctx, false);
+            tb->nzeroed = (int64_t)nzf;
+            return CS_OK;
+        }
+    }
+    CS_REQUIRE(!block_is_log, CS_ERR_ARG, "internal: the two-pass table fit expects a sigma block");
     unsigned nb = (unsigned)((nnu + 255) / 256);
     table_log_kernel<<<nb, 256, 0, st>>>(d_block, nnu, nk, (unsigned long long*)(base + offc));
     CS_CUDA(cudaGetLastError());
@@ -693,10 +907,14 @@ extern "C" int32_t cs_bake(cs_lines* L, int32_t shape, int64_t nnu, const double
         return CS_ERR_NOMEM;
     }
     int32_t rc = ctx->s_nu.reserve(sizeof(double) * (size_t)nnu);
+    bool want_log = false;
     if (!rc) {
         cudaMemcpyAsync(ctx->s_nu.p, nu, sizeof(double) * (size_t)nnu, cudaMemcpyHostToDevice, ctx->stream);
+        // the fused fit reads ln sigma: let the line sum write it directly (one log per output point is free there),
+        // unless the caller wants the sigma block kept
+        want_log = !keep_block && fit_is_fused(ctx, nnu, nT, nP);
         rc = cs_lines_accumulate(L, shape, nnu, ctx->s_nu.as<double>(), nu, nk, T.data(), P.data(), Pp.data(), nullptr,
-                                 cut, blk, 0);
+                                 cut, blk, want_log ? 2 : 0);
     }
     if (!rc && keep_block) {
         // keep sigma with the zero-mixing repair applied, exactly what bake hands to OpacityTable
@@ -709,7 +927,7 @@ extern "C" int32_t cs_bake(cs_lines* L, int32_t shape, int64_t nnu, const double
             cs_count_launch(ctx);
         }
     }
-    if (!rc) rc = fit_table(ctx, tb, blk);
+    if (!rc) rc = fit_table(ctx, tb, blk, want_log);
     cs_free(blk, ctx->stream);
     if (rc) { cs_table_free(tb); return rc; }
     *out = tb;
