@@ -34,23 +34,11 @@
 
 namespace {
 
-#ifndef CS_LS_QUAD
-#define CS_LS_QUAD 1
-#endif
 #ifndef CS_LS_FOLD
 #define CS_LS_FOLD 16
 #endif
-#ifndef CS_LS_DYNREM
-#define CS_LS_DYNREM 1
-#endif
 #ifndef CS_LS_MINBLK
 #define CS_LS_MINBLK 16
-#endif
-#ifndef CS_LS_EDGE          // far-wing edge lines: 0 = quad loop with FP64 predicates, 1 = hot-loop fold with index ranges, 2 = per slice
-#define CS_LS_EDGE 0
-#endif
-#ifndef CS_LS_NEAR          // near lines (Voigt): 0 = per tile, 2 = per slice
-#define CS_LS_NEAR 0
 #endif
 #ifndef CS_LS_WARPS
 #define CS_LS_WARPS 1
@@ -353,7 +341,6 @@ struct WarpCold {
     uint32_t* queue;           // [LS_QCAP] deferred (line, point) pairs
     const double4* slow_lev;   // near-centre parameters of this level, from the first line of the window (global)
     double cut, B1, B2;
-    double cn;                 // near-centre half width of THIS level as a fraction of the line position (LevelParams::cnear)
     int lane;
     bool edge_is_far;
 };
@@ -432,260 +419,6 @@ __device__ __forceinline__ void fold_tail(const double4* __restrict__ st, int& j
     }
 #pragma unroll
     for (int r = 0; r < R; r++) acc[r] = fma(fn[r], cs_rcp(fd[r]), acc[r]);
-}
-
-// ---- per-slice refinement of the cold classes --------------------------------------------------------------------------
-// The tile-level classes (edge, near) are decided for the whole 32*R-point tile, so most of their (line, point) pairs do not
-// need the expensive form: an "edge" line is inside the cut-off for ALL points of some 32-point slices and for NONE of others,
-// a "near" line is safely in the far wing for the slices that lie away from its centre.  The R points of a lane lie in R
-// different slices, so a per-(line, slice) decision is warp-uniform, and because the lines are sorted every such decision is
-// a monotone predicate of the line index: the lines that need the expensive form for slice r are ONE contiguous sub-range.
-// The sub-ranges are found with ballots (32 lines per round), then each slice runs cheap folds over the lines outside its
-// sub-range (one point per lane, CS_LS_FOLD-style groups of 8) and the expensive form only inside it.
-
-// sum over lines [l0, l1) of K/(dnu^2 + g^2) for ONE point per lane: groups of 8 lines per reciprocal, folded left to right
-__device__ __forceinline__ double fold_far(const double4* __restrict__ st, int l0, int l1, double nu)
-{
-    double acc = 0.0;
-    int j = l0;
-    for (; j + 7 < l1; j += 8) {
-        const double4 ra = st[j];
-        const double da = nu - ra.x;
-        double fd = fma(da, da, ra.y), fn = ra.z;
-#pragma unroll
-        for (int g = 1; g < 8; g++) {
-            const double4 rb = st[j + g];
-            const double db = nu - rb.x;
-            const double qb = fma(db, db, rb.y);
-            fn = fma(rb.z, fd, fn * qb);
-            fd *= qb;
-        }
-        acc = fma(fn, cs_rcp(fd), acc);
-    }
-    if (j < l1) {
-        const double4 ra = st[j];
-        const double da = nu - ra.x;
-        double fd = fma(da, da, ra.y), fn = ra.z;
-#pragma unroll 1
-        for (j++; j < l1; j++) {
-            const double4 rb = st[j];
-            const double db = nu - rb.x;
-            const double qb = fma(db, db, rb.y);
-            fn = fma(rb.z, fd, fn * qb);
-            fd *= qb;
-        }
-        acc = fma(fn, cs_rcp(fd), acc);
-    }
-    return acc;
-}
-
-// the same with the inclusive cut-off predicate of line_shapes.jl:10 folded into the numerators (K -> 0 outside the window)
-__device__ __forceinline__ double fold_far_cut(const double4* __restrict__ st, int l0, int l1, double nu, double cut)
-{
-    double acc = 0.0;
-    int j = l0;
-    while (j < l1) {
-        const int je = min(j + 8, l1);
-        const double4 ra = st[j];
-        const double da = nu - ra.x;
-        double fd = fma(da, da, ra.y), fn = (fabs(da) > cut) ? 0.0 : ra.z;
-#pragma unroll 1
-        for (j++; j < je; j++) {
-            const double4 rb = st[j];
-            const double db = nu - rb.x;
-            const double qb = fma(db, db, rb.y);
-            fn = fma((fabs(db) > cut) ? 0.0 : rb.z, fd, fn * qb);
-            fd *= qb;
-        }
-        acc = fma(fn, cs_rcp(fd), acc);
-    }
-    return acc;
-}
-
-// edge lines of a tile whose edge classes are safely in the far wing (Voigt far wing / Lorentz), per slice:
-//   lines [e0, e0+o1) and [e1-o2, e1) are outside the cut-off for every point of the slice   -> skipped
-//   lines [e0+s1, e1-s2) are inside for every point                                         -> plain fold
-//   the rest straddle the window edge                                                       -> fold with the predicate
-// o1, s1 count prefixes (line too far BELOW the slice's first / last point), o2, s2 suffixes (too far ABOVE the last / first
-// point); the tests are the reference's own subtraction on the slice's end points, and fl(nu - nul) is monotone in nu, so
-// "both ends inside" implies every point inside, exactly.
-template <int R>
-__device__ __noinline__ void cold_edge_sliced(const WarpCold& w, const double4* st, int e0, int e1)
-{
-    const int lane = w.lane;
-    const double cut = w.cut;
-    double smin[R], smax[R];
-    int o1[R], s1[R], s2[R], o2[R];
-#pragma unroll
-    for (int r = 0; r < R; r++) { smin[r] = w.nutile[32 * r]; smax[r] = w.nutile[32 * r + 31]; o1[r] = s1[r] = s2[r] = o2[r] = 0; }
-    for (int base = e0; base < e1; base += 32) {
-        const int j = base + lane;
-        const bool valid = j < e1;
-        const double x = st[valid ? j : e1 - 1].x;
-#pragma unroll
-        for (int r = 0; r < R; r++) {
-            o1[r] += __popc(__ballot_sync(0xffffffffu, valid && (smin[r] - x) > cut));
-            s1[r] += __popc(__ballot_sync(0xffffffffu, valid && (smax[r] - x) > cut));
-            s2[r] += __popc(__ballot_sync(0xffffffffu, valid && (x - smin[r]) > cut));
-            o2[r] += __popc(__ballot_sync(0xffffffffu, valid && (x - smax[r]) > cut));
-        }
-    }
-#pragma unroll
-    for (int r = 0; r < R; r++) {
-        const double nu = w.nutile[32 * r + lane];
-        const int a = e0 + o1[r], d = e1 - o2[r];            // [a, d): lines that reach some point of the slice
-        int b = e0 + s1[r], c = e1 - s2[r];                  // [b, c): lines that reach every point
-        if (b > c) { b = d; c = d; }                         // window narrower than the slice: everything straddles
-        double v = fold_far_cut(st, a, b, nu, cut);
-        v += fold_far(st, b, c, nu);
-        v += fold_far_cut(st, c, d, nu, cut);
-        w.cacc[32 * r + lane] += v;
-    }
-}
-
-// near lines (Voigt), per slice and per level: for slice r the lines [n0+nb, n1-na) have their centre within cn*nul of the
-// slice (cn = THIS level's near-centre fraction, not the batch maximum the tile-level range was sized with) and take the
-// region-selecting form, four lines at a time (four independent chains for the lane's one point); the others are far wing.
-template <int R>
-__device__ __noinline__ int cold_near_sliced(const WarpCold& w, const double4* st, int c0, int n0, int n1, int qn)
-{
-    const int lane = w.lane;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    const uint32_t qaddr = smem_u32(w.queue);
-    const double cnp = 1.0 + w.cn, cnm = 1.0 - w.cn;
-    double smin[R], smax[R];
-    int nb[R], na[R];
-#pragma unroll
-    for (int r = 0; r < R; r++) { smin[r] = w.nutile[32 * r]; smax[r] = w.nutile[32 * r + 31]; nb[r] = na[r] = 0; }
-    for (int base = n0; base < n1; base += 32) {
-        const int j = base + lane;
-        const bool valid = j < n1;
-        const double x = st[valid ? j : n1 - 1].x;
-        const double xl = x * cnp, xh = x * cnm;
-#pragma unroll
-        for (int r = 0; r < R; r++) {
-            nb[r] += __popc(__ballot_sync(0xffffffffu, valid && xl < smin[r]));
-            na[r] += __popc(__ballot_sync(0xffffffffu, valid && xh > smax[r]));
-        }
-    }
-#pragma unroll
-    for (int r = 0; r < R; r++) {
-        const double nu = w.nutile[32 * r + lane];
-        const int a = n0 + nb[r], b = max(a, n1 - na[r]);
-        double acc = fold_far(st, n0, a, nu) + fold_far(st, b, n1, nu);
-        for (int j = a; j < b; j += 4) {
-            if (qn > LS_QCAP - 128) { cold_flush<CS_VOIGT, R>(w, st, c0, qn); qn = 0; }
-            bool need[4];
-            unsigned m[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const bool ok = j + u < b;
-                const double4 rc = st[ok ? j + u : b - 1];
-                double v = voigt_12(rc, nu - rc.x, need[u]);
-                need[u] = need[u] && ok;
-                acc += (need[u] || !ok) ? 0.0 : v;
-            }
-#pragma unroll
-            for (int u = 0; u < 4; u++) m[u] = __ballot_sync(0xffffffffu, need[u]);
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                if (m[u]) {
-                    if (need[u]) {
-                        const uint32_t en = ((uint32_t)(j + u) << 8) | (uint32_t)(32 * r + lane);
-                        asm volatile("st.shared.u32 [%0], %1;" ::"r"(qaddr + 4u * (uint32_t)(qn + __popc(m[u] & lt_mask))), "r"(en)
-                                     : "memory");
-                    }
-                    qn += __popc(m[u]);
-                }
-            }
-        }
-        w.cacc[32 * r + lane] += acc;
-    }
-    __syncwarp();
-    return qn;
-}
-
-// edge lines of a tile whose edge classes are safely in the far wing (Voigt far wing / Lorentz), in the hot loop's own form.
-// The lines are sorted, so for ONE point the inclusive cut-off rule !(|nu - nul| > cut) (line_shapes.jl:10) selects a
-// contiguous index range [lo, hi) of the edge lines: two binary searches per point (with the reference's own subtraction, and
-// fl(nu - nul) is monotone in nul, so the range is exact) replace the FP64 compare per evaluation by an integer compare that
-// runs on the ALU pipe, and the fold needs no FP64 predicate at all: K -> 0 outside [lo, hi).
-template <int R>
-__device__ __noinline__ void cold_edge_fold(const WarpCold& w, const double4* st, int e0, int e1)
-{
-    const int lane = w.lane;
-    const double cut = w.cut;
-    double nup[R], acc[R];
-    int lo[R], len[R];
-#pragma unroll
-    for (int r = 0; r < R; r++) { nup[r] = w.nutile[32 * r + lane]; acc[r] = 0.0; lo[r] = e0; len[r] = e1 - e0; }
-    // lines too far BELOW the point form a prefix, lines too far ABOVE a suffix; each search only runs when some point of the
-    // tile can need it (warp-uniform tests on the tile's end points)
-    if ((w.nutile[32 * R - 1] - st[e0].x) > cut) {
-        int a[R], b[R];
-#pragma unroll
-        for (int r = 0; r < R; r++) { a[r] = e0; b[r] = e1; }
-        for (int it = 0; it < 8; it++) {        // e1 - e0 <= LS_CHUNK = 128 < 2^8
-#pragma unroll
-            for (int r = 0; r < R; r++) {
-                const int m = (a[r] + b[r]) >> 1;
-                const bool below = (a[r] < b[r]) && ((nup[r] - st[m < e1 ? m : e1 - 1].x) > cut);
-                const bool shrink = (a[r] < b[r]) && !below;
-                a[r] = below ? m + 1 : a[r];
-                b[r] = shrink ? m : b[r];
-            }
-        }
-#pragma unroll
-        for (int r = 0; r < R; r++) { lo[r] = a[r]; len[r] = e1 - a[r]; }
-    }
-    if ((st[e1 - 1].x - w.nutile[0]) > cut) {
-        int a[R], b[R];
-#pragma unroll
-        for (int r = 0; r < R; r++) { a[r] = lo[r]; b[r] = e1; }
-        for (int it = 0; it < 8; it++) {
-#pragma unroll
-            for (int r = 0; r < R; r++) {
-                const int m = (a[r] + b[r]) >> 1;
-                const bool inside = (a[r] < b[r]) && !((st[m < e1 ? m : e1 - 1].x - nup[r]) > cut);
-                const bool shrink = (a[r] < b[r]) && !inside;
-                a[r] = inside ? m + 1 : a[r];
-                b[r] = shrink ? m : b[r];
-            }
-        }
-#pragma unroll
-        for (int r = 0; r < R; r++) len[r] = a[r] - lo[r];
-    }
-    for (int j = e0; j < e1; j += 8) {
-        double fn[R], fd[R];
-        int t[R];
-#pragma unroll
-        for (int r = 0; r < R; r++) t[r] = j - lo[r];
-        {
-            const double4 ra = st[j];
-#pragma unroll
-            for (int r = 0; r < R; r++) {
-                const double da = nup[r] - ra.x;
-                fd[r] = fma(da, da, ra.y);
-                fn[r] = ((unsigned)t[r] < (unsigned)len[r]) ? ra.z : 0.0;
-            }
-        }
-#pragma unroll
-        for (int g = 1; g < 8; g++) {
-            const double4 rb = st[j + g < e1 ? j + g : e1 - 1];      // past the end: t + g >= len, so K -> 0
-#pragma unroll
-            for (int r = 0; r < R; r++) {
-                const double db = nup[r] - rb.x;
-                const double qb = fma(db, db, rb.y);
-                const double kb = ((unsigned)(t[r] + g) < (unsigned)len[r]) ? rb.z : 0.0;
-                fn[r] = fma(kb, fd[r], fn[r] * qb);
-                fd[r] *= qb;
-            }
-        }
-#pragma unroll
-        for (int r = 0; r < R; r++) acc[r] = fma(fn[r], cs_rcp(fd[r]), acc[r]);
-    }
-#pragma unroll
-    for (int r = 0; r < R; r++) w.cacc[32 * r + lane] += acc[r];
 }
 
 // edge lines: exact inclusive per-point predicate (line_shapes.jl:10)
@@ -1003,7 +736,7 @@ __global__ void __launch_bounds__(LS_THREADS, CS_LS_MINBLK / LS_WARPS) line_sum_
     w.cacc = reinterpret_cast<double*>(xb) + TILE;
     w.queue = reinterpret_cast<uint32_t*>(w.cacc + TILE);
     w.slow_lev = a.slow ? a.slow + (size_t)lev * a.nl : nullptr;
-    w.cut = a.cut; w.B1 = lp.B1; w.B2 = lp.B2; w.cn = lp.cnear; w.lane = lane;
+    w.cut = a.cut; w.B1 = lp.B1; w.B2 = lp.B2; w.lane = lane;
 
     if (lane == 0) {
         for (int s = 0; s < LS_STAGES; s++) mbar_init(&full_bar[warp][s], 1);
@@ -1415,11 +1148,7 @@ __global__ void __launch_bounds__(LS_THREADS, CS_LS_MINBLK / LS_WARPS) line_sum_
                 }
             }
         } else {
-        if (xa > 0) {
-            if (CS_LS_EDGE == 2 && (SHAPE == CS_VOIGT || SHAPE == CS_LORENTZ) && w.edge_is_far) cold_edge_sliced<R>(w, st, 0, xa);
-            else if (CS_LS_EDGE == 1 && (SHAPE == CS_VOIGT || SHAPE == CS_LORENTZ) && w.edge_is_far) cold_edge_fold<R>(w, st, 0, xa);
-            else cold_edge<SHAPE, R>(w, st, c0, 0, xa);
-        }
+        if (xa > 0) cold_edge<SHAPE, R>(w, st, c0, 0, xa);
 #pragma unroll 1
         for (int pass = 0; pass < 2; pass++) {
             // far lines: inside the cut-off for every point and safely in the far wing -> no test of any kind
@@ -1427,44 +1156,12 @@ __global__ void __launch_bounds__(LS_THREADS, CS_LS_MINBLK / LS_WARPS) line_sum_
             const int f1 = pass ? xd : xb_;
             if (SHAPE != CS_DOPPLER) {      // Doppler: exp(-(dnu/alpha)^2) underflows to exactly 0 out here
                 if (SHAPE == CS_VOIGT || SHAPE == CS_LORENTZ) {
-#if CS_LS_FOLD > 1
                     // direct mode (long ranges: whole chunks) in groups of CS_LS_FOLD lines per reciprocal, the short direct
                     // remainder of the expansion mode in groups of 8: a group is one dependent chain per point, and a short
-                    // range has nothing else to overlap it with (measured: 16 / 8 is the best pair on C2)
+                    // range has nothing else to overlap it with (measured on C2: 16 / 8 is the best pair; the 2 x 2 tree of
+                    // round 1 -- four lines per reciprocal, 5.25 FP64 ops per evaluation -- was 5 % slower)
                     fold_run<R, (MP ? 8 : CS_LS_FOLD)>(st, j, f1, nup, acc);
-#endif
-#if CS_LS_FOLD > 1 && CS_LS_DYNREM
                     fold_tail<R>(st, j, f1, nup, acc);
-#endif
-#if CS_LS_QUAD && !(CS_LS_FOLD > 1 && CS_LS_DYNREM)
-                    // four lines per reciprocal: n1/d1 + n2/d2 = (n1 d2 + n2 d1)/(d1 d2), twice -> 5.25 FP64 ops/eval
-                    for (; j + 3 < f1; j += 4) {
-                        double4 ra = st[j], rb = st[j + 1], rc = st[j + 2], rd = st[j + 3];
-#pragma unroll
-                        for (int r = 0; r < R; r++) {
-                            double da = nup[r] - ra.x, db = nup[r] - rb.x, dc = nup[r] - rc.x, dd = nup[r] - rd.x;
-                            double qa = fma(da, da, ra.y), qb = fma(db, db, rb.y);
-                            double qc = fma(dc, dc, rc.y), qd = fma(dd, dd, rd.y);
-                            double n1 = fma(rb.z, qa, ra.z * qb), d1 = qa * qb;
-                            double n2 = fma(rd.z, qc, rc.z * qd), d2 = qc * qd;
-                            double num = fma(n2, d1, n1 * d2);
-                            acc[r] = fma(num, cs_rcp(d1 * d2), acc[r]);
-                        }
-                    }
-#endif
-#if !(CS_LS_FOLD > 1 && CS_LS_DYNREM)
-                    for (; j + 1 < f1; j += 2) {
-                        double4 ra = st[j], rb = st[j + 1];
-#pragma unroll
-                        for (int r = 0; r < R; r++) {
-                            double da = nup[r] - ra.x, db = nup[r] - rb.x;
-                            double qa = fma(da, da, ra.y), qb = fma(db, db, rb.y);
-                            double num = ra.z * qb;
-                            num = fma(rb.z, qa, num);
-                            acc[r] = fma(num, cs_rcp(qa * qb), acc[r]);
-                        }
-                    }
-#endif
                 }
                 for (; j < f1; j++) {
                     double4 rc = st[j];
@@ -1480,16 +1177,9 @@ __global__ void __launch_bounds__(LS_THREADS, CS_LS_MINBLK / LS_WARPS) line_sum_
                     }
                 }
             }
-            if (pass == 0 && xb_ < xc) {
-                if (CS_LS_NEAR == 2 && SHAPE == CS_VOIGT) qn = cold_near_sliced<R>(w, st, c0, xb_, xc, qn);
-                else qn = cold_near<SHAPE, R>(w, st, c0, xb_, xc, qn);
-            }
+            if (pass == 0 && xb_ < xc) qn = cold_near<SHAPE, R>(w, st, c0, xb_, xc, qn);
         }
-        if (xd < n) {
-            if (CS_LS_EDGE == 2 && (SHAPE == CS_VOIGT || SHAPE == CS_LORENTZ) && w.edge_is_far) cold_edge_sliced<R>(w, st, xd, n);
-            else if (CS_LS_EDGE == 1 && (SHAPE == CS_VOIGT || SHAPE == CS_LORENTZ) && w.edge_is_far) cold_edge_fold<R>(w, st, xd, n);
-            else cold_edge<SHAPE, R>(w, st, c0, xd, n);
-        }
+        if (xd < n) cold_edge<SHAPE, R>(w, st, c0, xd, n);
         if (SHAPE == CS_VOIGT && qn > 0) { cold_flush<SHAPE, R>(w, st, c0, qn); qn = 0; }
         }
         // stage s is free again: refill it with chunk c + LS_STAGES

@@ -8,7 +8,7 @@
 #include "cs_internal.cuh"
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_select.cuh>
-#include <cub/iterator/counting_input_iterator.cuh>
+#include <thrust/iterator/counting_iterator.h>
 #include <cstring>
 #include <limits>
 
@@ -308,7 +308,7 @@ extern "C" int32_t cs_par_read(cs_ctx* ctx, int64_t nbytes, const char* text, in
     const size_t o_out = take(8 * n * sizeof(double)), o_mio = take(2 * n * sizeof(int16_t));
     size_t tmp_sel = 0, tmp_sort = 0;
     {
-        cub::CountingInputIterator<int64_t> it(0);
+        thrust::counting_iterator<int64_t> it(0);
         cub::DeviceSelect::Flagged((void*)nullptr, tmp_sel, it, (const uint8_t*)nullptr, (int64_t*)nullptr, (int64_t*)nullptr, (int)nrec, st);
         cub::DeviceRadixSort::SortPairs((void*)nullptr, tmp_sort, (const unsigned long long*)nullptr, (unsigned long long*)nullptr,
                                         (const int64_t*)nullptr, (int64_t*)nullptr, (int)nrec, 0, 64, st);
@@ -343,7 +343,7 @@ extern "C" int32_t cs_par_read(cs_ctx* ctx, int64_t nbytes, const char* text, in
     int64_t *ia = (int64_t*)(base + o_ia), *ib = (int64_t*)(base + o_ib);
     unsigned long long *ka = (unsigned long long*)(base + o_ka), *kb = (unsigned long long*)(base + o_kb);
     {
-        cub::CountingInputIterator<int64_t> it(0);
+        thrust::counting_iterator<int64_t> it(0);
         size_t tb = tmp_bytes;
         CS_CUDA(cub::DeviceSelect::Flagged(base + o_tmp, tb, it, keep, ia, (int64_t*)cnt, (int)nrec, st));
     }

@@ -774,9 +774,11 @@ int32_t eval_table(cs_table* tb, int64_t nlev, const double* T, const double* P,
         double lp = log(P[l]);
         // StrictBoundaries: out-of-domain coordinates are an error (gases.jl:85 via BichebyshevInterpolator)
         CS_REQUIRE(T[l] >= tb->Ta && T[l] <= tb->Tb, CS_ERR_DOMAIN,
-                   "temperature %g K outside the opacity-table domain [%g, %g]", T[l], tb->Ta, tb->Tb);
+                   "node %lld of %lld: temperature %g K (at %g Pa) outside the opacity-table domain [%g, %g] K", (long long)(l + 1),
+                   (long long)nlev, T[l], P[l], tb->Ta, tb->Tb);
         CS_REQUIRE(lp >= tb->lnPa && lp <= tb->lnPb, CS_ERR_DOMAIN,
-                   "pressure %g Pa outside the opacity-table domain [%g, %g]", P[l], exp(tb->lnPa), exp(tb->lnPb));
+                   "node %lld of %lld: pressure %g Pa (at %g K) outside the opacity-table domain [%g, %g] Pa", (long long)(l + 1),
+                   (long long)nlev, P[l], T[l], exp(tb->lnPa), exp(tb->lnPb));
         double xt = 2 * (T[l] - tb->Ta) / (tb->Tb - tb->Ta) - 1;
         double xp = 2 * (lp - tb->lnPa) / (tb->lnPb - tb->lnPa) - 1;
         ct[0] = 1; ct[1] = xt;

@@ -160,23 +160,36 @@ def c5sharded(small):
 
 
 def par(small):
-    """.par ingestion: 250k synthetic CO2 lines written as 160-column records (40 MB), host parser vs GPU parser"""
+    """.par ingestion: 250k synthetic CO2 lines written as 160-column records (40 MB): host readpar vs the one-call device
+    readpar (cs_par_read: pinned double-buffered H2D of the text, parse, filter, maxlines, stable sort by nu on the GPU)"""
     import tempfile
     n = 20_000 if small else 250_000
     sl = bench.synthetic_lines(cs, n, 20261018, 2, (0.06, 0.13))
     fn = os.path.join(tempfile.mkdtemp(), "syn_co2.par")
     cs.writepar(fn, sl)
     nbytes = os.path.getsize(fn)
-    t0 = time.perf_counter(); a = cs.readpar(fn); th = time.perf_counter() - t0
-    cs.readpar_b200(fn)
-    t0 = time.perf_counter(); b = cs.readpar_b200(fn); tg = time.perf_counter() - t0
-    kms = cs.default_context().timers()["total"]
-    same = all(np.array_equal(a[k], b[k]) for k in a)
+    ctx = cs.default_context()
+    out = {"config": "par", "lines": n, "bytes": nbytes}
+    for tag, kw in (("all", {}), ("filtered", dict(νmin=500.0, νmax=2500.0, Scut=1e-27, maxlines=100_000))):
+        t0 = time.perf_counter(); a = cs.readpar(fn, **kw); th = time.perf_counter() - t0
+        cs.readpar_b200(fn, **kw)
+        best = None
+        for _ in range(3):
+            tm = {}
+            t0 = time.perf_counter(); b = cs.readpar_b200(fn, timing=tm, **kw); tg = time.perf_counter() - t0
+            tm["kernels_ms"] = ctx.timers()["total"]
+            tm["wall_s"] = tg
+            if best is None or tm["call_s"] < best["call_s"]:
+                best = tm
+        out[tag] = {"rows_out": int(len(b["ν"])), "bit_identical": bool(all(np.array_equal(a[k], b[k]) for k in a)), "host_readpar_s": th,
+                    "gpu_readpar_s": best["wall_s"], "file_read_s": best["read_s"], "device_call_s": best["call_s"],
+                    "kernels_ms": best["kernels_ms"], "call_GBps_text": nbytes / best["call_s"] / 1e9}
     buf = open(fn, "rb").read()
+    cs.parse_records_b200(buf)
     t0 = time.perf_counter(); cs.parse_records_b200(buf); tp = time.perf_counter() - t0
-    return {"config": "par", "lines": n, "bytes": nbytes, "bit_identical": bool(same), "host_readpar_s": th, "gpu_readpar_s": tg,
-            "gpu_parse_call_s": tp, "parse_kernel_ms": kms, "kernel_GBps_text": nbytes / (kms * 1e-3) / 1e9,
-            "kernel_GBps_text_plus_outputs": (nbytes + n * 69) / (kms * 1e-3) / 1e9}
+    out["parse_only_call_s"] = tp
+    out["parse_kernel_ms"] = ctx.timers()["total"]
+    return out
 
 
 if __name__ == "__main__":
