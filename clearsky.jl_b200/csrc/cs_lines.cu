@@ -37,6 +37,9 @@ namespace {
 #ifndef CS_LS_FOLD
 #define CS_LS_FOLD 16
 #endif
+#ifndef CS_LS_R_EXP         // points per lane (tile = 32 R points) of the Voigt / Lorentz line sum in expansion mode
+#define CS_LS_R_EXP 2
+#endif
 #ifndef CS_LS_MINBLK
 #define CS_LS_MINBLK 16
 #endif
@@ -1435,8 +1438,16 @@ int32_t cs_lines_accumulate(cs_lines* L, int32_t shape, int64_t nnu, const doubl
         for (int64_t k = 0; k < kb; k++) cn = std::max(cn, hl[(size_t)k].cnear);
         switch (shape) {
         case CS_DOPPLER: CS_TRY((launch_line_sum<CS_DOPPLER, 4>(ctx, la, (int)kb, cn))); break;
-        case CS_LORENTZ: CS_TRY((launch_line_sum<CS_LORENTZ, 4>(ctx, la, (int)kb, cn))); break;
-        case CS_VOIGT:   CS_TRY((launch_line_sum<CS_VOIGT, 4>(ctx, la, (int)kb, cn))); break;
+        // expansion mode: what is left for the pair-by-pair sum scales with the tile width (cut-off edges, lines within 4 half
+        // widths, the near band), the far field does not -- 64-point tiles there, 128-point tiles for the direct sum
+        case CS_LORENTZ:
+            if (la.mp_theta > 0.0 && CS_LS_R_EXP != 4) CS_TRY((launch_line_sum<CS_LORENTZ, CS_LS_R_EXP>(ctx, la, (int)kb, cn)));
+            else CS_TRY((launch_line_sum<CS_LORENTZ, 4>(ctx, la, (int)kb, cn)));
+            break;
+        case CS_VOIGT:
+            if (la.mp_theta > 0.0 && CS_LS_R_EXP != 4) CS_TRY((launch_line_sum<CS_VOIGT, CS_LS_R_EXP>(ctx, la, (int)kb, cn)));
+            else CS_TRY((launch_line_sum<CS_VOIGT, 4>(ctx, la, (int)kb, cn)));
+            break;
         default:         CS_TRY((launch_line_sum<CS_PHCO2, 4>(ctx, la, (int)kb, cn))); break;
         }
         cs_span_end(ctx, sp_sum);
