@@ -40,6 +40,9 @@ namespace {
 #ifndef CS_LS_R_EXP         // points per lane (tile = 32 R points) of the Voigt / Lorentz line sum in expansion mode
 #define CS_LS_R_EXP 2
 #endif
+#ifndef CS_LS_NEAR_TRIM     // per-level trimming of the near range (Voigt)
+#define CS_LS_NEAR_TRIM 1
+#endif
 #ifndef CS_LS_MINBLK
 #define CS_LS_MINBLK 16
 #endif
@@ -182,6 +185,7 @@ struct LineSumArgs {
     double mp_theta;        // > 0: far-field expansion for lines farther than mp_theta half tile widths (Voigt, Lorentz)
     const double* ffc;      // far-field coefficients [nlev][ntiles][MP_P] precomputed by farfield_kernel (or null)
     double nul_lo, nul_hi;  // first / last prefiltered line position (host copy)
+    double near_cn;         // near-centre fraction the per-tile ranges were built with (maximum over the level batch)
     const double2* chix;    // PHCO2 expansion: {X, 1/X}, X = exp(0.0232 (nul - chix_ref)) per prefiltered line (or null)
     double chix_ref;
 };
@@ -749,6 +753,7 @@ __global__ void __launch_bounds__(LS_THREADS, CS_LS_MINBLK / LS_WARPS) line_sum_
     __syncwarp();
 
     // all line indices below are 32-bit and relative to the first line of the tile's window (wlo64)
+    const double near_cn = a.near_cn;
     const int64_t* rg = a.ranges + tile * a.nr;
     const int64_t wlo64 = rg[0];
     const int whi = (int)(rg[1] - wlo64);
@@ -1065,8 +1070,24 @@ __global__ void __launch_bounds__(LS_THREADS, CS_LS_MINBLK / LS_WARPS) line_sum_
         const double4* st = ring + (size_t)s * LS_CHUNK;
         // chunk-local boundaries of the five classes: [0,xa) edge | [xa,xb) far | [xb,xc) near | [xc,xd) far | [xd,n) edge
         const int n = c1 - c0;
-        const int xa = min(max(ilo - c0, 0), n), xb_ = min(max(nlo - c0, 0), n);
-        const int xc = min(max(nhi - c0, 0), n), xd = min(max(ihi - c0, 0), n);
+        const int xa = min(max(ilo - c0, 0), n), xd = min(max(ihi - c0, 0), n);
+        int xb_ = min(max(nlo - c0, 0), n), xc = min(max(nhi - c0, 0), n);
+        if (SHAPE == CS_VOIGT && CS_LS_NEAR_TRIM && xb_ < xc && lp.cnear < near_cn) {
+            // the per-tile near range was sized with the widest Doppler zone of the level batch (its warmest level); at THIS
+            // level the lines at both ends of it are still safely in the far wing: hand them back to the far ranges
+            const double tlo = w.nutile[0], thi = w.nutile[TILE - 1];
+            const double cp = 1.0 + lp.cnear, cm = 1.0 - lp.cnear;
+            int nb = 0, na = 0;
+            for (int base = xb_; base < xc; base += 32) {
+                const int j = base + lane;
+                const bool ok = j < xc;
+                const double x = st[ok ? j : xc - 1].x;
+                nb += __popc(__ballot_sync(0xffffffffu, ok && x * cp < tlo));
+                na += __popc(__ballot_sync(0xffffffffu, ok && x * cm > thi));
+            }
+            xb_ += nb;
+            xc = max(xb_, xc - na);
+        }
         if (SHAPE == CS_PHCO2) {
             // per-line chi factors of this chunk (lines in one of the six factorised segments)
             for (int jj = lane; jj < n; jj += 32) {
@@ -1209,6 +1230,7 @@ template <int SHAPE, int R> int32_t launch_line_sum(cs_ctx* ctx, LineSumArgs a, 
     constexpr int TILE = 32 * R;
     cudaStream_t st = ctx->stream;
     a.ntiles = (a.nnu + TILE - 1) / TILE;
+    a.near_cn = cn;
     if (SHAPE == CS_DOPPLER) a.mp_theta = 0.0;
     a.nr = (SHAPE == CS_PHCO2) ? LS_NR : (a.mp_theta > 0.0 ? 8 : 6);
     // scratch: the per-tile ranges, then (PHCO2 expansion) the per-line chi factors of the >= 120 cm^-1 class, which are

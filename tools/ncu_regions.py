@@ -7,6 +7,14 @@ import re
 import sys
 
 rows = list(csv.reader(open(sys.argv[1])))
+# a listing may hold several kernels, each introduced by a "Kernel Name" row: take the one whose name contains argv[3] (default:
+# the first)
+starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+want = sys.argv[3] if len(sys.argv) > 3 else ""
+pick = next((i for i in starts if want in rows[i][1]), starts[0])
+end = next((i for i in starts if i > pick), len(rows))
+print("kernel:", rows[pick][1])
+rows = rows[pick:end]
 hdr = rows[1]
 ix = {h: i for i, h in enumerate(hdr)}
 ins = []
