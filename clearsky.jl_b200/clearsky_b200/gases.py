@@ -40,9 +40,14 @@ def _as_conc(fC):
 
 
 def checkν(ν):
-    """gases.jl:90-95"""
-    assert np.all(np.diff(ν) > 0), "wavenumbers must be unique and in ascending order"
-    assert np.all(ν >= 0), "wavenumbers must be positive"
+    """gases.jl:90-95 (one comparison pass; ascending + first element non-negative implies all non-negative)"""
+    assert len(ν) < 2 or bool(np.all(ν[1:] > ν[:-1])), "wavenumbers must be unique and in ascending order"
+    assert len(ν) == 0 or ν[0] >= 0, "wavenumbers must be positive"
+
+
+def _meanmolarmass(sl):
+    """mean molar mass of a line list, Σ(A·μ)/ΣA over the lines (gases.jl:233) -- informational only"""
+    return float(np.dot(sl.A, sl.μ) / np.sum(sl.A))
 
 
 class AbstractGas:
@@ -58,8 +63,8 @@ class Gas(AbstractGas):
         assert len(ν) > 0
         self.ctx = ctx or _lib.default_context()
         self.name, self.formula = sl.name, sl.formula
-        self.μ = float(np.sum(sl.A * sl.μ) / np.sum(sl.A))   # gases.jl:233
-        self.ν = f64(np.array(ν, dtype=np.float64))
+        self.μ = _meanmolarmass(sl)
+        self.ν = f64(np.asarray(ν, dtype=np.float64))       # shared with the caller, never written
         checkν(self.ν)
         self.Ω = Ω
         self.fC = _as_conc(fC)
@@ -154,8 +159,8 @@ class LineGas(AbstractGas):
     def __init__(self, sl, fC, ν, shape="voigt", Δνcut=None, ctx=None):
         self.ctx = ctx or _lib.default_context()
         self.name, self.formula = sl.name, sl.formula
-        self.μ = float(np.sum(sl.A * sl.μ) / np.sum(sl.A))
-        self.ν = f64(np.array(ν, dtype=np.float64))
+        self.μ = _meanmolarmass(sl)
+        self.ν = f64(np.asarray(ν, dtype=np.float64))       # shared with the caller, never written
         checkν(self.ν)
         self.fC = _as_conc(fC)
         self.sid = shape_id(shape)

@@ -451,6 +451,15 @@ extern "C" int32_t cs_count_evals(cs_lines* L, int64_t nnu, const double* nu, do
 
 // ------------------------------------------------------------------------------------------------
 // sigma workspace
+__global__ void trapz_weights_kernel(const double* __restrict__ nu, int64_t nnu, double* __restrict__ w)
+{
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nnu) return;
+    const double dl = j > 0 ? nu[j] - nu[j - 1] : 0.0;
+    const double dr = j + 1 < nnu ? nu[j + 1] - nu[j] : 0.0;
+    w[j] = (dl + dr) / 2;
+}
+
 extern "C" int32_t cs_sigma_create(cs_ctx* ctx, int64_t nnu, const double* nu, int64_t nnode, cs_sigma** out)
 {
     CS_REQUIRE(ctx && nu && out, CS_ERR_ARG, "null argument");
@@ -470,19 +479,8 @@ extern "C" int32_t cs_sigma_create(cs_ctx* ctx, int64_t nnu, const double* nu, i
     s->w = nullptr;
     int32_t rc = upload(&s->nu, nu, (size_t)nnu, ctx->stream);
     if (rc) { delete s; return rc; }
-    {
-        // w_j = (dnu_{j-1} + dnu_j)/2: trapz(nu, y) = sum_j w_j y_j with every interval counted once
-        std::vector<double> hw((size_t)nnu);
-        for (int64_t j = 0; j < nnu; j++) {
-            double dl = j > 0 ? nu[j] - nu[j - 1] : 0.0;
-            double dr = j + 1 < nnu ? nu[j + 1] - nu[j] : 0.0;
-            hw[(size_t)j] = (dl + dr) / 2;
-        }
-        rc = upload(&s->w, hw.data(), (size_t)nnu, ctx->stream);
-        if (rc) { cs_free(s->nu, ctx->stream); delete s; return rc; }
-        CS_CUDA(cudaStreamSynchronize(ctx->stream));
-    }
-    cudaError_t e = cs_malloc((void**)&s->sig, sizeof(double) * (size_t)nnu * nnode, ctx->stream);
+    cudaError_t e = cs_malloc((void**)&s->w, sizeof(double) * (size_t)nnu, ctx->stream);
+    if (e == cudaSuccess) e = cs_malloc((void**)&s->sig, sizeof(double) * (size_t)nnu * nnode, ctx->stream);
     if (e != cudaSuccess) {
         cs_free(s->nu, ctx->stream);
         cs_free(s->w, ctx->stream);
@@ -490,7 +488,12 @@ extern "C" int32_t cs_sigma_create(cs_ctx* ctx, int64_t nnu, const double* nu, i
         cs_set_error("cudaMalloc(sigma workspace %zu bytes): %s", sizeof(double) * (size_t)nnu * nnode, cudaGetErrorString(e));
         return CS_ERR_NOMEM;
     }
+    // w_j = (dnu_{j-1} + dnu_j)/2: trapz(nu, y) = sum_j w_j y_j with every interval counted once (computed from the device copy)
+    trapz_weights_kernel<<<(unsigned)((nnu + 255) / 256), 256, 0, ctx->stream>>>(s->nu, nnu, s->w);
+    CS_CUDA(cudaGetLastError());
+    cs_count_launch(ctx);
     CS_CUDA(cudaMemsetAsync(s->sig, 0, sizeof(double) * (size_t)nnu * nnode, ctx->stream));
+    // the caller's nu is only valid for the duration of the call: wait for its copy (everything else is stream-ordered)
     CS_CUDA(cudaStreamSynchronize(ctx->stream));
     *out = s;
     return CS_OK;
