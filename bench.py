@@ -14,6 +14,7 @@ slice ± cutoff only, and ONE NCCL all-reduce of the 2*np spectrally integrated 
 the same workload; the Julia reference itself cannot run in this image (no Julia runtime).
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -541,8 +542,8 @@ def run_ours(args):
             parity_fail = ps
     if rank == 0:
         print(json.dumps(line, ensure_ascii=False))
-    if world > 1:
-        dist.destroy_process_group()
+    torch.cuda.synchronize()
+    _shutdown(dist, world)
     if parity_fail is not None:
         print(f"bench.py: PARITY FAILURE against the oracle on the sample: {parity_fail}", file=sys.stderr)
         sys.exit(3)
@@ -645,6 +646,22 @@ class _HostColumn:
             i += n - 1
         Pr[-1] = Pe[-1]
         self.Pr = np.sort(Pr)
+
+
+def _shutdown(dist, world, grace=20.0):
+    """leave torch.distributed without ever hanging the launch: stdout is flushed first, and a watchdog ends the process if
+    destroy_process_group does not return (the JSON line is already out)"""
+    sys.stdout.flush()
+    sys.stderr.flush()
+    if world <= 1:
+        return
+    t = threading.Timer(grace, lambda: os._exit(0))
+    t.daemon = True
+    t.start()
+    try:
+        dist.destroy_process_group()
+    finally:
+        t.cancel()
 
 
 def run_c5(args):
@@ -848,9 +865,14 @@ def run_c5(args):
             parity_fail = ps
     if rank == 0:
         print(json.dumps(line, ensure_ascii=False))
+    # the captured step holds the NCCL all-reduce: release the graph before the communicator goes away (destroying the process
+    # group under a live graph hung the torchrun launch of this workload), and never let the shutdown outlive the result
+    run_step = None
+    graph = None
+    gc.collect()
+    torch.cuda.synchronize()
     lib().cs_rcm_free(h)
-    if world > 1:
-        dist.destroy_process_group()
+    _shutdown(dist, world)
     if parity_fail is not None:
         print(f"bench.py: PARITY FAILURE against the oracle: {parity_fail}", file=sys.stderr)
         sys.exit(3)

@@ -188,3 +188,19 @@ def test_dispatch_of_scalar_and_vector_pressure_forms(cs):
         cs.opticaldepth(1e5, 10.0, 9.8, 250.0, 0.029, 0.0, gray)
     with pytest.raises(AssertionError):
         cs.opticaldepth(1e5, 10.0, 9.8, 250.0, 0.029, 2.0, gray)       # checkazimuth before any device work
+
+
+def test_checknu_and_record_geometry(cs):
+    """one-pass checkν keeps the reference's two asserts (gases.jl:90-95); .par record geometry of the device reader"""
+    from clearsky_b200.gases import checkν
+    from clearsky_b200.par import _record_geometry
+    checkν(np.array([0.0, 1.0, 2.5]))
+    checkν(np.array([3.0]))
+    for bad, msg in ((np.array([1.0, 1.0]), "ascending"), (np.array([2.0, 1.0]), "ascending"), (np.array([-1.0, 1.0]), "positive")):
+        with pytest.raises(AssertionError, match=msg):
+            checkν(bad)
+    rec = b" 21" + b"x" * 157
+    assert _record_geometry((rec + b"\n") * 3) == (161, 3)
+    assert _record_geometry((rec + b"\n") * 3 + b"\n") == (161, 3)            # trailing blank line is not a record
+    assert _record_geometry((rec + b"\r\n") * 2) == (162, 2)
+    assert _record_geometry((rec + b"\n") * 2 + rec) == (161, 3)               # last record without terminator
