@@ -72,6 +72,8 @@ static int32_t ctx_create(int32_t device, void* stream, bool own, cs_ctx** out)
     if (const char* ff = getenv("CS_FARFIELD"))
         c->farfield = (strcmp(ff, "expansion") == 0) ? CS_FARFIELD_EXPANSION : CS_FARFIELD_DIRECT;
     c->ff_no_moments = getenv("CS_FARFIELD_NO_MOMENTS") != nullptr;
+    c->ls_no_band = getenv("CS_LINESUM_NO_BAND") != nullptr;
+    c->ls_no_split = getenv("CS_LINESUM_NO_SPLIT") != nullptr;
     c->table_no_mma = getenv("CS_TABLE_EVAL_NO_MMA") != nullptr;
     c->table_no_fused = getenv("CS_TABLE_FIT_NO_FUSED") != nullptr;
     {
@@ -353,8 +355,11 @@ extern "C" int32_t cs_lines_upload(cs_ctx* ctx, int64_t n, const double* nu, con
     L->mu_min = mu[0];
     for (int64_t j = 1; j < n; j++) L->mu_min = std::min(L->mu_min, mu[j]);
     L->g_max = 0.0; L->na_min = na[0]; L->na_max = na[0];
+    L->ga_min = ga[0]; L->gs_min = gs[0];
     for (int64_t j = 0; j < n; j++) {
         L->g_max = std::max(L->g_max, std::max(ga[j], gs[j]));
+        L->ga_min = std::min(L->ga_min, ga[j]);
+        L->gs_min = std::min(L->gs_min, gs[j]);
         L->na_min = std::min(L->na_min, na[j]);
         L->na_max = std::max(L->na_max, na[j]);
     }

@@ -43,6 +43,18 @@ namespace {
 #ifndef CS_LS_NEAR_TRIM     // per-level trimming of the near range (Voigt)
 #define CS_LS_NEAR_TRIM 1
 #endif
+#ifndef CS_LS_BAND          // Voigt: near-centre lines go through the far-wing fold, their band is corrected per point
+#define CS_LS_BAND 1
+#endif
+#ifndef CS_LS_SPLIT         // direct mode, Voigt (band) / Lorentz: cold classes in line_sum_kernel<.., COLD>, far wings in far_fold_kernel
+#define CS_LS_SPLIT 1
+#endif
+#ifndef CS_LS_COLD_MINBLK   // resident one-warp CTAs per SM of line_sum_kernel<.., COLD> (latency-bound: more warps, fewer registers)
+#define CS_LS_COLD_MINBLK 24
+#endif
+#ifndef CS_LS_HOT_MINBLK    // resident one-warp CTAs per SM of far_fold_kernel
+#define CS_LS_HOT_MINBLK 16
+#endif
 #ifndef CS_LS_MINBLK
 #define CS_LS_MINBLK 16
 #endif
@@ -186,6 +198,8 @@ struct LineSumArgs {
     const double* ffc;      // far-field coefficients [nlev][ntiles][MP_P] precomputed by farfield_kernel (or null)
     double nul_lo, nul_hi;  // first / last prefiltered line position (host copy)
     double near_cn;         // near-centre fraction the per-tile ranges were built with (maximum over the level batch)
+    int band;               // Voigt: 1 = per-point band correction of the near-centre lines (host: damping parameter bounded below)
+    int split;              // 1 = two launches: cold classes (this kernel, COLD) then far_fold_kernel over the all-inside lines
     const double2* chix;    // PHCO2 expansion: {X, 1/X}, X = exp(0.0232 (nul - chix_ref)) per prefiltered line (or null)
     double chix_ref;
 };
@@ -526,6 +540,121 @@ __device__ __noinline__ int cold_near(const WarpCold& w, const double4* st, int 
     return qn;
 }
 
+// ---- Voigt near band, per point.  The per-tile near range [nlo,nhi) holds every line whose Doppler zone (|z|^2 < 1.6e4)
+// touches SOME point of the tile; for one point only the lines with nul (1 - cn) <= nu <= nul (1 + cn) can be inside their
+// zone -- ~1/4 of the (line, point) pairs of the range on the C2 grid.  So the whole range goes through the far-wing fold
+// like any other line (K/q for every pair, no test), and each lane walks the band of ITS points (two binary searches per
+// point, records read straight from L1/L2: the lanes read different lines) adding the difference to the true value:
+//   2 convergents:  K d^2 (s+1/2)/D - K/q = K (3/2 s - 1/4 - 2 y^2)/(q D),  D = (s-1/2)^2 + 2 y^2   (no cancellation)
+//   general routine (|z|^2 < 160 and the guard slivers): w985 value - K/q, deferred to the queue as before.
+// K/q exceeds the true value by at most 1/(sqrt(pi) y) (at the line centre), so the subtraction costs log10 of that in
+// digits: the host only selects this path when y >= 1e-5 for every line of every level of the batch.
+template <int R>
+__device__ __noinline__ void band_flush(const WarpCold& w, const double4* __restrict__ rec_near,
+                                        const double4* __restrict__ slow_near, int qn)
+{
+    for (int e = w.lane; e < qn; e += 32) {
+        const uint32_t en = w.queue[e];
+        const int j = (int)(en >> 8), p = (int)(en & 255u);
+        const double4 rc = ld_rec(rec_near + j);
+        const double dnu = w.nutile[p] - rc.x;
+        atomicAdd(&w.cacc[p], voigt_near(slow_near, j, dnu, 1.0) - rc.z * cs_rcp(fma(dnu, dnu, rc.y)));
+    }
+    __syncwarp();
+}
+
+template <int R>
+__device__ __noinline__ void band_near(const WarpCold& w, const double4* __restrict__ rec_near,
+                                       const double4* __restrict__ slow_near, const double* __restrict__ nul_near, int nn, double cn)
+{
+    const int lane = w.lane;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const uint32_t qaddr = smem_u32(w.queue);
+    const double cp = 1.0 + cn, cm = 1.0 - cn;
+    double nup[R], acc[R];
+    int jlo[R], len[R];
+    int maxlen = 0;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        nup[r] = w.nutile[32 * r + lane];
+        acc[r] = 0.0;
+    }
+    // band of each point: [first line with !(nul (1+cn) < nu), first line with nul (1-cn) > nu) -- the same two predicates the
+    // per-tile range was built with (tile_ranges_kernel, entries 4 and 5), so a pair outside the band is certainly far wing
+    {
+        int lo[R], hi[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) { lo[r] = 0; hi[r] = nn; }
+        for (int it = nn; it > 0; it >>= 1) {
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                if (lo[r] < hi[r]) {
+                    const int m = (lo[r] + hi[r]) >> 1;
+                    if (__ldg(nul_near + m) * cp < nup[r]) lo[r] = m + 1; else hi[r] = m;
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; r++) { jlo[r] = lo[r]; hi[r] = nn; }
+        for (int it = nn; it > 0; it >>= 1) {
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                if (lo[r] < hi[r]) {
+                    const int m = (lo[r] + hi[r]) >> 1;
+                    if (!(__ldg(nul_near + m) * cm > nup[r])) lo[r] = m + 1; else hi[r] = m;
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; r++) { len[r] = lo[r] - jlo[r]; maxlen = max(maxlen, len[r]); }
+    }
+    maxlen = __reduce_max_sync(0xffffffffu, maxlen);
+    int qn = 0;
+    for (int k = 0; k < maxlen; k++) {
+        if (qn > LS_QCAP - 32 * R) { band_flush<R>(w, rec_near, slow_near, qn); qn = 0; }
+        bool need[R];
+        int jj[R];
+        unsigned m[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const bool valid = k < len[r];
+            jj[r] = min(jlo[r] + k, nn - 1);
+            const double4 rc = ld_rec(rec_near + jj[r]);
+            const double dnu = nup[r] - rc.x;
+            const double q = fma(dnu, dnu, rc.y);
+            const double s = rc.w * q;
+            const int hs = __double2hiint(s);
+            const bool one = hs > CS_S1_HI;
+            const bool two = (hs < CS_S1_LO) & (hs > CS_S2_HI);
+            const double y2 = rc.w * rc.y;
+            const double sm = s - 0.5;
+            const double D = fma(sm, sm, 2.0 * y2);
+            const double num = rc.z * fma(-2.0, y2, fma(1.5, s, -0.25));
+            const double v = num * cs_rcp(q * D);
+            acc[r] += (valid & two) ? v : 0.0;
+            need[r] = valid & !(one | two);
+        }
+#pragma unroll
+        for (int r = 0; r < R; r++) m[r] = __ballot_sync(0xffffffffu, need[r]);
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            if (m[r]) {
+                if (need[r]) {
+                    const uint32_t en = ((uint32_t)jj[r] << 8) | (uint32_t)(32 * r + lane);
+                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(qaddr + 4u * (uint32_t)(qn + __popc(m[r] & lt_mask))), "r"(en)
+                                 : "memory");
+                }
+                qn += __popc(m[r]);
+            }
+        }
+    }
+    __syncwarp();
+    if (qn > 0) band_flush<R>(w, rec_near, slow_near, qn);
+#pragma unroll
+    for (int r = 0; r < R; r++) w.cacc[32 * r + lane] += acc[r];
+    __syncwarp();
+}
+
 // PHCO2 lines that straddle a chi-class border for this tile: far-wing form with chi evaluated per point
 template <int R>
 __device__ __noinline__ void cold_phco2_generic(const WarpCold& w, const double4* st, int g0, int g1)
@@ -720,8 +849,12 @@ __global__ void __launch_bounds__(128) farfield_kernel(FarFieldArgs a)
 // take 8 adjacent tiles of the same level: their windows overlap by ~98 %, so the copies hit L2.
 // MP = the far-field expansion is compiled in (a direct-mode launch takes the MP = false instantiation: none of the expansion's
 // code, segment tables or registers)
-template <int SHAPE, int R, bool MP>
-__global__ void __launch_bounds__(LS_THREADS, CS_LS_MINBLK / LS_WARPS) line_sum_kernel(LineSumArgs a)
+// BAND = Voigt near-centre lines through the fold + per-point band correction (band_near) instead of cold_near per tile
+// COLD = only the cold classes (cut-off edges, band / deferred evaluations): the lines inside the cut-off for every point are
+// left to far_fold_kernel, launched after this one.  The partial sum goes to `out` in the form far_fold_kernel completes:
+//   accumulate 0: out = scale*cold   1: out += scale*cold   2: out = cold (far_fold_kernel writes log(scale*(out + far)))
+template <int SHAPE, int R, bool MP, bool BAND, bool COLD = false>
+__global__ void __launch_bounds__(LS_THREADS, (COLD ? CS_LS_COLD_MINBLK : CS_LS_MINBLK) / LS_WARPS) line_sum_kernel(LineSumArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[LS_WARPS][LS_STAGES];
@@ -802,7 +935,7 @@ __global__ void __launch_bounds__(LS_THREADS, CS_LS_MINBLK / LS_WARPS) line_sum_
     //                                     tile would cost more in chunk prologues than the ring saves)
     //   no expansion:                     [0,whi)
     // (kept in shared memory: indexed dynamically by the chunk number, warp-uniform)
-    const bool multi = mp || px;
+    const bool multi = mp || px || COLD;
     int* slo = seg_tab[warp];
     int* shi = seg_tab[warp] + LS_NSEG;
     int* sch = seg_tab[warp] + 2 * LS_NSEG;
@@ -821,6 +954,9 @@ __global__ void __launch_bounds__(LS_THREADS, CS_LS_MINBLK / LS_WARPS) line_sum_
             slo[2] = bnd[4];  shi[2] = bnd[13];
             slo[3] = bnd[14]; shi[3] = bnd[15];
             slo[4] = bnd[16]; shi[4] = whi;
+        } else if (COLD) {
+            slo[0] = 0;   shi[0] = ilo;
+            slo[1] = ihi; shi[1] = whi;
         } else {
             shi[0] = whi;
         }
@@ -1060,6 +1196,9 @@ __global__ void __launch_bounds__(LS_THREADS, CS_LS_MINBLK / LS_WARPS) line_sum_
         }
     }
 
+    if (BAND && nlo < nhi)
+        band_near<R>(w, rec_lev + nlo, w.slow_lev + nlo, a.nul + wlo64 + nlo, nhi - nlo, lp.cnear);
+
     int sgc = 0;   // PHCO2: cursor into the 17 chi-class segments
     for (int c = nchunkA; c < nchunk; c++) {
         const int s = c % LS_STAGES;
@@ -1072,7 +1211,8 @@ __global__ void __launch_bounds__(LS_THREADS, CS_LS_MINBLK / LS_WARPS) line_sum_
         const int n = c1 - c0;
         const int xa = min(max(ilo - c0, 0), n), xd = min(max(ihi - c0, 0), n);
         int xb_ = min(max(nlo - c0, 0), n), xc = min(max(nhi - c0, 0), n);
-        if (SHAPE == CS_VOIGT && CS_LS_NEAR_TRIM && xb_ < xc && lp.cnear < near_cn) {
+        if (BAND) { xb_ = xd; xc = xd; }      // the near range is folded like any far range; band_near corrected it per point
+        if (!BAND && SHAPE == CS_VOIGT && CS_LS_NEAR_TRIM && xb_ < xc && lp.cnear < near_cn) {
             // the per-tile near range was sized with the widest Doppler zone of the level batch (its warmest level); at THIS
             // level the lines at both ends of it are still safely in the far wing: hand them back to the far ranges
             const double tlo = w.nutile[0], thi = w.nutile[TILE - 1];
@@ -1219,8 +1359,86 @@ __global__ void __launch_bounds__(LS_THREADS, CS_LS_MINBLK / LS_WARPS) line_sum_
         int64_t i = tile0 + 32 * r + lane;
         if (i < a.nnu) {
             size_t o = (size_t)lev * a.nnu + i;
-            double v = lp.scale * (acc[r] + w.cacc[32 * r + lane]);
-            a.out[o] = a.accumulate == 1 ? a.out[o] + v : (a.accumulate == 2 ? log(v) : v);
+            if (COLD) {
+                const double c = acc[r] + w.cacc[32 * r + lane];
+                a.out[o] = a.accumulate == 1 ? a.out[o] + lp.scale * c : (a.accumulate == 2 ? c : lp.scale * c);
+            } else {
+                double v = lp.scale * (acc[r] + w.cacc[32 * r + lane]);
+                a.out[o] = a.accumulate == 1 ? a.out[o] + v : (a.accumulate == 2 ? log(v) : v);
+            }
+        }
+    }
+}
+
+// K2, far wings only (direct mode, Voigt with the band correction and Lorentz): the lines inside the cut-off for EVERY point of
+// the tile -- 95 % of the window on C2 -- need no test of any kind, so they get a kernel that is nothing but the fold: same work
+// unit (one warp = tile x level, private TMA ring), a fraction of the registers and of the instruction footprint of
+// line_sum_kernel, hence more resident warps to keep the FP64 pipe fed.  Runs after line_sum_kernel<.., COLD> and completes `out`.
+constexpr int HF_STAGES = 2;
+template <int R>
+__global__ void __launch_bounds__(32, CS_LS_HOT_MINBLK) far_fold_kernel(LineSumArgs a)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[HF_STAGES];
+    constexpr int TILE = 32 * R;
+    const int lane = threadIdx.x;
+    const int lev = blockIdx.y;
+    const int64_t tile = blockIdx.x;
+    const int64_t tile0 = tile * TILE;
+    double4* ring = reinterpret_cast<double4*>(smem_raw);
+    if (lane == 0) {
+        for (int s = 0; s < HF_STAGES; s++) mbar_init(&full_bar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncwarp();
+    // the same all-inside range as line_sum_kernel computes (window-relative, clamped)
+    const int64_t* rg = a.ranges + tile * a.nr;
+    const int64_t wlo64 = rg[0];
+    const int whi = (int)(rg[1] - wlo64);
+    int ilo = (int)max(min(rg[2] - wlo64, (int64_t)whi), (int64_t)0), ihi = (int)max(min(rg[3] - wlo64, (int64_t)whi), (int64_t)0);
+    if (ilo >= ihi) { ilo = whi; ihi = whi; }
+    const int nfar = ihi - ilo;
+    const int nchunk = (nfar + LS_CHUNK - 1) / LS_CHUNK;
+    const double4* rec_far = a.rec + (size_t)lev * a.nl + wlo64 + ilo;
+    auto issue = [&](int c) {   // lane 0 only
+        const int s = c % HF_STAGES;
+        const int c0 = c * LS_CHUNK;
+        const uint32_t bytes = (uint32_t)(min(LS_CHUNK, nfar - c0)) * (uint32_t)sizeof(double4);
+        mbar_arrive_expect_tx(&full_bar[s], bytes);
+        tma_bulk_g2s(ring + (size_t)s * LS_CHUNK, rec_far + c0, bytes, &full_bar[s]);
+    };
+    if (lane == 0)
+        for (int c = 0; c < HF_STAGES && c < nchunk; c++) issue(c);
+    double nup[R], acc[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const int64_t i = tile0 + 32 * r + lane;
+        nup[r] = a.nu[i < a.nnu ? i : (a.nnu - 1)];
+        acc[r] = 0.0;
+    }
+    for (int c = 0; c < nchunk; c++) {
+        const int s = c % HF_STAGES;
+        mbar_wait(&full_bar[s], (uint32_t)((c / HF_STAGES) & 1));
+        const double4* st = ring + (size_t)s * LS_CHUNK;
+        const int n = min(LS_CHUNK, nfar - c * LS_CHUNK);
+        int j = 0;
+        fold_run<R, CS_LS_FOLD>(st, j, n, nup, acc);
+        fold_tail<R>(st, j, n, nup, acc);
+        __syncwarp();
+        if (lane == 0 && c + HF_STAGES < nchunk) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue(c + HF_STAGES);
+        }
+    }
+    const double scale = a.lev[lev].scale;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const int64_t i = tile0 + 32 * r + lane;
+        if (i < a.nnu) {
+            const size_t o = (size_t)lev * a.nnu + i;
+            const double prev = a.out[o];
+            a.out[o] = a.accumulate == 2 ? log(scale * (prev + acc[r])) : fma(scale, acc[r], prev);
         }
     }
 }
@@ -1280,14 +1498,38 @@ template <int SHAPE, int R> int32_t launch_line_sum(cs_ctx* ctx, LineSumArgs a, 
         a.ffc = fa.ffc;
     }
     size_t smem = (size_t)LS_WARPS * (LS_STAGES * LS_CHUNK * sizeof(double4) + ls_extra_bytes<SHAPE, R>());
+    constexpr bool CAN_BAND = CS_LS_BAND && SHAPE == CS_VOIGT;
+    const bool band = CAN_BAND && a.band;
     if (smem > 48 * 1024)   // per device: not cached, several contexts may live on different GPUs
     {
-        CS_CUDA(cudaFuncSetAttribute(line_sum_kernel<SHAPE, R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CS_CUDA(cudaFuncSetAttribute(line_sum_kernel<SHAPE, R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CS_CUDA(cudaFuncSetAttribute(line_sum_kernel<SHAPE, R, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CS_CUDA(cudaFuncSetAttribute(line_sum_kernel<SHAPE, R, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (CAN_BAND) {
+            CS_CUDA(cudaFuncSetAttribute(line_sum_kernel<SHAPE, R, true, CAN_BAND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CS_CUDA(cudaFuncSetAttribute(line_sum_kernel<SHAPE, R, false, CAN_BAND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        }
     }
     dim3 grid((unsigned)((a.ntiles + LS_WARPS - 1) / LS_WARPS), (unsigned)nlev);
-    if (a.mp_theta > 0.0) line_sum_kernel<SHAPE, R, true><<<grid, LS_THREADS, smem, st>>>(a);
-    else line_sum_kernel<SHAPE, R, false><<<grid, LS_THREADS, smem, st>>>(a);
+    constexpr bool CAN_SPLIT = CS_LS_SPLIT && LS_WARPS == 1 && ((SHAPE == CS_VOIGT && CAN_BAND) || SHAPE == CS_LORENTZ);
+    if (CAN_SPLIT && a.split && !(a.mp_theta > 0.0) && (band || SHAPE == CS_LORENTZ)) {
+        constexpr bool B = SHAPE == CS_VOIGT;
+        if (smem > 48 * 1024)
+            CS_CUDA(cudaFuncSetAttribute(line_sum_kernel<SHAPE, R, false, B, CAN_SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem));
+        line_sum_kernel<SHAPE, R, false, B, CAN_SPLIT><<<grid, LS_THREADS, smem, st>>>(a);
+        CS_CUDA(cudaGetLastError());
+        far_fold_kernel<R><<<dim3((unsigned)a.ntiles, (unsigned)nlev), 32, HF_STAGES * LS_CHUNK * sizeof(double4), st>>>(a);
+        CS_CUDA(cudaGetLastError());
+        cs_count_launch(ctx, 3);
+        return CS_OK;
+    }
+    if (band) {
+        if (a.mp_theta > 0.0) line_sum_kernel<SHAPE, R, true, CAN_BAND><<<grid, LS_THREADS, smem, st>>>(a);
+        else line_sum_kernel<SHAPE, R, false, CAN_BAND><<<grid, LS_THREADS, smem, st>>>(a);
+    } else {
+        if (a.mp_theta > 0.0) line_sum_kernel<SHAPE, R, true, false><<<grid, LS_THREADS, smem, st>>>(a);
+        else line_sum_kernel<SHAPE, R, false, false><<<grid, LS_THREADS, smem, st>>>(a);
+    }
     CS_CUDA(cudaGetLastError());
     cs_count_launch(ctx, 2);
     return CS_OK;
@@ -1458,6 +1700,24 @@ int32_t cs_lines_accumulate(cs_lines* L, int32_t shape, int64_t nnu, const doubl
         la.nul_lo = ln[(size_t)j0]; la.nul_hi = ln[(size_t)j1 - 1];
         double cn = 0.0;
         for (int64_t k = 0; k < kb; k++) cn = std::max(cn, hl[(size_t)k].cnear);
+        // Voigt band correction (band_near): only where the damping parameter y = gamma d is bounded below for every line of
+        // every level of the batch -- gamma >= min((296/T)^na) (ga_min (P - Pp) + gs_min Pp)/atm, d >= sqrt(ln 2)/(nul_max vth)
+        la.band = 0;
+        if (shape == CS_VOIGT) {
+            double ymin = 1e300;
+            for (int64_t k = 0; k < kb; k++) {
+                const LevelParams& lp = hl[(size_t)k];
+                const double tr = CS_TREF / lp.T;
+                const double gmin = std::min(pow(tr, L->na_min), pow(tr, L->na_max)) *
+                                    (L->ga_min * (lp.P - lp.Pp) + L->gs_min * lp.Pp) / CS_ATM;
+                const double vth = sqrt(2.0 * CS_R * lp.T / L->mu_min) / CS_C;
+                const double dmin = 0.83255461115769775635 / (std::max(la.nul_hi, 1e-300) * vth);
+                ymin = std::min(ymin, gmin * dmin);
+            }
+            la.band = (ymin >= 1e-5) ? 1 : 0;      // also false for NaN / negative bounds
+            if (ctx->ls_no_band) la.band = 0;
+        }
+        la.split = ctx->ls_no_split ? 0 : 1;
         switch (shape) {
         case CS_DOPPLER: CS_TRY((launch_line_sum<CS_DOPPLER, 4>(ctx, la, (int)kb, cn))); break;
         // expansion mode: what is left for the pair-by-pair sum scales with the tile width (cut-off edges, lines within 4 half
