@@ -31,9 +31,10 @@ sys.path.insert(0, ROOT)
 METRIC = "line×ν×layer evals/s"
 UNIT = "evals/s"
 FLOP_PER_EVAL = 10.0   # Voigt, far-wing dominated
-# dram__bytes_read.sum + dram__bytes_write.sum of one line_sum_kernel<VOIGT> launch (one gas, 101 levels) on C2, from the
-# ncu --set full capture summarised in profiles/r1_ncu_full_line_sum_voigt.csv
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 1.662827e9 + 0.237128e9
+# dram__bytes_read.sum + dram__bytes_write.sum of the line sum of one gas (101 levels) on C2 = its two launches,
+# line_sum_kernel<VOIGT, COLD> (1.661 + 0.232 GB) + far_fold_kernel<4> (1.094 + 0.311 GB), from the ncu --set full capture
+# summarised in profiles/r2_ncu_full_line_sum_voigt_split.csv
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 1.660745e9 + 0.232055e9 + 1.094015e9 + 0.311331e9
 
 
 # ------------------------------------------------------------------------------------------------
@@ -447,12 +448,13 @@ def run_ours(args):
                 "max_rel_diff_fluxes_vs_resident": float(np.max(np.abs(Fe - F) / np.maximum(np.abs(F), 1e-300)))},
         "gpu_launches": int(launches),
         "clocks": clk.summary(),
-        "roofline": {"bound": "fp64", "kernel": "line_sum_kernel<VOIGT>", "achieved": achieved, "peak": fp64_peak / 1e12,
+        "roofline": {"bound": "fp64", "kernel": "Voigt line sum = line_sum_kernel<VOIGT, COLD> + far_fold_kernel<4> (two launches per gas)",
+                     "achieved": achieved, "peak": fp64_peak / 1e12,
                      "unit": "TFLOP/s", "frac": (achieved / (fp64_peak / 1e12)) if achieved else None,
                      "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH if wl["name"] == "c2" and world == 1 else None,
                      "peak_source": "cs_fp64_peak DFMA microbenchmark run in this process (FP64 is not in MEASURED_PEAKS.json; "
                                     "recorded with clocks in profiles/r2_fp64_peak.json)",
-                     "flop_per_eval": FLOP_PER_EVAL, "kernel_ms_per_step": ls_ms, "launches_per_step": n_ls_launch,
+                     "flop_per_eval": FLOP_PER_EVAL, "kernel_ms_per_step": ls_ms, "launches_per_step": 2 * n_ls_launch,
                      "kernel_share_of_step": ls_ms / ms_step if ms_step > 0 else None,
                      "rt_kernel_ms_per_step": timers_acc["rt"] / args.steps,
                      "prep_kernel_ms_per_step": timers_acc["prep"] / args.steps},

@@ -50,7 +50,7 @@ namespace {
 #define CS_LS_SPLIT 1
 #endif
 #ifndef CS_LS_COLD_MINBLK   // resident one-warp CTAs per SM of line_sum_kernel<.., COLD> (latency-bound: more warps, fewer registers)
-#define CS_LS_COLD_MINBLK 24
+#define CS_LS_COLD_MINBLK 16
 #endif
 #ifndef CS_LS_HOT_MINBLK    // resident one-warp CTAs per SM of far_fold_kernel
 #define CS_LS_HOT_MINBLK 16
@@ -1498,14 +1498,15 @@ template <int SHAPE, int R> int32_t launch_line_sum(cs_ctx* ctx, LineSumArgs a, 
         a.ffc = fa.ffc;
     }
     size_t smem = (size_t)LS_WARPS * (LS_STAGES * LS_CHUNK * sizeof(double4) + ls_extra_bytes<SHAPE, R>());
+    // the band correction pays in direct mode (the near lines ride the long far-wing fold); in expansion mode the direct fold is
+    // short and the per-tile cold_near measured faster (26.6 against 27.9 ms on C2)
     constexpr bool CAN_BAND = CS_LS_BAND && SHAPE == CS_VOIGT;
-    const bool band = CAN_BAND && a.band;
+    const bool band = CAN_BAND && a.band && !(a.mp_theta > 0.0);
     if (smem > 48 * 1024)   // per device: not cached, several contexts may live on different GPUs
     {
         CS_CUDA(cudaFuncSetAttribute(line_sum_kernel<SHAPE, R, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CS_CUDA(cudaFuncSetAttribute(line_sum_kernel<SHAPE, R, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         if (CAN_BAND) {
-            CS_CUDA(cudaFuncSetAttribute(line_sum_kernel<SHAPE, R, true, CAN_BAND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             CS_CUDA(cudaFuncSetAttribute(line_sum_kernel<SHAPE, R, false, CAN_BAND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         }
     }
@@ -1524,8 +1525,7 @@ template <int SHAPE, int R> int32_t launch_line_sum(cs_ctx* ctx, LineSumArgs a, 
         return CS_OK;
     }
     if (band) {
-        if (a.mp_theta > 0.0) line_sum_kernel<SHAPE, R, true, CAN_BAND><<<grid, LS_THREADS, smem, st>>>(a);
-        else line_sum_kernel<SHAPE, R, false, CAN_BAND><<<grid, LS_THREADS, smem, st>>>(a);
+        line_sum_kernel<SHAPE, R, false, CAN_BAND><<<grid, LS_THREADS, smem, st>>>(a);      // direct mode only (see above)
     } else {
         if (a.mp_theta > 0.0) line_sum_kernel<SHAPE, R, true, false><<<grid, LS_THREADS, smem, st>>>(a);
         else line_sum_kernel<SHAPE, R, false, false><<<grid, LS_THREADS, smem, st>>>(a);

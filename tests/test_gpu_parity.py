@@ -143,6 +143,41 @@ def test_xsec_line_centres(cs, orc, co2):
     assert relerr(got, ref, 1e-290) < XSEC_TOL
 
 
+def test_voigt_direct_sum_variants(cs, orc, monkeypatch):
+    """direct-mode Voigt is two launches by default (cold classes with the per-point band correction, then far_fold_kernel);
+    CS_LINESUM_NO_SPLIT keeps the band in one launch, CS_LINESUM_NO_BAND is the per-tile near range.  All three against the
+    oracle on a grid that crosses line centres at 10 Pa .. 1 bar; a level at 1e-5 Pa (damping parameter below the bound the
+    band correction needs) must silently take the per-tile path and still agree"""
+    sl = synthetic_lines(cs, 4000, seed=11, νmax=160.0)
+    ν = 40.0 + 0.01 * np.arange(7013)
+    ν[100:140] = np.sort(sl.ν[(sl.ν > 41.0) & (sl.ν < 110.0)][:40])          # points exactly on line centres
+    ν = np.unique(ν)
+    P = np.array([10.0, 2e3, 1e5])
+    T = np.array([160.0, 230.0, 296.0])
+    Pp = np.array([1e-2, 1.0, 3e4])
+    ref = orc.xsec(orc.VOIGT, sl, ν, T, P, Pp, 25.0, nthreads=0)
+    lref = orc.xsec(orc.LORENTZ, sl, ν, T, P, Pp, 25.0, nthreads=0)
+    Plow = np.array([1e-5, 10.0])
+    reflow = orc.xsec(orc.VOIGT, sl, ν[:1500], T[:2], Plow, 1e-3 * Plow, 25.0, nthreads=0)
+    for env in ({}, {"CS_LINESUM_NO_SPLIT": "1"}, {"CS_LINESUM_NO_BAND": "1"}):
+        for k in ("CS_LINESUM_NO_SPLIT", "CS_LINESUM_NO_BAND"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        ctx = cs.Context(0)                       # the switches are read when a context is created
+        try:
+            n0 = ctx.launches()
+            got = cs.xsec("voigt", ν, sl, T, P, Pp, 25.0, ctx=ctx)
+            nlaunch = ctx.launches() - n0
+            assert relerr(got, ref, 1e-290) < XSEC_TOL, env
+            assert nlaunch == (4 if not env else 3), (env, nlaunch)      # prep + ranges + (cold, far fold | one line-sum kernel)
+            assert relerr(cs.xsec("lorentz", ν, sl, T, P, Pp, 25.0, ctx=ctx), lref, 1e-290) < XSEC_TOL, env
+            assert relerr(cs.xsec("voigt", ν[:1500], sl, T[:2], Plow, 1e-3 * Plow, 25.0, ctx=ctx), reflow, 1e-290) < XSEC_TOL, env
+        finally:
+            sl.__dict__.pop("_dev", None)         # the uploaded copy goes before its context
+            ctx.close()
+
+
 def test_xsec_cutoff_is_inclusive(cs, orc):
     """a point exactly Δνcut away from a line is included (line_shapes.jl:10); the strict prefilter
     (line_shapes.jl:18-22) drops a line sitting exactly at min(ν) - cut"""

@@ -68,9 +68,13 @@ def worker(nlev):
 def time_all(nlev):
     import numpy as np
     names = sorted(os.listdir(VAR))
-    for n in names:
-        env = dict(os.environ, CLEARSKY_B200_LIB=os.path.join(VAR, n, "libclearsky_b200.so"), K2_NAME=n)
+    # K2_ENVS="CS_LINESUM_NCOLD=0;CS_LINESUM_NCOLD=4": every built variant is also timed under each of these run-time settings
+    envs = [e for e in os.environ.get("K2_ENVS", "").split(";") if e]
+    runs = [(n, n, {}) for n in names] if not envs else [(n, f"{n}[{e}]", dict([e.split("=", 1)])) for n in names for e in envs]
+    for n, label, extra in runs:
+        env = dict(os.environ, CLEARSKY_B200_LIB=os.path.join(VAR, n, "libclearsky_b200.so"), K2_NAME=label, **extra)
         subprocess.call([sys.executable, os.path.abspath(__file__), "worker", str(nlev)], env=env)
+    names = [label for _, label, _ in runs]
     for mode in ("direct", "expansion"):
         ref = np.load(f"/tmp/k2var_{names[0]}_{mode}.npy")
         for n in names[1:]:

@@ -26,15 +26,15 @@ WANT = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
 def main(rep, out):
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
-    hdr, units, vals = rows[0], rows[1], rows[2]
-    name = vals[hdr.index("Kernel Name")] if "Kernel Name" in hdr else ""
+    hdr, units, kernels = rows[0], rows[1], rows[2:]          # one row per captured launch
+    names = [k[hdr.index("Kernel Name")] if "Kernel Name" in hdr else "" for k in kernels]
     with open(out, "w") as f:
-        f.write("metric,unit,value\n")
-        f.write(f"kernel,,\"{name}\"\n")
+        f.write("metric,unit," + ",".join(f"value_{i}" for i in range(len(kernels))) + "\n" if len(kernels) > 1 else "metric,unit,value\n")
+        f.write("kernel,," + ",".join(f'"{n}"' for n in names) + "\n")
         for w in WANT:
             if w in hdr:
                 i = hdr.index(w)
-                f.write(f"{w},{units[i]},{vals[i]}\n")
+                f.write(f"{w},{units[i]}," + ",".join(k[i] for k in kernels) + "\n")
 
 
 if __name__ == "__main__":
