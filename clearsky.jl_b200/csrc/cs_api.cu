@@ -65,7 +65,7 @@ static int32_t ctx_create(int32_t device, void* stream, bool own, cs_ctx** out)
     c->own_stream = own;
     {
         DevBuf* bufs[] = {&c->s_nu, &c->s_lev, &c->s_rec, &c->s_slow, &c->s_sigma, &c->s_misc, &c->s_part,
-                          &c->s_tau, &c->s_planck, &c->s_out0, &c->s_out1, &c->s_out2, &c->s_w};
+                          &c->s_tau, &c->s_planck, &c->s_out0, &c->s_out1, &c->s_out2, &c->s_w, &c->s_q};
         for (DevBuf* b : bufs) b->st = c->stream;
     }
     // environment switches are read once here, never in a launch path
@@ -99,7 +99,7 @@ extern "C" int32_t cs_ctx_free(cs_ctx* c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     DevBuf* bufs[] = {&c->s_nu, &c->s_lev, &c->s_rec, &c->s_slow, &c->s_sigma, &c->s_misc, &c->s_part,
-                      &c->s_tau, &c->s_planck, &c->s_out0, &c->s_out1, &c->s_out2, &c->s_w};
+                      &c->s_tau, &c->s_planck, &c->s_out0, &c->s_out1, &c->s_out2, &c->s_w, &c->s_q};
     for (DevBuf* b : bufs) b->release();
     for (TimerSpan& sp : c->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (cudaEvent_t e : c->ev_free) cudaEventDestroy(e);
@@ -373,6 +373,17 @@ extern "C" int32_t cs_lines_upload(cs_ctx* ctx, int64_t n, const double* nu, con
         cs_lines_free(L);
         return rc;
     }
+    if (cudaMallocAsync(&L->dref, sizeof(double) * (size_t)n, st) != cudaSuccess) {
+        cudaGetLastError();
+        cs_set_error("cs_lines_upload: out of device memory");
+        L->dref = nullptr;
+        cs_lines_free(L);
+        return CS_ERR_NOMEM;
+    }
+    if ((rc = cs_lines_static(L))) {
+        cs_lines_free(L);
+        return rc;
+    }
     // the caller's arrays are only valid for the duration of the call: wait for the copies
     cudaError_t e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) {
@@ -401,7 +412,7 @@ extern "C" int32_t cs_lines_free(cs_lines* L)
     cudaSetDevice(L->ctx->device);
     cudaStream_t st = L->ctx->stream;
     cs_free(L->nu, st); cs_free(L->S, st); cs_free(L->ga, st); cs_free(L->gs, st); cs_free(L->Epp, st); cs_free(L->na, st);
-    cs_free(L->mu, st); cs_free(L->iso, st); cs_free(L->ncheb, st); cs_free(L->cheb, st);
+    cs_free(L->mu, st); cs_free(L->dref, st); cs_free(L->iso, st); cs_free(L->ncheb, st); cs_free(L->cheb, st);
     delete L;
     return CS_OK;
 }

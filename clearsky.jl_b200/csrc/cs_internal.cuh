@@ -117,7 +117,7 @@ struct cs_ctx {
     std::recursive_mutex mtx;
     // scratch
     DevBuf s_nu, s_lev, s_rec, s_slow, s_sigma, s_misc, s_part, s_tau, s_planck, s_out0, s_out1, s_out2;
-    DevBuf s_w;
+    DevBuf s_w, s_q;
     // kernel timing (ms), measured with CUDA events on ctx->stream and read lazily
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
     std::vector<TimerSpan> spans;          // recorded, not yet read
@@ -141,6 +141,7 @@ struct cs_lines {
     int64_t n;
     // device SoA (sorted by wavenumber, as SpectralLines guarantees: par.jl:267)
     double *nu, *S, *ga, *gs, *Epp, *na, *mu;
+    double* dref = nullptr;   // per line: level-independent denominator of scaleintensity (line_static_kernel)
     int16_t* iso;
     int32_t niso;
     int32_t* ncheb;   // [niso]
@@ -357,6 +358,7 @@ void cs_span_end(cs_ctx* c, int span);
 void cs_spans_collect(cs_ctx* c, bool block);
 // asynchronous host->device copy of a small parameter block through the context's pinned staging ring
 int32_t cs_stage_h2d(cs_ctx* c, void* dst, const void* src, size_t bytes);
+int32_t cs_lines_static(cs_lines* L);
 int32_t cs_lines_accumulate(cs_lines* L, int32_t shape, int64_t nnu, const double* d_nu,
                             const double* h_nu, int64_t nlev, const double* h_T, const double* h_P,
                             const double* h_Pp, const double* h_scale, double cut, double* d_out,

@@ -86,6 +86,7 @@ struct LevelParams {
     double B1, B2;   // PHCO2 chi coefficients of this level (line_shapes.jl:472,476)
     double cnear;    // lines with |nul - nu| > cnear*nul are safely in the far wing at this level (< 0: no near range)
     double pexp_ok;  // PHCO2: 1 when (chi*gamma/dnu)^2 < 1e-4 for every line with |dnu| >= 30 at this level (expansion allowed)
+    double lgtr;     // log(296/T): (296/T)^na = exp(na lgtr) in K1 (one exp instead of a pow per line and level)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -93,6 +94,9 @@ struct LevelParams {
 // alpha-doppler (:144), gamma-lorentz (:255-257); then the shape-specific record.
 struct PrepArgs {
     const double *nu, *S, *ga, *gs, *Epp, *na, *mu;
+    const double* dref;        // per line: exp(-c2 E''/296) (1 - exp(-c2 nul/296)), the level-independent denominator of scaleintensity
+    const double* qtab;        // [nlev][niso] Qref/Q(T) (chebyQrefQ depends on the isotopologue and the level only)
+    int niso;
     const int16_t* iso;
     const int32_t* ncheb;
     const double* cheb;
@@ -118,24 +122,13 @@ __global__ void __launch_bounds__(256) prep_kernel(PrepArgs a)
     double ea = -c2 * a.Epp[j];
     double eb = -c2 * nul;
     double n = exp(ea / T) * (1 - exp(eb / T));
-    double d = exp(ea / CS_TREF) * (1 - exp(eb / CS_TREF));
+    double d = a.dref[j];                                  // level-independent: computed once per line list (line_static_kernel)
     int is = a.iso[j] - 1;
-    const double* ch = a.cheb + (size_t)is * CS_MAXCHEB;
-    int nch = a.ncheb[is];
-    double tau = 2 * (T - CS_TMIN) / (CS_TMAX - CS_TMIN) - 1;
-    double c1 = 1.0, c2c = tau;
-    double y = ch[0] + ch[1] * c2c;
-    for (int q = 2; q < nch; q++) {
-        double c3 = 2 * tau * c2c - c1;
-        y += ch[q] * c3;
-        c1 = c2c;
-        c2c = c3;
-    }
-    double QrefQ = 1.0 / y;
+    double QrefQ = a.qtab[(size_t)k * a.niso + is];        // per (isotopologue, level): qrefq_kernel
     double S = a.S[j] * QrefQ * (n / d);
     // --- widths
     double alpha = (nul / CS_C) * sqrt(2.0 * CS_R * T / a.mu[j]);
-    double gamma = (pow(CS_TREF / T, a.na[j])) * (a.ga[j] * (lp.P - lp.Pp) + a.gs[j] * lp.Pp) / CS_ATM;
+    double gamma = exp(a.na[j] * lp.lgtr) * (a.ga[j] * (lp.P - lp.Pp) + a.gs[j] * lp.Pp) / CS_ATM;
     const double sqpi = 1.7724538509055160273;       // sqrt(pi)
     const double sqln2 = 0.83255461115769775635;     // sqrt(log(2))
     const double osqpiln2 = 0.46971863934982566689;  // 1/sqrt(pi/log(2))
@@ -159,6 +152,39 @@ __global__ void __launch_bounds__(256) prep_kernel(PrepArgs a)
     size_t o = (size_t)k * a.nl + jj;
     a.rec[o] = r;
     if (a.slow) a.slow[o] = s;
+}
+
+// level-independent part of scaleintensity (line_shapes.jl:122), once per line list
+__global__ void __launch_bounds__(256) line_static_kernel(const double* __restrict__ nu, const double* __restrict__ Epp, int64_t n,
+                                                          double* __restrict__ dref)
+{
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const double c2 = 100.0 * CS_H * CS_C / CS_KB;
+    double ea = -c2 * Epp[j], eb = -c2 * nu[j];
+    dref[j] = exp(ea / CS_TREF) * (1 - exp(eb / CS_TREF));
+}
+
+// chebyQrefQ (line_shapes.jl:27-48) per (level, isotopologue): forward recurrence starting from a[1] + a[2] tau
+__global__ void qrefq_kernel(const LevelParams* __restrict__ lev, const int32_t* __restrict__ ncheb, const double* __restrict__ cheb,
+                             int niso, double* __restrict__ qtab)
+{
+    const int is = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = blockIdx.y;
+    if (is >= niso) return;
+    const double T = lev[k].T;
+    const double* ch = cheb + (size_t)is * CS_MAXCHEB;
+    const int nch = ncheb[is];
+    double tau = 2 * (T - CS_TMIN) / (CS_TMAX - CS_TMIN) - 1;
+    double c1 = 1.0, c2c = tau;
+    double y = ch[0] + ch[1] * c2c;
+    for (int q = 2; q < nch; q++) {
+        double c3 = 2 * tau * c2c - c1;
+        y += ch[q] * c3;
+        c1 = c2c;
+        c2c = c3;
+    }
+    qtab[(size_t)k * niso + is] = 1.0 / y;
 }
 
 // first j in [lo,hi) for which pred(nul[j]) is false, given pred is true on a prefix
@@ -1568,6 +1594,16 @@ __global__ void fill_kernel(double* p, size_t n, double v)
 
 }  // namespace
 
+// called by cs_lines_upload once the line arrays are on the device
+int32_t cs_lines_static(cs_lines* L)
+{
+    cudaStream_t st = L->ctx->stream;
+    line_static_kernel<<<(unsigned)((L->n + 255) / 256), 256, 0, st>>>(L->nu, L->Epp, L->n, L->dref);
+    CS_CUDA(cudaGetLastError());
+    cs_count_launch(L->ctx);
+    return CS_OK;
+}
+
 extern "C" int32_t cs_line_params(cs_lines* L, double T, double P, double Pp, double* S_T, double* alpha, double* gamma)
 {
     CS_REQUIRE(L, CS_ERR_ARG, "null argument");
@@ -1577,13 +1613,14 @@ extern "C" int32_t cs_line_params(cs_lines* L, double T, double P, double Pp, do
     std::lock_guard<std::recursive_mutex> lk(ctx->mtx);
     CS_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
-    LevelParams lp = {T, P, Pp, 1.0, 0, 0, 0, 0};
+    LevelParams lp = {T, P, Pp, 1.0, 0, 0, 0, 0, 0};
     CS_TRY(ctx->s_lev.reserve(sizeof(LevelParams)));
     CS_TRY(ctx->s_misc.reserve(sizeof(double) * 3 * (size_t)L->n));
     CS_CUDA(cudaMemcpyAsync(ctx->s_lev.p, &lp, sizeof(lp), cudaMemcpyHostToDevice, st));
     PrepArgs pa;
     pa.nu = L->nu; pa.S = L->S; pa.ga = L->ga; pa.gs = L->gs; pa.Epp = L->Epp; pa.na = L->na; pa.mu = L->mu;
     pa.iso = L->iso; pa.ncheb = L->ncheb; pa.cheb = L->cheb; pa.j0 = 0; pa.nl = L->n;
+    pa.dref = L->dref; pa.qtab = nullptr; pa.niso = L->niso;
     pa.lev = ctx->s_lev.as<LevelParams>(); pa.nlev = 1; pa.rec = nullptr; pa.slow = nullptr; pa.shape = CS_VOIGT;
     double* d = ctx->s_misc.as<double>();
     line_params_kernel<<<(unsigned)((L->n + 255) / 256), 256, 0, st>>>(pa, d, d + L->n, d + 2 * L->n);
@@ -1644,6 +1681,7 @@ int32_t cs_lines_accumulate(cs_lines* L, int32_t shape, int64_t nnu, const doubl
     CS_TRY(ctx->s_rec.reserve((size_t)nb * nl * sizeof(double4)));
     if (need_slow) CS_TRY(ctx->s_slow.reserve((size_t)nb * nl * sizeof(double4)));
     CS_TRY(ctx->s_lev.reserve(sizeof(LevelParams) * (size_t)nb));
+    CS_TRY(ctx->s_q.reserve(sizeof(double) * (size_t)nb * (size_t)L->niso));
 
     std::vector<LevelParams> hl((size_t)nb);
     for (int64_t k0 = 0; k0 < nlev; k0 += nb) {
@@ -1656,6 +1694,7 @@ int32_t cs_lines_accumulate(cs_lines* L, int32_t shape, int64_t nnu, const doubl
             lp.scale = h_scale ? h_scale[k0 + k] : 1.0;
             lp.B1 = 0.0888 - 0.16 * exp(-0.0041 * lp.T);   // line_shapes.jl:472
             lp.B2 = 0.0526 * exp(-0.00152 * lp.T);          // line_shapes.jl:476
+            lp.lgtr = log(CS_TREF / lp.T);
             // near-centre half width as a fraction of the line position: sqrt(thr_j) = nul_j * f(T, mu_j)
             double vth = sqrt(2.0 * CS_R * lp.T / L->mu_min) / CS_C;
             if (shape == CS_VOIGT || shape == CS_PHCO2)
@@ -1680,15 +1719,19 @@ int32_t cs_lines_accumulate(cs_lines* L, int32_t shape, int64_t nnu, const doubl
         PrepArgs pa;
         pa.nu = L->nu; pa.S = L->S; pa.ga = L->ga; pa.gs = L->gs; pa.Epp = L->Epp; pa.na = L->na; pa.mu = L->mu;
         pa.iso = L->iso; pa.ncheb = L->ncheb; pa.cheb = L->cheb;
+        pa.dref = L->dref; pa.qtab = ctx->s_q.as<double>(); pa.niso = L->niso;
         pa.j0 = j0; pa.nl = nl; pa.lev = ctx->s_lev.as<LevelParams>(); pa.nlev = (int)kb;
         pa.rec = ctx->s_rec.as<double4>();
         pa.slow = need_slow ? ctx->s_slow.as<double4>() : nullptr;
         pa.shape = shape;
         const int sp_prep = cs_span_begin(ctx, CS_T_PREP, false);
         dim3 pg((unsigned)((nl + 255) / 256), (unsigned)kb);
+        qrefq_kernel<<<dim3((unsigned)((L->niso + 63) / 64), (unsigned)kb), 64, 0, st>>>(pa.lev, L->ncheb, L->cheb, L->niso,
+                                                                                      ctx->s_q.as<double>());
+        CS_CUDA(cudaGetLastError());
         prep_kernel<<<pg, 256, 0, st>>>(pa);
         CS_CUDA(cudaGetLastError());
-        cs_count_launch(ctx);
+        cs_count_launch(ctx, 2);
         cs_span_end(ctx, sp_prep);
         const int sp_sum = cs_span_begin(ctx, CS_T_LINESUM, false);
 
