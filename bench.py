@@ -727,7 +727,34 @@ def run_c5(args):
     dF = torch.zeros(2 * nrad, dtype=torch.float64, device=dev)
     T0 = f64(col.T)
 
+    # the step's only exchange: 2*nrad doubles.  Default for N > 1: fused into the step's tail kernel through peer-memory
+    # mailboxes (CUDA IPC between the ranks, stores over NVLink, cs_rcm_enqueue_step_peer); --c5-collective nccl keeps the
+    # NCCL all-reduce between the flux kernels and the column update
+    peer = world > 1 and args.c5_collective == "peer"
+    opened = []
+    if peer:
+        box, nb = C.c_void_p(), C.c_int64()
+        check(lib().cs_rcm_peer_mailbox(h, world, C.byref(box), C.byref(nb)))
+        hb = (C.c_uint8 * 64)()
+        check(lib().cs_ipc_export(box, hb))
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(hb))
+        ptrs = (C.c_void_p * world)()
+        for q in range(world):
+            if q == rank:
+                ptrs[q] = box.value
+            else:
+                pq = C.c_void_p()
+                check(lib().cs_ipc_open(ctx.h, (C.c_uint8 * 64).from_buffer_copy(handles[q]), C.byref(pq)))
+                ptrs[q] = pq.value
+                opened.append(pq)
+        check(lib().cs_rcm_peer_connect(h, rank, world, ptrs))
+        dist.barrier()
+
     def enqueue_step():
+        if peer:
+            check(lib().cs_rcm_enqueue_step_peer(h, C5_DT))
+            return
         check(lib().cs_rcm_enqueue_fluxes(h, dF.data_ptr()))
         if world > 1:
             dist.all_reduce(dF)
@@ -822,7 +849,11 @@ def run_c5(args):
             "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": c5_config(wl, world, nrad),
             "olr_w_m2": float(Fup[0]), "T_surface_K": float(Tend[-1]), "setup_s": t_setup,
-            "step_launch": "cuda-graph replay (flux kernels + all-reduce + column update)" if graph is not None else "plain launches",
+            "step_launch": ("cuda-graph replay" if graph is not None else "plain launches") +
+                           (" (flux kernels + one tail kernel: peer-memory exchange over NVLink + column update)" if peer
+                            else " (flux kernels + all-reduce + column update)"),
+            "collective": ("fused into the step's tail kernel (peer-memory mailboxes, CUDA IPC)" if peer else
+                           ("NCCL all-reduce of 2*nrad doubles" if world > 1 else "none (one rank)")),
             "e2e": {"value": 1.0 / dte, "unit": C5_UNIT, "h2d_bytes_per_step": int(npc * 8), "d2h_bytes_per_step": int((2 * npc + 2 * nrad) * 8),
                     "ms_per_step": dte * 1e3, "steps": args.steps, "host_memory": "pinned",
                     "max_rel_diff_T_vs_resident": float(np.max(np.abs(Th - Tend) / Tend))},
@@ -873,6 +904,16 @@ def run_c5(args):
     graph = None
     gc.collect()
     torch.cuda.synchronize()
+    if peer:
+        late = C.c_int32(0)
+        check(lib().cs_rcm_peer_status(h, None, C.byref(late)))
+        if late.value:
+            print("bench.py: a rank's partial fluxes did not arrive within the time limit of the fused step", file=sys.stderr)
+            parity_fail = parity_fail or {"peer_exchange": "timed out"}
+        dist.barrier()                   # nobody unmaps a mailbox another rank may still be writing to
+        for pq in opened:
+            lib().cs_ipc_close(ctx.h, pq)
+        dist.barrier()
     lib().cs_rcm_free(h)
     _shutdown(dist, world)
     if parity_fail is not None:
@@ -942,6 +983,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-expansion", action="store_true", help="skip the extra far-field-expansion measurement")
     ap.add_argument("--no-graph", action="store_true", help="c5: plain launches instead of a CUDA graph per step")
+    ap.add_argument("--c5-collective", default="peer", choices=["peer", "nccl"],
+                    help="c5, N > 1: exchange of the 2*nrad partial fluxes -- fused into the step's tail kernel over peer memory "
+                         "(default) or an NCCL all-reduce between the flux kernels and the column update")
     ap.add_argument("--single-process", action="store_true",
                     help="c2: drive all --gpus N devices from THIS process through the library's own device group (cs_group_*: one "
                          "host thread per device, ncclAllReduce inside the library) instead of one torchrun rank per GPU")

@@ -99,6 +99,13 @@ SIGNATURES = {
     "cs_rcm_enqueue_fluxes": [_vp, _vp],
     "cs_rcm_enqueue_update": [_vp, _vp, C.c_double],
     "cs_rcm_flux_buffer": [_vp, C.POINTER(_vp)],
+    "cs_rcm_peer_mailbox": [_vp, C.c_int32, C.POINTER(_vp), C.POINTER(C.c_int64)],
+    "cs_rcm_peer_connect": [_vp, C.c_int32, C.c_int32, C.POINTER(_vp)],
+    "cs_rcm_enqueue_step_peer": [_vp, C.c_double],
+    "cs_rcm_peer_status": [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int32)],
+    "cs_ipc_export": [_vp, C.POINTER(C.c_uint8)],
+    "cs_ipc_open": [_vp, C.POINTER(C.c_uint8), C.POINTER(_vp)],
+    "cs_ipc_close": [_vp, _vp],
 }
 
 _lib = None

@@ -54,6 +54,8 @@ struct cs_group {
     std::vector<ncclComm_t> comm;
     NcclApi nccl;
     std::mutex mtx;
+    bool peer_ok = false;        // every device of the group can map every other one's memory (NVLink / NVSwitch peer access)
+    bool rcm_nccl = false;       // CS_GROUP_RCM_NCCL: keep the NCCL all-reduce in cs_group_rcm_step
 };
 
 extern "C" int32_t cs_group_create(int32_t ndev, const int32_t* devices, cs_group** out)
@@ -83,6 +85,24 @@ extern "C" int32_t cs_group_create(int32_t ndev, const int32_t* devices, cs_grou
             g->comm.clear();
             cs_group_free(g);
             return CS_ERR_CUDA;
+        }
+    }
+    // peer access between all pairs (the fused RCM step stores its partial sums straight into the other devices' mailboxes)
+    g->rcm_nccl = getenv("CS_GROUP_RCM_NCCL") != nullptr;
+    g->peer_ok = ndev > 1;
+    for (int i = 0; i < ndev && g->peer_ok; i++) {
+        for (int j = 0; j < ndev && g->peer_ok; j++) {
+            if (i == j) continue;
+            int can = 0;
+            if (g->dev[(size_t)i] == g->dev[(size_t)j] ||
+                cudaDeviceCanAccessPeer(&can, g->dev[(size_t)i], g->dev[(size_t)j]) != cudaSuccess || !can) {
+                g->peer_ok = g->dev[(size_t)i] == g->dev[(size_t)j] ? g->peer_ok : false;
+                continue;
+            }
+            cudaSetDevice(g->dev[(size_t)i]);
+            cudaError_t e = cudaDeviceEnablePeerAccess(g->dev[(size_t)j], 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) g->peer_ok = false;
+            cudaGetLastError();
         }
     }
     *out = g;
@@ -162,9 +182,11 @@ extern "C" int32_t cs_group_read(cs_group* g, int32_t i, int64_t count, double* 
 }
 
 // radiative-convective steps on a nu-sharded column: every device holds the same column state and its own slice of the
-// spectrum.  Per step and device: partial fluxes (2 kernels) -> ONE ncclAllReduce of 2*nrad doubles -> column update
-// (1 kernel), all enqueued from this one host thread without any synchronisation until the last step; the devices then
-// hold bit-identical temperatures (same summed fluxes, same arithmetic).
+// spectrum.  With peer access between the devices a step is two kernels per device and no collective call: the flux
+// kernel and a tail kernel that exchanges the 2*nrad partial sums through peer-memory mailboxes and updates the column
+// (cs_rcm_enqueue_step_peer).  Otherwise (or with CS_GROUP_RCM_NCCL set): partial fluxes (2 kernels) -> ONE ncclAllReduce of
+// 2*nrad doubles -> column update (1 kernel).  Everything is enqueued from this one host thread without any synchronisation
+// until the last step; the devices then hold bit-identical temperatures (same summed fluxes, same arithmetic).
 extern "C" int32_t cs_group_rcm_step(cs_group* g, cs_rcm* const* rcm, double dt, int64_t nsteps)
 {
     CS_REQUIRE(g && rcm && nsteps >= 0, CS_ERR_ARG, "bad arguments");
@@ -186,6 +208,28 @@ extern "C" int32_t cs_group_rcm_step(cs_group* g, cs_rcm* const* rcm, double dt,
         CS_CUDA(cudaSetDevice(g->dev[(size_t)i]));
         CS_TRY(g->buf[(size_t)i].reserve(sizeof(double) * 2 * (size_t)nrad));
         buf[(size_t)i] = g->buf[(size_t)i].as<double>();
+    }
+    if (n > 1 && g->peer_ok && !g->rcm_nccl) {
+        // fused form: no collective call -- each device's tail kernel stores its partial sums into every mailbox and sums
+        // what arrives in its own (cs_rt.cu: rcm_tail_kernel).  Mailboxes are created and connected on first use.
+        int64_t done = 0;
+        int32_t late = 0;
+        if (cs_rcm_peer_status(rcm[0], &done, &late) != CS_OK) {
+            std::vector<void*> box((size_t)n, nullptr);
+            for (int i = 0; i < n; i++) CS_TRY(cs_rcm_peer_mailbox(rcm[i], n, &box[(size_t)i], nullptr));
+            for (int i = 0; i < n; i++) CS_TRY(cs_rcm_peer_connect(rcm[i], i, n, box.data()));
+        }
+        for (int64_t k = 0; k < nsteps; k++)
+            for (int i = 0; i < n; i++) CS_TRY(cs_rcm_enqueue_step_peer(rcm[i], dt));
+        for (int i = 0; i < n; i++) {
+            CS_CUDA(cudaSetDevice(g->dev[(size_t)i]));
+            CS_CUDA(cudaStreamSynchronize(g->ctx[(size_t)i]->stream));
+        }
+        for (int i = 0; i < n; i++) {
+            CS_TRY(cs_rcm_peer_status(rcm[i], &done, &late));
+            CS_REQUIRE(!late, CS_ERR_CUDA, "device %d: the partial fluxes of another device did not arrive within the time limit", i);
+        }
+        return CS_OK;
     }
     for (int64_t k = 0; k < nsteps; k++) {
         for (int i = 0; i < n; i++) CS_TRY(cs_rcm_enqueue_fluxes(rcm[i], buf[(size_t)i]));

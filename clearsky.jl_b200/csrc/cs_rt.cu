@@ -12,6 +12,7 @@
 // with warp shuffles, then across warps in shared memory, and finally across CTAs by a second, fixed-order
 // kernel (run-to-run bit-stable; no atomics).
 #include "cs_internal.cuh"
+#include <cstring>
 #include <algorithm>
 #include <cmath>
 
@@ -924,9 +925,8 @@ __device__ __forceinline__ double rcm_lin(const double* x, const double* y, int 
     return __dadd_rn(__ddiv_rn(__dmul_rn(q - x[i], y[i + 1] - y[i]), x[i + 1] - x[i]), y[i]);
 }
 
-__global__ void __launch_bounds__(256) rcm_update_kernel(RcmColArgs a)
+__device__ __forceinline__ void rcm_update_body(const RcmColArgs& a, double* sm)
 {
-    extern __shared__ double sm[];
     double* sFnet = sm;                  // [nrad]
     double* sR = sFnet + a.nrad;         // [np]
     double* sT = sR + a.np;              // [np]
@@ -966,6 +966,85 @@ __global__ void __launch_bounds__(256) rcm_update_kernel(RcmColArgs a)
     }
 }
 
+__global__ void __launch_bounds__(256) rcm_update_kernel(RcmColArgs a)
+{
+    extern __shared__ double sm[];
+    rcm_update_body(a, sm);
+}
+
+// ---- nu-sharded step with the collective fused into the step's last kernel.  Every rank owns a mailbox in its own device
+// memory, mapped into the other ranks' address spaces (CUDA IPC between processes, peer access inside one):
+//   flags  uint64 [2][nranks]          flag[slot][r] = step + 1 once rank r's partial sums of that step have landed
+//   data   double [2][nranks][n2]      n2 = 2 nrad partial sums (F+ then F-) of rank r
+// The tail kernel (one CTA) does the fixed-order spectral reduction of this rank's per-CTA partials (as flux_reduce_kernel),
+// stores the n2 sums straight into EVERY rank's mailbox over NVLink (plain peer stores, then a system fence, then the flag),
+// spins on its own mailbox until all nranks flags of this step are there, adds the nranks vectors in RANK ORDER -- the same
+// bits on every rank, which the replicated column update needs -- and runs the column update.  Slots alternate with the step
+// parity: a rank can only be one step ahead of the slowest one (it needs everybody's flag to finish a step), and it posts step
+// s+1 after it has consumed step s, so two slots are enough.  A bounded spin (about two seconds of SM clocks) raises an error
+// word instead of hanging the device when a rank never arrives.
+constexpr int RCM_MAX_RANKS = 16;
+struct RcmPeerArgs {
+    const double* part;                  // [nblocks][n2] per-CTA partial sums of rcm_rt_kernel
+    int nblocks, n2, rank, nranks;
+    unsigned long long* step;            // device word: steps completed so far (the same on every rank)
+    int* err;                            // device word: set when a flag did not arrive in time
+    size_t data_off;                     // byte offset of the data block inside a mailbox
+    char* mail[RCM_MAX_RANKS];           // the nranks mailboxes as visible from this device (mail[rank] = its own)
+};
+
+__global__ void __launch_bounds__(256) rcm_tail_kernel(RcmColArgs a, RcmPeerArgs p)
+{
+    extern __shared__ double sm[];
+    double* sF = sm + a.nrad + 2 * a.np;          // [n2], behind the column update's scratch
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n2 = p.n2;
+    if (p.part) {
+        for (int t = warp; t < n2; t += 8) {
+            double v = 0.0;
+            for (int b = lane; b < p.nblocks; b += 32) v += p.part[(size_t)b * n2 + t];
+            v = warp_sum(v);
+            if (lane == 0) sF[t] = v;
+        }
+    } else {
+        for (int t = tid; t < n2; t += 256) sF[t] = a.F[t];      // already reduced by flux_reduce_kernel (one warp per output)
+    }
+    __syncthreads();
+    if (p.nranks > 1) {
+        const unsigned long long step = *p.step;
+        const int slot = (int)(step & 1ULL);
+        for (int q = 0; q < p.nranks; q++) {
+            double* dst = reinterpret_cast<double*>(p.mail[q] + p.data_off) + ((size_t)slot * p.nranks + p.rank) * n2;
+            for (int t = tid; t < n2; t += 256) dst[t] = sF[t];
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (tid < p.nranks) {
+            volatile unsigned long long* f = reinterpret_cast<unsigned long long*>(p.mail[tid]) + (size_t)slot * p.nranks + p.rank;
+            *f = step + 1ULL;
+        }
+        if (tid < p.nranks) {
+            volatile unsigned long long* f = reinterpret_cast<unsigned long long*>(p.mail[p.rank]) + (size_t)slot * p.nranks + tid;
+            const long long t0 = clock64();
+            while (*f != step + 1ULL) {
+                if (clock64() - t0 > 4000000000LL) { atomicExch(p.err, 1); break; }
+            }
+        }
+        __syncthreads();
+        __threadfence_system();
+        const double* src = reinterpret_cast<const double*>(p.mail[p.rank] + p.data_off) + (size_t)slot * p.nranks * n2;
+        for (int t = tid; t < n2; t += 256) {
+            double v = 0.0;
+            for (int r = 0; r < p.nranks; r++) v += __ldcv(src + (size_t)r * n2 + t);
+            sF[t] = v;
+        }
+        __syncthreads();
+        if (tid == 0) *p.step = step + 1ULL;
+    }
+    a.F = sF;
+    rcm_update_body(a, sm);
+}
+
 int findcell_host(const std::vector<double>& x, double q)
 {
     const int n = (int)x.size();
@@ -996,6 +1075,12 @@ struct cs_rcm {
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
     bool graph_tried = false;
+    // peer exchange (cs_rcm_peer_*): own mailbox (cudaMalloc: exportable), the ranks' mailboxes as seen from this device
+    char* mail_own = nullptr;
+    size_t mail_bytes = 0, mail_data_off = 0;
+    int peer_rank = 0, peer_nranks = 0;
+    char* mail[16] = {nullptr};
+    unsigned long long* peer_step = nullptr;     // [2 words]: step counter, error flag
 };
 
 namespace {
@@ -1009,8 +1094,20 @@ template <int NS> int32_t rcm_launch_rt(cs_rcm* r, cudaStream_t st, const RcmRtA
 
 size_t rcm_rt_smem(const cs_rcm* r) { return sizeof(double) * ((size_t)r->nrad + 2 * r->ns + (size_t)2 * r->nrad * RT_WARPS); }
 
+int32_t rcm_enqueue_rt(cs_rcm* r);
+
 // partial fluxes of this device: rt + spectral reduction into dF (2*nrad doubles, device)
 int32_t rcm_enqueue_fluxes(cs_rcm* r, double* dF)
+{
+    CS_TRY(rcm_enqueue_rt(r));
+    flux_reduce_kernel<<<(2 * r->nrad + 3) / 4, 128, 0, r->ctx->stream>>>(r->part, r->nblocks, 2 * r->nrad, dF);
+    CS_CUDA(cudaGetLastError());
+    cs_count_launch(r->ctx, 1);
+    return CS_OK;
+}
+
+// the flux kernel alone: per-CTA partial sums in r->part
+int32_t rcm_enqueue_rt(cs_rcm* r)
 {
     cs_ctx* ctx = r->ctx;
     cudaStream_t st = ctx->stream;
@@ -1027,9 +1124,35 @@ int32_t rcm_enqueue_fluxes(cs_rcm* r, double* dF)
     case 8: CS_TRY(rcm_launch_rt<8>(r, st, a, smem)); break;
     default: CS_TRY(rcm_launch_rt<0>(r, st, a, smem)); break;
     }
-    flux_reduce_kernel<<<(2 * r->nrad + 3) / 4, 128, 0, st>>>(r->part, r->nblocks, 2 * r->nrad, dF);
+    cs_count_launch(ctx, 1);
+    return CS_OK;
+}
+
+RcmColArgs rcm_col_args(const cs_rcm* r, const double* dF)
+{
+    RcmColArgs a;
+    a.np = r->np; a.nrad = r->nrad; a.F = dF; a.beamF = r->has_beam ? r->beamF : nullptr;
+    a.lnPr = r->lnPr; a.lnPe = r->lnPe; a.ecell = r->ecell; a.dPe = r->dPe; a.gcp = r->gcp; a.cs_surf = r->cs_surf;
+    a.lnP = r->lnP; a.rcell = r->rcell; a.dt = r->dt; a.T = r->T; a.H = r->H; a.R = r->R; a.Fout = r->Fout;
+    a.rkT = r->rkT; a.Tlev = r->Tlev;
+    return a;
+}
+
+// flux kernels + the fused tail (peer exchange, column update): no collective call
+int32_t rcm_enqueue_step_peer(cs_rcm* r)
+{
+    // the second-stage spectral reduction keeps its own launch: one warp per output over ~600 per-CTA partials is 2 us on 51
+    // CTAs, but 50+ us when a single CTA walks the 2*nrad outputs (measured: the fully fused tail made the step slower)
+    CS_TRY(rcm_enqueue_fluxes(r, r->F));
+    RcmColArgs a = rcm_col_args(r, r->F);       // this rank's sums; the tail replaces them by the sums over all ranks
+    RcmPeerArgs p;
+    p.part = nullptr; p.nblocks = r->nblocks; p.n2 = 2 * r->nrad; p.rank = r->peer_rank; p.nranks = r->peer_nranks;
+    p.step = r->peer_step; p.err = reinterpret_cast<int*>(r->peer_step + 1); p.data_off = r->mail_data_off;
+    for (int q = 0; q < RCM_MAX_RANKS; q++) p.mail[q] = q < r->peer_nranks ? r->mail[q] : nullptr;
+    const size_t smem = sizeof(double) * (3 * (size_t)r->nrad + 2 * (size_t)r->np);
+    rcm_tail_kernel<<<1, 256, smem, r->ctx->stream>>>(a, p);
     CS_CUDA(cudaGetLastError());
-    cs_count_launch(ctx, 2);
+    cs_count_launch(r->ctx, 1);
     return CS_OK;
 }
 
@@ -1037,11 +1160,7 @@ int32_t rcm_enqueue_fluxes(cs_rcm* r, double* dF)
 int32_t rcm_enqueue_update(cs_rcm* r, const double* dF)
 {
     cudaStream_t st = r->ctx->stream;
-    RcmColArgs a;
-    a.np = r->np; a.nrad = r->nrad; a.F = dF; a.beamF = r->has_beam ? r->beamF : nullptr;
-    a.lnPr = r->lnPr; a.lnPe = r->lnPe; a.ecell = r->ecell; a.dPe = r->dPe; a.gcp = r->gcp; a.cs_surf = r->cs_surf;
-    a.lnP = r->lnP; a.rcell = r->rcell; a.dt = r->dt; a.T = r->T; a.H = r->H; a.R = r->R; a.Fout = r->Fout;
-    a.rkT = r->rkT; a.Tlev = r->Tlev;
+    RcmColArgs a = rcm_col_args(r, dF);
     const size_t smem = sizeof(double) * ((size_t)r->nrad + 2 * (size_t)r->np);
     rcm_update_kernel<<<1, 256, smem, st>>>(a);
     CS_CUDA(cudaGetLastError());
@@ -1068,6 +1187,9 @@ extern "C" int32_t cs_rcm_free(cs_rcm* r)
     if (r->graph) cudaGraphDestroy(r->graph);
     cs_free(r->tau, st); cs_free(r->tr, st); cs_free(r->B_s, st); cs_free(r->part, st); cs_free(r->beam_surf, st);
     cs_free(r->fa, st); cs_free(r->nu, st); cs_free(r->w, st); cs_free(r->col, st);
+    if (r->mail_own || r->peer_step) cudaStreamSynchronize(st);
+    if (r->mail_own) cudaFree(r->mail_own);       // the peers must have closed their mappings (cs_ipc_close) before
+    if (r->peer_step) cudaFree(r->peer_step);
     delete r;
     return CS_OK;
 }
@@ -1217,6 +1339,103 @@ extern "C" int32_t cs_rcm_enqueue_update(cs_rcm* r, const double* d_F, double dt
     CS_CUDA(cudaSetDevice(r->ctx->device));
     CS_TRY(rcm_set_dt(r, dt));
     return rcm_enqueue_update(r, d_F ? d_F : r->F);
+}
+
+static size_t rcm_mail_layout(int nranks, int n2, size_t* data_off)
+{
+    const size_t flags = ((sizeof(unsigned long long) * 2 * (size_t)nranks + 255) / 256) * 256;
+    if (data_off) *data_off = flags;
+    return flags + sizeof(double) * 2 * (size_t)nranks * (size_t)n2;
+}
+
+extern "C" int32_t cs_rcm_peer_mailbox(cs_rcm* r, int32_t nranks, void** d_mailbox, int64_t* nbytes)
+{
+    CS_REQUIRE(r && d_mailbox, CS_ERR_ARG, "null argument");
+    CS_REQUIRE(nranks >= 1 && nranks <= RCM_MAX_RANKS, CS_ERR_ARG, "number of ranks must be in [1,%d]", RCM_MAX_RANKS);
+    cs_ctx* ctx = r->ctx;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mtx);
+    CS_CUDA(cudaSetDevice(ctx->device));
+    CS_REQUIRE(!r->mail_own, CS_ERR_ARG, "the mailbox of this column already exists");
+    size_t off = 0;
+    const size_t bytes = rcm_mail_layout(nranks, 2 * r->nrad, &off);
+    // plain cudaMalloc, not the stream-ordered pool: the block is exported to other processes (cudaIpcGetMemHandle)
+    CS_CUDA(cudaMalloc((void**)&r->mail_own, bytes));
+    CS_CUDA(cudaMemset(r->mail_own, 0, bytes));
+    CS_CUDA(cudaMalloc((void**)&r->peer_step, 2 * sizeof(unsigned long long)));
+    CS_CUDA(cudaMemset(r->peer_step, 0, 2 * sizeof(unsigned long long)));
+    CS_CUDA(cudaDeviceSynchronize());
+    r->mail_bytes = bytes; r->mail_data_off = off; r->peer_nranks = nranks;
+    *d_mailbox = r->mail_own;
+    if (nbytes) *nbytes = (int64_t)bytes;
+    return CS_OK;
+}
+
+extern "C" int32_t cs_rcm_peer_connect(cs_rcm* r, int32_t rank, int32_t nranks, void* const* d_mailboxes)
+{
+    CS_REQUIRE(r && d_mailboxes, CS_ERR_ARG, "null argument");
+    CS_REQUIRE(r->mail_own && nranks == r->peer_nranks, CS_ERR_ARG, "cs_rcm_peer_mailbox(nranks) comes first, with the same nranks");
+    CS_REQUIRE(rank >= 0 && rank < nranks, CS_ERR_ARG, "rank %d outside [0,%d)", rank, nranks);
+    std::lock_guard<std::recursive_mutex> lk(r->ctx->mtx);
+    for (int q = 0; q < nranks; q++) {
+        CS_REQUIRE(d_mailboxes[q] || q == rank, CS_ERR_ARG, "mailbox of rank %d is null", q);
+        r->mail[q] = q == rank ? r->mail_own : static_cast<char*>(d_mailboxes[q]);
+    }
+    r->peer_rank = rank;
+    return CS_OK;
+}
+
+extern "C" int32_t cs_rcm_enqueue_step_peer(cs_rcm* r, double dt)
+{
+    CS_REQUIRE(r, CS_ERR_ARG, "null argument");
+    CS_REQUIRE(r->mail_own && r->mail[r->peer_rank] == r->mail_own, CS_ERR_ARG, "cs_rcm_peer_connect comes first");
+    std::lock_guard<std::recursive_mutex> lk(r->ctx->mtx);
+    CS_CUDA(cudaSetDevice(r->ctx->device));
+    CS_TRY(rcm_set_dt(r, dt));
+    return rcm_enqueue_step_peer(r);
+}
+
+extern "C" int32_t cs_rcm_peer_status(cs_rcm* r, int64_t* steps, int32_t* timed_out)
+{
+    CS_REQUIRE(r && r->peer_step, CS_ERR_ARG, "no peer exchange on this column");
+    std::lock_guard<std::recursive_mutex> lk(r->ctx->mtx);
+    CS_CUDA(cudaSetDevice(r->ctx->device));
+    unsigned long long h[2] = {0, 0};
+    CS_CUDA(cudaMemcpyAsync(h, r->peer_step, sizeof(h), cudaMemcpyDeviceToHost, r->ctx->stream));
+    CS_CUDA(cudaStreamSynchronize(r->ctx->stream));
+    if (steps) *steps = (int64_t)h[0];
+    if (timed_out) *timed_out = (int32_t)(h[1] & 0xffffffffULL);
+    return CS_OK;
+}
+
+extern "C" int32_t cs_ipc_export(void* d_ptr, uint8_t* handle64)
+{
+    CS_REQUIRE(d_ptr && handle64, CS_ERR_ARG, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+    cudaIpcMemHandle_t h;
+    CS_CUDA(cudaIpcGetMemHandle(&h, d_ptr));
+    memcpy(handle64, &h, 64);
+    return CS_OK;
+}
+
+extern "C" int32_t cs_ipc_open(cs_ctx* ctx, const uint8_t* handle64, void** d_ptr)
+{
+    CS_REQUIRE(ctx && handle64 && d_ptr, CS_ERR_ARG, "null argument");
+    std::lock_guard<std::recursive_mutex> lk(ctx->mtx);
+    CS_CUDA(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    CS_CUDA(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return CS_OK;
+}
+
+extern "C" int32_t cs_ipc_close(cs_ctx* ctx, void* d_ptr)
+{
+    CS_REQUIRE(ctx && d_ptr, CS_ERR_ARG, "null argument");
+    std::lock_guard<std::recursive_mutex> lk(ctx->mtx);
+    CS_CUDA(cudaSetDevice(ctx->device));
+    CS_CUDA(cudaStreamSynchronize(ctx->stream));
+    CS_CUDA(cudaIpcCloseMemHandle(d_ptr));
+    return CS_OK;
 }
 
 extern "C" int32_t cs_rcm_step(cs_rcm* r, double dt, int64_t nsteps)

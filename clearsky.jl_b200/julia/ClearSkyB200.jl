@@ -156,6 +156,16 @@ cs_rcm_ctx(rcm, ctx) = ccall((:cs_rcm_ctx, LIB), Int32, (Ptr{Cvoid}, Ref{Ptr{Cvo
 cs_rcm_enqueue_fluxes(rcm, dF) = ccall((:cs_rcm_enqueue_fluxes, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}), rcm, dF)
 cs_rcm_enqueue_update(rcm, dF, Δt) = ccall((:cs_rcm_enqueue_update, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Float64), rcm, dF, Δt)
 cs_rcm_flux_buffer(rcm, dF) = ccall((:cs_rcm_flux_buffer, LIB), Int32, (Ptr{Cvoid}, Ref{Ptr{Float64}}), rcm, dF)
+cs_rcm_peer_mailbox(rcm, nranks, mailbox, nbytes) =
+    ccall((:cs_rcm_peer_mailbox, LIB), Int32, (Ptr{Cvoid}, Int32, Ref{Ptr{Cvoid}}, Ref{Int64}), rcm, nranks, mailbox, nbytes)
+cs_rcm_peer_connect(rcm, rank, nranks, mailboxes) =
+    ccall((:cs_rcm_peer_connect, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{Ptr{Cvoid}}), rcm, rank, nranks, mailboxes)
+cs_rcm_enqueue_step_peer(rcm, Δt) = ccall((:cs_rcm_enqueue_step_peer, LIB), Int32, (Ptr{Cvoid}, Float64), rcm, Δt)
+cs_rcm_peer_status(rcm, steps, timedout) =
+    ccall((:cs_rcm_peer_status, LIB), Int32, (Ptr{Cvoid}, Ref{Int64}, Ref{Int32}), rcm, steps, timedout)
+cs_ipc_export(p, handle) = ccall((:cs_ipc_export, LIB), Int32, (Ptr{Cvoid}, Ptr{UInt8}), p, handle)
+cs_ipc_open(ctx, handle, p) = ccall((:cs_ipc_open, LIB), Int32, (Ptr{Cvoid}, Ptr{UInt8}, Ref{Ptr{Cvoid}}), ctx, handle, p)
+cs_ipc_close(ctx, p) = ccall((:cs_ipc_close, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}), ctx, p)
 cs_par_parse(ctx, nbytes, text, reclen, nrec, M, I, ν, S, A, γa, γs, Epp, na, δa, flags) =
     ccall((:cs_par_parse, LIB), Int32,
           (Ptr{Cvoid}, Int64, Ptr{UInt8}, Int32, Int64, Ptr{Int16}, Ptr{Int16}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
@@ -884,6 +894,33 @@ function fluxbuffer(d::DeviceRCM)
     p = Ref{Ptr{F64}}(C_NULL)
     check(Lib.cs_rcm_flux_buffer(d.h, p))
     p[]
+end
+# ν-sharded step with the collective fused into the step's last kernel (one Julia process per GPU: exchange the 64-byte
+# handles of `peermailbox` with MPI.Allgather / Distributed, map them with `ipcopen`, then `peerconnect!`)
+function peermailbox(d::DeviceRCM, nranks::Integer)
+    p = Ref{Ptr{Cvoid}}(C_NULL); n = Ref{Int64}(0)
+    check(Lib.cs_rcm_peer_mailbox(d.h, Int32(nranks), p, n))
+    p[], n[]
+end
+function ipcexport(p::Ptr{Cvoid})
+    h = Vector{UInt8}(undef, 64)
+    GC.@preserve h check(Lib.cs_ipc_export(p, pointer(h)))
+    h
+end
+function ipcopen(c::Context, h::Vector{UInt8})
+    p = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve h check(Lib.cs_ipc_open(c.h, pointer(h), p))
+    p[]
+end
+ipcclose(c::Context, p::Ptr{Cvoid}) = check(Lib.cs_ipc_close(c.h, p))
+function peerconnect!(d::DeviceRCM, rank::Integer, mailboxes::Vector{Ptr{Cvoid}})
+    GC.@preserve mailboxes check(Lib.cs_rcm_peer_connect(d.h, Int32(rank), Int32(length(mailboxes)), pointer(mailboxes)))
+end
+enqueue_step_peer!(d::DeviceRCM, Δt::Real) = check(Lib.cs_rcm_enqueue_step_peer(d.h, F64(Δt)))
+function peerstatus(d::DeviceRCM)
+    n = Ref{Int64}(0); t = Ref{Int32}(0)
+    check(Lib.cs_rcm_peer_status(d.h, n, t))
+    n[], t[] != 0
 end
 function rcmcontext(d::DeviceRCM)
     c = Ref{Handle}(C_NULL)

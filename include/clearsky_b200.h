@@ -255,6 +255,24 @@ int32_t cs_rcm_ctx(cs_rcm* rcm, cs_ctx** ctx);
 int32_t cs_rcm_enqueue_fluxes(cs_rcm* rcm, double* d_F);
 int32_t cs_rcm_enqueue_update(cs_rcm* rcm, const double* d_F, double dt);
 int32_t cs_rcm_flux_buffer(cs_rcm* rcm, double** d_F);
+/* The same nu-sharded step with the collective FUSED into the step's last kernel (no NCCL call, two launches per step).
+ * Every rank owns a mailbox in its own device memory (cs_rcm_peer_mailbox: a plain cudaMalloc block so that it can be
+ * exported with cs_ipc_export and mapped by the other processes with cs_ipc_open; inside one process peer access does the
+ * same).  cs_rcm_peer_connect hands a rank the nranks mailbox addresses as visible from ITS device (its own entry may be
+ * NULL).  cs_rcm_enqueue_step_peer = flux kernel + one tail kernel that reduces this rank's partial sums in a fixed order,
+ * stores the 2*nrad sums straight into every rank's mailbox over NVLink (peer stores, system fence, flag), spins on its own
+ * mailbox until the flags of all ranks for this step have arrived, adds the nranks vectors in rank order (bit-identical on
+ * every rank) and updates the column (radiative_convective.jl:123-149).  All ranks must enqueue the same number of steps.
+ * cs_rcm_peer_status: steps completed and whether a flag ever failed to arrive within ~2 s of SM clocks (the step then
+ * went on with incomplete sums instead of hanging the device).  Capturable in a CUDA graph like the two-call form. */
+int32_t cs_rcm_peer_mailbox(cs_rcm* rcm, int32_t nranks, void** d_mailbox, int64_t* nbytes);
+int32_t cs_rcm_peer_connect(cs_rcm* rcm, int32_t rank, int32_t nranks, void* const* d_mailboxes);
+int32_t cs_rcm_enqueue_step_peer(cs_rcm* rcm, double dt);
+int32_t cs_rcm_peer_status(cs_rcm* rcm, int64_t* steps, int32_t* timed_out);
+/* CUDA IPC plumbing for the mailboxes: a 64-byte handle of a cudaMalloc'ed block / its mapping in another process */
+int32_t cs_ipc_export(void* d_ptr, uint8_t* handle64);
+int32_t cs_ipc_open(cs_ctx* ctx, const uint8_t* handle64, void** d_ptr);
+int32_t cs_ipc_close(cs_ctx* ctx, void* d_ptr);
 
 /* ---- HITRAN .par ingestion on the GPU (the step BEFORE the path; readpar's parse loop, src/hitran/par.jl:127-152) ----
  * text = the file's bytes, nrec fixed-width records of reclen bytes each (160 columns + line terminator), column map

@@ -839,6 +839,82 @@ def test_sharded_tables_and_rcm(cs, co2, h2o):
     grp.close()
 
 
+def test_rcm_fused_peer_step(cs, co2):
+    """nu-sharded RCM step with the exchange fused into the step's tail kernel (cs_rcm_enqueue_step_peer: peer-memory mailboxes,
+    flags, rank-ordered sum, column update) -- two "ranks" as two contexts on ONE device so that it runs on a one-GPU box (their
+    mailboxes are then plain device pointers; between processes they are cs_ipc_export / cs_ipc_open mappings, bench.py c5).
+    Both ranks must hold bit-identical columns, equal to the unsharded device loop."""
+    import ctypes as C
+
+    import bench
+    from clearsky_b200._lib import check, f64, lib, ptr
+    ν = np.linspace(500.0, 900.0, 2001)
+    wts = bench.trapz_weights(ν)
+    wl = dict(Pe=cs.pressuregrid(10.0, 1e5, 13), radmul=2)
+    wl["Te"] = cs.DryAdiabat(288.0, 1e5, 1040.0, 0.029, Ptropo=1e4)(wl["Pe"])
+    col = bench._HostColumn(cs, wl)
+    Pe, Pr, nrad, npc = f64(wl["Pe"]), f64(col.Pr), len(col.Pr), len(wl["Pe"])
+    m, W = (f64(x) for x in cs.streamnodes(5))
+    wlob = f64(cs.lobattonodes(2)[1])
+    μn = f64(np.full((nrad - 1, 2), 0.029))
+    cp = f64(np.full(npc - 1, 1040.0))
+    Tlev = f64(cs.AtmosphericProfile(col.P, col.T)(col.Pr))
+
+    def make(ctx, i0, i1):
+        νs = np.ascontiguousarray(ν[i0:i1])
+        ws = cs.SigmaWorkspace(νs, nrad, ctx)
+        cs.UnifiedAbsorber(cs.LineGas(co2, 400e-6, νs, "voigt", 25.0, ctx=ctx)).sigma_nodes(ws, Tlev, Pr)
+        h = C.c_void_p()
+        check(lib().cs_rcm_create(ws.h, npc, ptr(Pe), ptr(f64(col.P)), ptr(f64(col.T)), ptr(cp), 1e7, nrad, ptr(Pr), 2, ptr(wlob),
+                                  ptr(μn), 9.8, None, None, 0.841, 5, ptr(m), ptr(W), ptr(f64(wts[i0:i1])), C.byref(h)))
+        return h, ws
+
+    def state(h):
+        T, H, Fu, Fd = np.empty(npc), np.empty(npc), np.empty(nrad), np.empty(nrad)
+        check(lib().cs_rcm_state(h, ptr(T), ptr(H), None, ptr(Fu), ptr(Fd), None))
+        return T, H, Fu, Fd
+
+    ctxs = [cs.Context(0), cs.Context(0), cs.Context(0)]
+    full, _w0, parts = None, None, []
+    try:
+        full, _w0 = make(ctxs[0], 0, len(ν))
+        parts = [make(ctxs[1], 0, 1000), make(ctxs[2], 1000, len(ν))]
+        boxes = (C.c_void_p * 2)()
+        for q, (h, _) in enumerate(parts):
+            b = C.c_void_p()
+            check(lib().cs_rcm_peer_mailbox(h, 2, C.byref(b), None))
+            boxes[q] = b.value
+        for q, (h, _) in enumerate(parts):
+            check(lib().cs_rcm_peer_connect(h, q, 2, boxes))
+        nsteps = 5
+        for _ in range(nsteps):                        # enqueue only: the two tails meet on the device
+            for h, _ in parts:
+                check(lib().cs_rcm_enqueue_step_peer(h, 1800.0))
+        check(lib().cs_rcm_step(full, 1800.0, nsteps))
+        S = [state(h) for h, _ in parts]
+        for h, _ in parts:
+            n, late = C.c_int64(0), C.c_int32(0)
+            check(lib().cs_rcm_peer_status(h, C.byref(n), C.byref(late)))
+            assert n.value == nsteps and late.value == 0
+        for x, y in zip(S[0], S[1]):
+            assert np.array_equal(x, y)                # rank-ordered sums: the same bits on both ranks
+        T, H, Fu, Fd = state(full)
+        assert relerr(S[0][0], T) < 1e-12 and np.max(np.abs(S[0][1] - H)) < 1e-9 * np.max(np.abs(H))
+        assert relerr(S[0][2], Fu) < 1e-12 and relerr(S[0][3][1:], Fd[1:]) < 1e-12
+        with pytest.raises(cs.ClearSkyError):
+            check(lib().cs_rcm_peer_mailbox(parts[0][0], 2, C.byref(C.c_void_p()), None))      # one mailbox per column
+        with pytest.raises(cs.ClearSkyError):
+            check(lib().cs_rcm_enqueue_step_peer(full, 1800.0))                                 # not connected
+    finally:
+        for h in [full] + [h for h, _ in parts]:
+            if h is not None:
+                lib().cs_rcm_free(h)
+        del _w0, parts
+        co2.__dict__.pop("_dev", None)
+        for c in ctxs:
+            c.close()
+
+
 def test_group_spans_distinct_gpus(cs, co2):
     """driver-visible proof of the library's own NCCL path (cs_group.cu: ncclAllReduce over the group's communicator): needs two
     DISTINCT devices, so it is skipped on a one-GPU box (`gpurun --gpus 2 -- python -m pytest tests -m gpu -k distinct_gpus`).
