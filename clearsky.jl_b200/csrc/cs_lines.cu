@@ -46,6 +46,9 @@ namespace {
 #ifndef CS_LS_BAND          // Voigt: near-centre lines go through the far-wing fold, their band is corrected per point
 #define CS_LS_BAND 1
 #endif
+#ifndef CS_LS_BAND_PREFETCH  // 0: none, 1: prefetch the near range into L2, 2: into L1, before band_near walks it
+#define CS_LS_BAND_PREFETCH 0
+#endif
 #ifndef CS_LS_SPLIT         // direct mode, Voigt (band) / Lorentz: cold classes in line_sum_kernel<.., COLD>, far wings in far_fold_kernel
 #define CS_LS_SPLIT 1
 #endif
@@ -597,6 +600,20 @@ __device__ __noinline__ void band_near(const WarpCold& w, const double4* __restr
     const unsigned lt_mask = (1u << lane) - 1u;
     const uint32_t qaddr = smem_u32(w.queue);
     const double cp = 1.0 + cn, cm = 1.0 - cn;
+#if CS_LS_BAND_PREFETCH
+    // the records were written by K1 gigabytes ago: pull the near range (positions, records, near-centre parameters) towards the
+    // SM before the searches and the walk touch it line by line
+    for (int i = lane; 4 * i < nn; i += 32) {
+#if CS_LS_BAND_PREFETCH == 2
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(rec_near + 4 * i));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(slow_near + 4 * i));
+#else
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(rec_near + 4 * i));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(slow_near + 4 * i));
+#endif
+    }
+    for (int i = lane; 16 * i < nn; i += 32) asm volatile("prefetch.global.L1 [%0];" ::"l"(nul_near + 16 * i));
+#endif
     double nup[R], acc[R];
     int jlo[R], len[R];
     int maxlen = 0;
