@@ -206,6 +206,19 @@ static inline void cs_free(void* p, cudaStream_t st)
 // launch bookkeeping
 static inline void cs_count_launch(cs_ctx* c, int64_t n = 1) { c->launches += n; }
 
+// fast reciprocal for normal, finite, positive arguments: MUFU.RCP64H seed (measured max relative error 9.9e-7 =
+// 2^-19.9 on B200, tools/micro/rcp_accuracy.cu) + ONE cubic Newton step r(1 + e + e^2), e = 1 - a r, which leaves
+// e^3 ~ 1e-18 < 2^-53: the result is within 1 ulp of 1/a (measured max 2.2e-16).  nvcc's own 1.0/x adds a second,
+// quadratic step and an exponent-range fix-up for correct rounding; a 1e-9 parity budget does not need them.
+__device__ __forceinline__ double cs_rcp(double a)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+    double e = fma(-a, r, 1.0);
+    e = fma(e, e, e);
+    return fma(r, e, r);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Device Re w(x+iy): Algorithm 985 (Zaghloul 2017), the arithmetic behind Faddeyeva985.faddeyeva(x,y)
 // (reference call site src/absorption/line_shapes.jl:375).  Written from the published algorithm, real
@@ -217,10 +230,12 @@ __device__ __forceinline__ cplx cmul(cplx a, cplx b)
 {
     return {a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re};
 }
+// |b|^2 is positive, normal and finite wherever the routine divides (polynomials of bounded arguments): one 1-ulp reciprocal
+// serves both components instead of two IEEE divisions (~30 instructions each)
 __device__ __forceinline__ cplx cdiv(cplx a, cplx b)
 {
-    double den = b.re * b.re + b.im * b.im;
-    return {(a.re * b.re + a.im * b.im) / den, (a.im * b.re - a.re * b.im) / den};
+    double rden = cs_rcp(b.re * b.re + b.im * b.im);
+    return {(a.re * b.re + a.im * b.im) * rden, (a.im * b.re - a.re * b.im) * rden};
 }
 __device__ __forceinline__ cplx cadd(cplx a, double r) { return {a.re + r, a.im}; }
 // c - u*acc  (Horner step of the Humlicek polynomials)
@@ -293,19 +308,6 @@ static __device__ __noinline__ double cs_faddeyeva985(double x, double y)
     den = cadd(cmul(den, t), 352.730625110963558);
     den = cadd(cmul(den, t), 122.607931773875350);
     return cdiv(num, den).re;
-}
-
-// fast reciprocal for normal, finite, positive arguments: MUFU.RCP64H seed (measured max relative error 9.9e-7 =
-// 2^-19.9 on B200, tools/micro/rcp_accuracy.cu) + ONE cubic Newton step r(1 + e + e^2), e = 1 - a r, which leaves
-// e^3 ~ 1e-18 < 2^-53: the result is within 1 ulp of 1/a (measured max 2.2e-16).  nvcc's own 1.0/x adds a second,
-// quadratic step and an exponent-range fix-up for correct rounding; a 1e-9 parity budget does not need them.
-__device__ __forceinline__ double cs_rcp(double a)
-{
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
-    double e = fma(-a, r, 1.0);
-    e = fma(e, e, e);
-    return fma(r, e, r);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -623,33 +623,30 @@ __device__ __noinline__ void band_near(const WarpCold& w, const double4* __restr
         acc[r] = 0.0;
     }
     // band of each point: [first line with !(nul (1+cn) < nu), first line with nul (1-cn) > nu) -- the same two predicates the
-    // per-tile range was built with (tile_ranges_kernel, entries 4 and 5), so a pair outside the band is certainly far wing
+    // per-tile range was built with (tile_ranges_kernel, entries 4 and 5), so a pair outside the band is certainly far wing.
+    // Both are true on a prefix of the sorted positions: two branch-free binary searches per point (counts of the prefixes),
+    // all 2 R loads of a step in flight together
     {
-        int lo[R], hi[R];
+        int c1[R], c2[R];
 #pragma unroll
-        for (int r = 0; r < R; r++) { lo[r] = 0; hi[r] = nn; }
-        for (int it = nn; it > 0; it >>= 1) {
+        for (int r = 0; r < R; r++) { c1[r] = 0; c2[r] = 0; }
+        int step = 1;
+        while (2 * step <= nn) step *= 2;
+        for (; step > 0; step >>= 1) {
+            double x1[R], x2[R];
 #pragma unroll
             for (int r = 0; r < R; r++) {
-                if (lo[r] < hi[r]) {
-                    const int m = (lo[r] + hi[r]) >> 1;
-                    if (__ldg(nul_near + m) * cp < nup[r]) lo[r] = m + 1; else hi[r] = m;
-                }
+                x1[r] = __ldg(nul_near + min(c1[r] + step, nn) - 1);
+                x2[r] = __ldg(nul_near + min(c2[r] + step, nn) - 1);
+            }
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                if (c1[r] + step <= nn && x1[r] * cp < nup[r]) c1[r] += step;
+                if (c2[r] + step <= nn && !(x2[r] * cm > nup[r])) c2[r] += step;
             }
         }
 #pragma unroll
-        for (int r = 0; r < R; r++) { jlo[r] = lo[r]; hi[r] = nn; }
-        for (int it = nn; it > 0; it >>= 1) {
-#pragma unroll
-            for (int r = 0; r < R; r++) {
-                if (lo[r] < hi[r]) {
-                    const int m = (lo[r] + hi[r]) >> 1;
-                    if (!(__ldg(nul_near + m) * cm > nup[r])) lo[r] = m + 1; else hi[r] = m;
-                }
-            }
-        }
-#pragma unroll
-        for (int r = 0; r < R; r++) { len[r] = lo[r] - jlo[r]; maxlen = max(maxlen, len[r]); }
+        for (int r = 0; r < R; r++) { jlo[r] = c1[r]; len[r] = max(c2[r] - c1[r], 0); maxlen = max(maxlen, len[r]); }
     }
     maxlen = __reduce_max_sync(0xffffffffu, maxlen);
     int qn = 0;
