@@ -165,8 +165,12 @@ class LineGas(AbstractGas):
         self.fC = _as_conc(fC)
         self.sid = shape_id(shape)
         self.Δνcut = DEFAULT_CUT[self.sid] if Δνcut is None else float(Δνcut)
-        self.dl = device_lines(sl, self.ctx)
-        self.Ω = None
+        self._sl = sl          # uploaded on first use (cs_lines_upload runs on the context's copy stream: inside sigma_nodes the
+        self.Ω = None          # upload of this gas overlaps the line sum of the previous one)
+
+    @property
+    def dl(self):
+        return device_lines(self._sl, self.ctx)
 
     def concentration(self, T, P):
         if np.ndim(T) == 0:

@@ -63,6 +63,10 @@ static int32_t ctx_create(int32_t device, void* stream, bool own, cs_ctx** out)
         c->stream = (cudaStream_t)stream;
     }
     c->own_stream = own;
+    if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaGetLastError();
+        c->copy_stream = nullptr;
+    }
     {
         DevBuf* bufs[] = {&c->s_nu, &c->s_lev, &c->s_rec, &c->s_slow, &c->s_sigma, &c->s_misc, &c->s_part,
                           &c->s_tau, &c->s_planck, &c->s_out0, &c->s_out1, &c->s_out2, &c->s_w, &c->s_q};
@@ -110,6 +114,7 @@ extern "C" int32_t cs_ctx_free(cs_ctx* c)
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
     cudaEventDestroy(c->ev2);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
     return CS_OK;
@@ -363,7 +368,11 @@ extern "C" int32_t cs_lines_upload(cs_ctx* ctx, int64_t n, const double* nu, con
         L->na_min = std::min(L->na_min, na[j]);
         L->na_max = std::max(L->na_max, na[j]);
     }
-    cudaStream_t st = ctx->stream;
+    // the copies run on the context's copy stream: the call returns when ITS copies are done (the caller's arrays are only
+    // valid during the call), without waiting for kernels of an earlier gas still running on the compute stream -- so the
+    // upload of the next gas overlaps the line sum of the previous one.  Everything enqueued on the compute stream after this
+    // call finds the data in place (the copy stream is synchronised below).
+    cudaStream_t st = ctx->copy_stream ? ctx->copy_stream : ctx->stream;
     int32_t rc = CS_OK;
     if ((rc = upload(&L->nu, nu, n, st)) || (rc = upload(&L->S, S, n, st)) || (rc = upload(&L->ga, ga, n, st)) ||
         (rc = upload(&L->gs, gs, n, st)) || (rc = upload(&L->Epp, Epp, n, st)) || (rc = upload(&L->na, na, n, st)) ||
@@ -380,7 +389,7 @@ extern "C" int32_t cs_lines_upload(cs_ctx* ctx, int64_t n, const double* nu, con
         cs_lines_free(L);
         return CS_ERR_NOMEM;
     }
-    if ((rc = cs_lines_static(L))) {
+    if ((rc = cs_lines_static(L, st))) {
         cs_lines_free(L);
         return rc;
     }

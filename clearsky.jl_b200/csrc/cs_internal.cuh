@@ -113,6 +113,8 @@ struct cs_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = true;
+    cudaStream_t copy_stream = nullptr;    // uploads of line lists: a blocking upload then waits for its own copies only, not for the
+                                           // line sum of the previous gas still running on `stream`
     int sm_count = 148;
     std::recursive_mutex mtx;
     // scratch
@@ -360,7 +362,7 @@ void cs_span_end(cs_ctx* c, int span);
 void cs_spans_collect(cs_ctx* c, bool block);
 // asynchronous host->device copy of a small parameter block through the context's pinned staging ring
 int32_t cs_stage_h2d(cs_ctx* c, void* dst, const void* src, size_t bytes);
-int32_t cs_lines_static(cs_lines* L);
+int32_t cs_lines_static(cs_lines* L, cudaStream_t st);
 int32_t cs_lines_accumulate(cs_lines* L, int32_t shape, int64_t nnu, const double* d_nu,
                             const double* h_nu, int64_t nlev, const double* h_T, const double* h_P,
                             const double* h_Pp, const double* h_scale, double cut, double* d_out,

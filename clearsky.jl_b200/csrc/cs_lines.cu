@@ -1609,9 +1609,8 @@ __global__ void fill_kernel(double* p, size_t n, double v)
 }  // namespace
 
 // called by cs_lines_upload once the line arrays are on the device
-int32_t cs_lines_static(cs_lines* L)
+int32_t cs_lines_static(cs_lines* L, cudaStream_t st)
 {
-    cudaStream_t st = L->ctx->stream;
     line_static_kernel<<<(unsigned)((L->n + 255) / 256), 256, 0, st>>>(L->nu, L->Epp, L->n, L->dref);
     CS_CUDA(cudaGetLastError());
     cs_count_launch(L->ctx);
