@@ -340,34 +340,12 @@ extern "C" int32_t cs_lines_upload(cs_ctx* ctx, int64_t n, const double* nu, con
     CS_REQUIRE(n > 0, CS_ERR_ARG, "no lines");
     CS_REQUIRE(nu && S && ga && gs && Epp && na && mu && iso, CS_ERR_ARG, "null line-parameter array");
     CS_REQUIRE(niso > 0 && ncheb && cheb && hascheb, CS_ERR_ARG, "missing Qref/Q Chebyshev tables");
-    for (int64_t j = 1; j < n; j++)
-        CS_REQUIRE(nu[j] >= nu[j - 1], CS_ERR_ARG, "line wavenumbers must be sorted ascending (line %lld)", (long long)j);
-    for (int64_t j = 0; j < n; j++) {
-        int is = iso[j];
-        CS_REQUIRE(is >= 1 && is <= niso, CS_ERR_ARG, "isotopologue number %d out of range [1,%d]", is, niso);
-        // scaleintensity throws when no interpolating polynomial exists (line_shapes.jl:115-119)
-        CS_REQUIRE(hascheb[is - 1], CS_ERR_ARG,
-                   "no interpolating polynomial available to compute Qref/Q for isotopologue %d", is);
-        CS_REQUIRE(ncheb[is - 1] >= 2 && ncheb[is - 1] <= CS_MAXCHEB, CS_ERR_ARG, "bad Chebyshev length %d", ncheb[is - 1]);
-    }
     std::lock_guard<std::recursive_mutex> lk(ctx->mtx);
     CS_CUDA(cudaSetDevice(ctx->device));
     cs_lines* L = new cs_lines();
     L->ctx = ctx;
     L->n = n;
     L->niso = niso;
-    L->h_nu.assign(nu, nu + n);
-    L->mu_min = mu[0];
-    for (int64_t j = 1; j < n; j++) L->mu_min = std::min(L->mu_min, mu[j]);
-    L->g_max = 0.0; L->na_min = na[0]; L->na_max = na[0];
-    L->ga_min = ga[0]; L->gs_min = gs[0];
-    for (int64_t j = 0; j < n; j++) {
-        L->g_max = std::max(L->g_max, std::max(ga[j], gs[j]));
-        L->ga_min = std::min(L->ga_min, ga[j]);
-        L->gs_min = std::min(L->gs_min, gs[j]);
-        L->na_min = std::min(L->na_min, na[j]);
-        L->na_max = std::max(L->na_max, na[j]);
-    }
     // the copies run on the context's copy stream: the call returns when ITS copies are done (the caller's arrays are only
     // valid during the call), without waiting for kernels of an earlier gas still running on the compute stream -- so the
     // upload of the next gas overlaps the line sum of the previous one.  Everything enqueued on the compute stream after this
@@ -379,17 +357,58 @@ extern "C" int32_t cs_lines_upload(cs_ctx* ctx, int64_t n, const double* nu, con
         (rc = upload(&L->mu, mu, n, st)) || (rc = upload(&L->iso, iso, n, st)) ||
         (rc = upload(&L->ncheb, ncheb, (size_t)niso, st)) ||
         (rc = upload(&L->cheb, cheb, (size_t)niso * CS_MAXCHEB, st))) {
+        cudaStreamSynchronize(st);
         cs_lines_free(L);
         return rc;
+    }
+    // host-side validation and statistics run while the copies are in flight
+    int32_t bad = CS_OK;
+    for (int64_t j = 1; j < n && !bad; j++)
+        if (!(nu[j] >= nu[j - 1])) {
+            cs_set_error("line wavenumbers must be sorted ascending (line %lld)", (long long)j);
+            bad = CS_ERR_ARG;
+        }
+    for (int64_t j = 0; j < n && !bad; j++) {
+        const int is = iso[j];
+        if (!(is >= 1 && is <= niso)) {
+            cs_set_error("isotopologue number %d out of range [1,%d]", is, niso);
+            bad = CS_ERR_ARG;
+        } else if (!hascheb[is - 1]) {
+            // scaleintensity throws when no interpolating polynomial exists (line_shapes.jl:115-119)
+            cs_set_error("no interpolating polynomial available to compute Qref/Q for isotopologue %d", is);
+            bad = CS_ERR_ARG;
+        } else if (!(ncheb[is - 1] >= 2 && ncheb[is - 1] <= CS_MAXCHEB)) {
+            cs_set_error("bad Chebyshev length %d", ncheb[is - 1]);
+            bad = CS_ERR_ARG;
+        }
+    }
+    if (bad) {
+        cudaStreamSynchronize(st);
+        cs_lines_free(L);
+        return bad;
+    }
+    L->h_nu.assign(nu, nu + n);
+    L->mu_min = mu[0];
+    L->g_max = 0.0; L->na_min = na[0]; L->na_max = na[0];
+    L->ga_min = ga[0]; L->gs_min = gs[0];
+    for (int64_t j = 0; j < n; j++) {
+        L->mu_min = std::min(L->mu_min, mu[j]);
+        L->g_max = std::max(L->g_max, std::max(ga[j], gs[j]));
+        L->ga_min = std::min(L->ga_min, ga[j]);
+        L->gs_min = std::min(L->gs_min, gs[j]);
+        L->na_min = std::min(L->na_min, na[j]);
+        L->na_max = std::max(L->na_max, na[j]);
     }
     if (cudaMallocAsync(&L->dref, sizeof(double) * (size_t)n, st) != cudaSuccess) {
         cudaGetLastError();
         cs_set_error("cs_lines_upload: out of device memory");
         L->dref = nullptr;
+        cudaStreamSynchronize(st);
         cs_lines_free(L);
         return CS_ERR_NOMEM;
     }
     if ((rc = cs_lines_static(L, st))) {
+        cudaStreamSynchronize(st);
         cs_lines_free(L);
         return rc;
     }
