@@ -49,6 +49,9 @@ namespace {
 #ifndef CS_LS_BAND_PREFETCH  // 0: none, 1: prefetch the near range into L2, 2: into L1, before band_near walks it
 #define CS_LS_BAND_PREFETCH 0
 #endif
+#ifndef CS_LS_EDGE_STAGES   // COLD launch: cut-off edges slice by slice (edge lines folded only for the 32-point slices they reach)
+#define CS_LS_EDGE_STAGES 1
+#endif
 #ifndef CS_LS_SPLIT         // direct mode, Voigt (band) / Lorentz: cold classes in line_sum_kernel<.., COLD>, far wings in far_fold_kernel
 #define CS_LS_SPLIT 1
 #endif
@@ -328,6 +331,7 @@ __global__ void chix_kernel(const double* __restrict__ nul, int64_t nl, double r
 //   [ilo,ihi): lines within the cut-off of ALL points (no per-point predicate needed)
 //   [nlo,nhi): lines whose centre is within cn*nul of the tile: the far-wing form may not apply there
 constexpr int LS_NR = 18;   // entries per tile (6 general + 12 PHCO2 chi-class boundaries)
+constexpr int LS_NR_SPLIT = 12;   // split direct mode with 128-point tiles: 6 general + 2 x 3 slice borders of the cut-off edges
 __global__ void tile_ranges_kernel(const double* __restrict__ nu, int64_t nnu, const double* __restrict__ nul,
                                    int64_t nl, double cut, double cn, int tile_pts, int64_t ntiles, int nr,
                                    double mp_theta, int64_t* __restrict__ ranges)
@@ -344,6 +348,23 @@ __global__ void tile_ranges_kernel(const double* __restrict__ nu, int64_t nnu, c
         const double cen = 0.5 * (tmin + tmax), D = mp_theta * (0.5 * (tmax - tmin));
         if (k == 6) v = first_false(nul, 0, nl, [=](double x) { return x <= cen - D; });
         else        v = first_false(nul, 0, nl, [=](double x) { return x < cen + D; });
+        ranges[t] = v;
+        return;
+    }
+    if (nr == LS_NR_SPLIT && k >= 6) {
+        // split direct mode: cut-off borders of the 32-point slices of the tile (the COLD launch sums the edge lines slice by
+        // slice).  Entries 6.. : b_r, r = 1..S-1 = first line partially inside slice r (b_0 = entry 0); then d_r, r = 0..S-2 =
+        // first line beyond slice r (d_{S-1} = entry 1); the same FP64 predicates as entries 0 and 1 on the slice's end points
+        const int S = tile_pts / 32;
+        if (k < 6 + (S - 1)) {
+            const int r = k - 5;
+            const double smin = nu[min(i0 + 32 * (int64_t)r, i1 - 1)];
+            v = first_false(nul, 0, nl, [=](double x) { return (smin - x) > cut; });
+        } else {
+            const int r = k - (6 + (S - 1));
+            const double smax = nu[min(i0 + 32 * (int64_t)r + 31, i1 - 1)];
+            v = first_false(nul, 0, nl, [=](double x) { return !((x - smax) > cut); });
+        }
         ranges[t] = v;
         return;
     }
@@ -695,6 +716,55 @@ __device__ __noinline__ void band_near(const WarpCold& w, const double4* __restr
     __syncwarp();
 }
 
+// ---- cut-off edges, slice by slice (COLD launch, far-wing form).  A line at the lower edge of the window is inside the cut-off
+// for the lowest 32-point slices of the tile only, so the edge lines [b_s, b_{s+1}) are folded for slices 0..s alone (the exact
+// inclusive predicate of line_shapes.jl:10 folded into the numerators), and likewise [d_s, d_{s+1}) for slices s..R-1 at the upper
+// edge: 10/16 of the (line, slice) pairs of the whole-tile edge loop, one record load per line for all active slices.
+// NA slices [R0, R0+NA) of the tile, lines [j0, j1) of the stage; one reciprocal per 16 lines
+template <int R, int R0, int NA>
+__device__ __forceinline__ void edge_fold(const double4* __restrict__ st, int j0, int j1, double cut, const double (&nup)[R],
+                                          double (&acc)[R])
+{
+    for (int j = j0; j < j1; j += 16) {
+        const int je = min(j + 16, j1);
+        double fn[NA], fd[NA];
+#pragma unroll
+        for (int r = 0; r < NA; r++) { fn[r] = 0.0; fd[r] = 1.0; }
+#pragma unroll 2
+        for (int g = j; g < je; g++) {
+            const double4 rb = st[g];
+#pragma unroll
+            for (int r = 0; r < NA; r++) {
+                const double db = nup[R0 + r] - rb.x;
+                const double kb = (fabs(db) > cut) ? 0.0 : rb.z;
+                const double qb = fma(db, db, rb.y);
+                fn[r] = fma(kb, fd[r], fn[r] * qb);
+                fd[r] *= qb;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < NA; r++) acc[R0 + r] = fma(fn[r], cs_rcp(fd[r]), acc[R0 + r]);
+    }
+}
+
+template <int R, int S> struct EdgeStages {
+    // lower edge: stage S = lines [b[S], b[S+1]) for slices 0..S; upper edge: stage S = lines [d[S], d[S+1]) for slices S..R-1
+    static __device__ __forceinline__ void lower(const double4* st, const int* b, int c0, int n, double cut, const double (&nup)[R],
+                                                 double (&acc)[R])
+    {
+        const int x0 = min(max(b[S] - c0, 0), n), x1 = min(max(b[S + 1] - c0, 0), n);
+        if (x0 < x1) edge_fold<R, 0, S + 1>(st, x0, x1, cut, nup, acc);
+        if constexpr (S + 1 < R) EdgeStages<R, S + 1>::lower(st, b, c0, n, cut, nup, acc);
+    }
+    static __device__ __forceinline__ void upper(const double4* st, const int* d, int c0, int n, double cut, const double (&nup)[R],
+                                                 double (&acc)[R])
+    {
+        const int x0 = min(max(d[S] - c0, 0), n), x1 = min(max(d[S + 1] - c0, 0), n);
+        if (x0 < x1) edge_fold<R, S, R - S>(st, x0, x1, cut, nup, acc);
+        if constexpr (S + 1 < R) EdgeStages<R, S + 1>::upper(st, d, c0, n, cut, nup, acc);
+    }
+};
+
 // PHCO2 lines that straddle a chi-class border for this tile: far-wing form with chi evaluated per point
 template <int R>
 __device__ __noinline__ void cold_phco2_generic(const WarpCold& w, const double4* st, int g0, int g1)
@@ -899,6 +969,7 @@ __global__ void __launch_bounds__(LS_THREADS, (COLD ? CS_LS_COLD_MINBLK : CS_LS_
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[LS_WARPS][LS_STAGES];
     __shared__ int seg_tab[LS_WARPS][3 * LS_NSEG];   // per warp: segment starts, ends, chunk counts (window-relative)
+    __shared__ int edge_tab[LS_WARPS][2 * (R + 1)];  // COLD: stage borders of the cut-off edges (window-relative)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int lev = blockIdx.y;
@@ -997,6 +1068,14 @@ __global__ void __launch_bounds__(LS_THREADS, (COLD ? CS_LS_COLD_MINBLK : CS_LS_
         } else if (COLD) {
             slo[0] = 0;   shi[0] = ilo;
             slo[1] = ihi; shi[1] = whi;
+            if (CS_LS_EDGE_STAGES && a.nr == LS_NR_SPLIT) {
+                // lower stages [b_s, b_{s+1}) with b_0 = 0, b_R = ilo; upper stages [d_s, d_{s+1}) with d_0 = ihi, d_R = whi
+                int* eb = edge_tab[warp];
+                int* ed = edge_tab[warp] + (R + 1);
+                eb[0] = 0; eb[R] = ilo; ed[0] = ihi; ed[R] = whi;
+                for (int r = 1; r < R; r++) { eb[r] = min(rel(5 + r), ilo); ed[r] = max(rel(6 + (R - 1) + (r - 1)), ihi); }
+                for (int r = 1; r <= R; r++) { eb[r] = max(eb[r], eb[r - 1]); ed[r] = max(ed[r], ed[r - 1]); }
+            }
         } else {
             shi[0] = whi;
         }
@@ -1352,7 +1431,11 @@ __global__ void __launch_bounds__(LS_THREADS, (COLD ? CS_LS_COLD_MINBLK : CS_LS_
                 }
             }
         } else {
-        if (xa > 0) cold_edge<SHAPE, R>(w, st, c0, 0, xa);
+        const bool staged = COLD && CS_LS_EDGE_STAGES && a.nr == LS_NR_SPLIT && w.edge_is_far;
+        if (xa > 0) {
+            if (staged) EdgeStages<R, 0>::lower(st, edge_tab[warp], c0, n, w.cut, nup, acc);
+            else cold_edge<SHAPE, R>(w, st, c0, 0, xa);
+        }
 #pragma unroll 1
         for (int pass = 0; pass < 2; pass++) {
             // far lines: inside the cut-off for every point and safely in the far wing -> no test of any kind
@@ -1383,7 +1466,10 @@ __global__ void __launch_bounds__(LS_THREADS, (COLD ? CS_LS_COLD_MINBLK : CS_LS_
             }
             if (pass == 0 && xb_ < xc) qn = cold_near<SHAPE, R>(w, st, c0, xb_, xc, qn);
         }
-        if (xd < n) cold_edge<SHAPE, R>(w, st, c0, xd, n);
+        if (xd < n) {
+            if (staged) EdgeStages<R, 0>::upper(st, edge_tab[warp] + (R + 1), c0, n, w.cut, nup, acc);
+            else cold_edge<SHAPE, R>(w, st, c0, xd, n);
+        }
         if (SHAPE == CS_VOIGT && qn > 0) { cold_flush<SHAPE, R>(w, st, c0, qn); qn = 0; }
         }
         // stage s is free again: refill it with chunk c + LS_STAGES
@@ -1490,7 +1576,13 @@ template <int SHAPE, int R> int32_t launch_line_sum(cs_ctx* ctx, LineSumArgs a, 
     a.ntiles = (a.nnu + TILE - 1) / TILE;
     a.near_cn = cn;
     if (SHAPE == CS_DOPPLER) a.mp_theta = 0.0;
-    a.nr = (SHAPE == CS_PHCO2) ? LS_NR : (a.mp_theta > 0.0 ? 8 : 6);
+    constexpr bool CAN_BAND = CS_LS_BAND && SHAPE == CS_VOIGT;
+    // the band correction pays in direct mode (the near lines ride the long far-wing fold); in expansion mode the direct fold is
+    // short and the per-tile cold_near measured faster (26.6 against 27.9 ms on C2)
+    const bool band = CAN_BAND && a.band && !(a.mp_theta > 0.0);
+    constexpr bool CAN_SPLIT = CS_LS_SPLIT && LS_WARPS == 1 && ((SHAPE == CS_VOIGT && CAN_BAND) || SHAPE == CS_LORENTZ);
+    const bool split = CAN_SPLIT && a.split && !(a.mp_theta > 0.0) && (band || SHAPE == CS_LORENTZ);
+    a.nr = (SHAPE == CS_PHCO2) ? LS_NR : (a.mp_theta > 0.0 ? 8 : ((split && R == 4) ? LS_NR_SPLIT : 6));
     // scratch: the per-tile ranges, then (PHCO2 expansion) the per-line chi factors of the >= 120 cm^-1 class, which are
     // level-independent (skipped when the span of the line list would overflow exp: the expansion is then off and every
     // pair is summed directly), or (Voigt / Lorentz expansion) the cluster moments and the far-field coefficients
@@ -1538,10 +1630,6 @@ template <int SHAPE, int R> int32_t launch_line_sum(cs_ctx* ctx, LineSumArgs a, 
         a.ffc = fa.ffc;
     }
     size_t smem = (size_t)LS_WARPS * (LS_STAGES * LS_CHUNK * sizeof(double4) + ls_extra_bytes<SHAPE, R>());
-    // the band correction pays in direct mode (the near lines ride the long far-wing fold); in expansion mode the direct fold is
-    // short and the per-tile cold_near measured faster (26.6 against 27.9 ms on C2)
-    constexpr bool CAN_BAND = CS_LS_BAND && SHAPE == CS_VOIGT;
-    const bool band = CAN_BAND && a.band && !(a.mp_theta > 0.0);
     if (smem > 48 * 1024)   // per device: not cached, several contexts may live on different GPUs
     {
         CS_CUDA(cudaFuncSetAttribute(line_sum_kernel<SHAPE, R, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1551,8 +1639,7 @@ template <int SHAPE, int R> int32_t launch_line_sum(cs_ctx* ctx, LineSumArgs a, 
         }
     }
     dim3 grid((unsigned)((a.ntiles + LS_WARPS - 1) / LS_WARPS), (unsigned)nlev);
-    constexpr bool CAN_SPLIT = CS_LS_SPLIT && LS_WARPS == 1 && ((SHAPE == CS_VOIGT && CAN_BAND) || SHAPE == CS_LORENTZ);
-    if (CAN_SPLIT && a.split && !(a.mp_theta > 0.0) && (band || SHAPE == CS_LORENTZ)) {
+    if (split) {
         constexpr bool B = SHAPE == CS_VOIGT;
         if (smem > 48 * 1024)
             CS_CUDA(cudaFuncSetAttribute(line_sum_kernel<SHAPE, R, false, B, CAN_SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
