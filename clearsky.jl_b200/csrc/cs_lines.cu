@@ -52,6 +52,9 @@ namespace {
 #ifndef CS_LS_EDGE_STAGES   // COLD launch: cut-off edges slice by slice (edge lines folded only for the 32-point slices they reach)
 #define CS_LS_EDGE_STAGES 1
 #endif
+#ifndef CS_LS_PHCO2_FOLD    // lines per reciprocal in the factorised chi classes of PHCO2 (0: pairs)
+#define CS_LS_PHCO2_FOLD 8
+#endif
 #ifndef CS_LS_SPLIT         // direct mode, Voigt (band) / Lorentz: cold classes in line_sum_kernel<.., COLD>, far wings in far_fold_kernel
 #define CS_LS_SPLIT 1
 #endif
@@ -765,6 +768,42 @@ template <int R, int S> struct EdgeStages {
     }
 };
 
+// PHCO2, factorised chi classes: the same left-to-right fold as fold_run with gamma_eff = E(nu) F(line) per pair -- 8 FP64
+// operations per evaluation (dnu, ge, ge^2, q, K ge, three for the fold) and one reciprocal per G lines, against 9.25 with two
+// lines per reciprocal.  q >= 9 (|dnu| >= 3 for every point of these classes), so a product of G = 8 of them is far from overflow.
+template <int R, int G>
+__device__ __forceinline__ void phco2_fold_run(const double4* __restrict__ st, const double* __restrict__ Fp, int& j, int x1,
+                                               const double (&nup)[R], const double (&E)[R], double (&acc)[R])
+{
+    for (; j + G - 1 < x1; j += G) {
+        double fn[R], fd[R];
+        {
+            const double4 ra = st[j];
+            const double fa = Fp[j];
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const double da = nup[r] - ra.x, gea = E[r] * fa;
+                fd[r] = fma(da, da, gea * gea);
+                fn[r] = ra.z * gea;
+            }
+        }
+#pragma unroll
+        for (int g = 1; g < G; g++) {
+            const double4 rb = st[j + g];
+            const double fb = Fp[j + g];
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const double db = nup[r] - rb.x, geb = E[r] * fb;
+                const double qb = fma(db, db, geb * geb);
+                fn[r] = fma(rb.z * geb, fd[r], fn[r] * qb);
+                fd[r] *= qb;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; r++) acc[r] = fma(fn[r], cs_rcp(fd[r]), acc[r]);
+    }
+}
+
 // PHCO2 lines that straddle a chi-class border for this tile: far-wing form with chi evaluated per point
 template <int R>
 __device__ __noinline__ void cold_phco2_generic(const WarpCold& w, const double4* st, int g0, int g1)
@@ -1407,6 +1446,9 @@ __global__ void __launch_bounds__(LS_THREADS, (COLD ? CS_LS_COLD_MINBLK : CS_LS_
 #pragma unroll
                 for (int r = 0; r < R; r++) E[r] = Etab[tab * TILE + 32 * r + lane];
                 int j = x0;
+#if CS_LS_PHCO2_FOLD
+                phco2_fold_run<R, CS_LS_PHCO2_FOLD>(st, Fp, j, x1, nup, E, acc);
+#endif
                 for (; j + 1 < x1; j += 2) {
                     double4 ra = st[j], rb = st[j + 1];
                     double fa = Fp[j], fb = Fp[j + 1];
