@@ -768,34 +768,40 @@ template <int R, int S> struct EdgeStages {
     }
 };
 
-// PHCO2, factorised chi classes: the same left-to-right fold as fold_run with gamma_eff = E(nu) F(line) per pair -- 8 FP64
-// operations per evaluation (dnu, ge, ge^2, q, K ge, three for the fold) and one reciprocal per G lines, against 9.25 with two
-// lines per reciprocal.  q >= 9 (|dnu| >= 3 for every point of these classes), so a product of G = 8 of them is far from overflow.
+// PHCO2, factorised chi classes: the same left-to-right fold as fold_run with gamma_eff = E(nu) F(line) per pair and one
+// reciprocal per G lines (two lines per reciprocal cost 9.25 FP64 operations per evaluation).  q >= 9 (|dnu| >= 3 for every point of these classes), so a product of G = 8 of them is far from overflow.
 template <int R, int G>
 __device__ __forceinline__ void phco2_fold_run(const double4* __restrict__ st, const double* __restrict__ Fp, int& j, int x1,
                                                const double (&nup)[R], const double (&E)[R], double (&acc)[R])
 {
+    // gamma_eff^2 = E^2 F^2 and K gamma_eff = (K F) E: the per-point squares and the per-line products are formed once, which
+    // leaves 7 operations per evaluation (dnu, E^2 F^2, q, (K F) E, three for the fold)
+    double E2[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) E2[r] = E[r] * E[r];
     for (; j + G - 1 < x1; j += G) {
         double fn[R], fd[R];
         {
             const double4 ra = st[j];
             const double fa = Fp[j];
+            const double f2 = fa * fa, kf = ra.z * fa;
 #pragma unroll
             for (int r = 0; r < R; r++) {
-                const double da = nup[r] - ra.x, gea = E[r] * fa;
-                fd[r] = fma(da, da, gea * gea);
-                fn[r] = ra.z * gea;
+                const double da = nup[r] - ra.x;
+                fd[r] = fma(da, da, E2[r] * f2);
+                fn[r] = kf * E[r];
             }
         }
 #pragma unroll
         for (int g = 1; g < G; g++) {
             const double4 rb = st[j + g];
             const double fb = Fp[j + g];
+            const double f2 = fb * fb, kf = rb.z * fb;
 #pragma unroll
             for (int r = 0; r < R; r++) {
-                const double db = nup[r] - rb.x, geb = E[r] * fb;
-                const double qb = fma(db, db, geb * geb);
-                fn[r] = fma(rb.z * geb, fd[r], fn[r] * qb);
+                const double db = nup[r] - rb.x;
+                const double qb = fma(db, db, E2[r] * f2);
+                fn[r] = fma(kf * E[r], fd[r], fn[r] * qb);
                 fd[r] *= qb;
             }
         }
