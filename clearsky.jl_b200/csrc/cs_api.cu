@@ -78,6 +78,7 @@ static int32_t ctx_create(int32_t device, void* stream, bool own, cs_ctx** out)
     c->ff_no_moments = getenv("CS_FARFIELD_NO_MOMENTS") != nullptr;
     c->ls_no_band = getenv("CS_LINESUM_NO_BAND") != nullptr;
     c->ls_no_split = getenv("CS_LINESUM_NO_SPLIT") != nullptr;
+    if (const char* fg = getenv("CS_LINESUM_FOLD")) c->ls_fold_g = atoi(fg);
     c->table_no_mma = getenv("CS_TABLE_EVAL_NO_MMA") != nullptr;
     c->table_no_fused = getenv("CS_TABLE_FIT_NO_FUSED") != nullptr;
     {
@@ -398,6 +399,14 @@ extern "C" int32_t cs_lines_upload(cs_ctx* ctx, int64_t n, const double* nu, con
         L->gs_min = std::min(L->gs_min, gs[j]);
         L->na_min = std::min(L->na_min, na[j]);
         L->na_max = std::max(L->na_max, na[j]);
+    }
+    {
+        const int ks[3] = {4, 8, 16};
+        for (int q = 0; q < 3; q++) {
+            double sp = 1e300;
+            for (int64_t j = 0; j + ks[q] - 1 < n; j++) sp = std::min(sp, nu[j + ks[q] - 1] - nu[j]);
+            L->span_k[q] = sp;
+        }
     }
     if (cudaMallocAsync(&L->dref, sizeof(double) * (size_t)n, st) != cudaSuccess) {
         cudaGetLastError();

@@ -130,6 +130,7 @@ struct cs_ctx {
     int stage_next = 0;
     bool ff_no_moments = false;            // CS_FARFIELD_NO_MOMENTS, read once at context creation
     bool ls_no_split = false;              // CS_LINESUM_NO_SPLIT: one launch for the cold classes and the far wings
+    int ls_fold_g = 0;                     // CS_LINESUM_FOLD: cap on the lines per reciprocal of far_fold_kernel (diagnostic)
     bool ls_no_band = false;               // CS_LINESUM_NO_BAND: Voigt near-centre lines per tile (cold_near) instead of the per-point band
     bool table_no_mma = false;             // CS_TABLE_EVAL_NO_MMA, likewise
     bool table_no_fused = false;           // CS_TABLE_FIT_NO_FUSED: two-pass GEMM fit instead of the fused single sweep
@@ -152,6 +153,7 @@ struct cs_lines {
     double mu_min;             // lightest isotopologue present (bounds the Doppler width)
     double g_max, na_min, na_max;   // max(gamma_a, gamma_s) and the range of the temperature exponent (bound gamma per level)
     double ga_min = 0.0, gs_min = 0.0;   // smallest air- / self-broadening coefficients (bound the Voigt damping parameter from below)
+    double span_k[3] = {0.0, 0.0, 0.0};  // narrowest span of 4 / 8 / 16 consecutive lines (bounds how many lines can sit on one point)
     // nu-sharded runs: first/last point of the GLOBAL grid, so that the strict includedlines prefilter
     // (line_shapes.jl:18-22) is applied to the grid the reference would see, not to a slice of it
     bool has_range = false;

@@ -235,6 +235,7 @@ struct LineSumArgs {
     double near_cn;         // near-centre fraction the per-tile ranges were built with (maximum over the level batch)
     int band;               // Voigt: 1 = per-point band correction of the near-centre lines (host: damping parameter bounded below)
     int split;              // 1 = two launches: cold classes (this kernel, COLD) then far_fold_kernel over the all-inside lines
+    int fold_g;             // lines per reciprocal in far_fold_kernel (32, 16 or 4: the host bounds the product of G values q)
     const double2* chix;    // PHCO2 expansion: {X, 1/X}, X = exp(0.0232 (nul - chix_ref)) per prefiltered line (or null)
     double chix_ref;
 };
@@ -1549,7 +1550,7 @@ __global__ void __launch_bounds__(LS_THREADS, (COLD ? CS_LS_COLD_MINBLK : CS_LS_
 // unit (one warp = tile x level, private TMA ring), a fraction of the registers and of the instruction footprint of
 // line_sum_kernel, hence more resident warps to keep the FP64 pipe fed.  Runs after line_sum_kernel<.., COLD> and completes `out`.
 constexpr int HF_STAGES = 2;
-template <int R>
+template <int R, int G>
 __global__ void __launch_bounds__(32, CS_LS_HOT_MINBLK) far_fold_kernel(LineSumArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -1597,7 +1598,7 @@ __global__ void __launch_bounds__(32, CS_LS_HOT_MINBLK) far_fold_kernel(LineSumA
         const double4* st = ring + (size_t)s * LS_CHUNK;
         const int n = min(LS_CHUNK, nfar - c * LS_CHUNK);
         int j = 0;
-        fold_run<R, CS_LS_FOLD>(st, j, n, nup, acc);
+        fold_run<R, G>(st, j, n, nup, acc);
         fold_tail<R>(st, j, n, nup, acc);
         __syncwarp();
         if (lane == 0 && c + HF_STAGES < nchunk) {
@@ -1694,7 +1695,11 @@ template <int SHAPE, int R> int32_t launch_line_sum(cs_ctx* ctx, LineSumArgs a, 
                                          (int)smem));
         line_sum_kernel<SHAPE, R, false, B, CAN_SPLIT><<<grid, LS_THREADS, smem, st>>>(a);
         CS_CUDA(cudaGetLastError());
-        far_fold_kernel<R><<<dim3((unsigned)a.ntiles, (unsigned)nlev), 32, HF_STAGES * LS_CHUNK * sizeof(double4), st>>>(a);
+        const dim3 hot_grid((unsigned)a.ntiles, (unsigned)nlev);
+        const size_t hot_smem = HF_STAGES * LS_CHUNK * sizeof(double4);
+        if (a.fold_g >= 32) far_fold_kernel<R, 32><<<hot_grid, 32, hot_smem, st>>>(a);
+        else if (a.fold_g >= 16) far_fold_kernel<R, 16><<<hot_grid, 32, hot_smem, st>>>(a);
+        else far_fold_kernel<R, 4><<<hot_grid, 32, hot_smem, st>>>(a);
         CS_CUDA(cudaGetLastError());
         cs_count_launch(ctx, 3);
         return CS_OK;
@@ -1909,6 +1914,38 @@ int32_t cs_lines_accumulate(cs_lines* L, int32_t shape, int64_t nnu, const doubl
             if (ctx->ls_no_band) la.band = 0;
         }
         la.split = ctx->ls_no_split ? 0 : 1;
+        // The fold keeps a running denominator d = product of G values q = dnu^2 + gamma^2.  Overflow: q <= dmax^2 + gamma_max^2 with
+        // dmax the largest distance the window allows.  Underflow (band / Lorentz: lines folded at their own centres): fewer than k
+        // lines can lie within s_k / 2 of a point (s_k = narrowest span of k consecutive lines), the others have q >= s_k^2 / 4, so
+        // d >= (gamma_min^2)^(k-1) (s_k^2/4)^(G-k+1) for every k.  G = 32 where that is safe, else 16, else 4.
+        la.fold_g = 4;
+        if (shape == CS_VOIGT || shape == CS_LORENTZ) {
+            double gmin = 1e300, gmax = 0.0;
+            for (int64_t k = 0; k < kb; k++) {
+                const LevelParams& lp = hl[(size_t)k];
+                const double tr = CS_TREF / lp.T;
+                const double plo = std::min(pow(tr, L->na_min), pow(tr, L->na_max)), phi = std::max(pow(tr, L->na_min), pow(tr, L->na_max));
+                gmin = std::min(gmin, plo * (L->ga_min * (lp.P - lp.Pp) + L->gs_min * lp.Pp) / CS_ATM);
+                gmax = std::max(gmax, phi * L->g_max * lp.P / CS_ATM);
+            }
+            const double dmax = std::min(cut, std::max(fabs(h_nu[nnu - 1] - la.nul_lo), fabs(la.nul_hi - h_nu[0])));
+            const double lq_hi = log10(dmax * dmax + gmax * gmax + 1e-300);
+            const double lg2 = gmin > 0.0 ? 2.0 * log10(gmin) : -1e300;
+            auto safe = [&](int G) {
+                if (G * std::max(lq_hi, 0.0) > 280.0) return false;
+                const int ks[3] = {4, 8, 16};
+                for (int q = 0; q < 3; q++) {
+                    if (ks[q] > G) continue;
+                    const double sk = L->span_k[q];
+                    const double lsk = sk > 0.0 ? std::min(2.0 * log10(0.5 * sk), 0.0) : -1e300;
+                    if ((ks[q] - 1) * std::min(lg2, 0.0) + (G - ks[q] + 1) * lsk > -280.0) return true;
+                }
+                return false;
+            };
+            la.fold_g = safe(32) ? 32 : (safe(16) ? 16 : 4);
+            if (shape == CS_VOIGT && la.fold_g < 16) la.band = 0;      // the single launch folds far lines only (q >= (c nul)^2)
+            if (ctx->ls_fold_g > 0) la.fold_g = std::min(la.fold_g, ctx->ls_fold_g);
+        }
         switch (shape) {
         case CS_DOPPLER: CS_TRY((launch_line_sum<CS_DOPPLER, 4>(ctx, la, (int)kb, cn))); break;
         // expansion mode: what is left for the pair-by-pair sum scales with the tile width (cut-off edges, lines within 4 half

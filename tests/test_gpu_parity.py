@@ -179,6 +179,25 @@ def test_voigt_direct_sum_variants(cs, orc, monkeypatch):
             ctx.close()
 
 
+def test_fold_guard_coincident_lines(cs, orc):
+    """the far-wing fold keeps a running product of G values q = dnu^2 + gamma^2; 40 lines sitting on the same wavenumber with
+    an evaluation point exactly there (q = gamma^2 for all of them, 1e-5 Pa .. 1 bar) must not underflow it: the host bounds
+    the product from the narrowest spans of 4 / 8 / 16 consecutive lines and falls back to shorter groups / the per-tile path"""
+    sl = synthetic_lines(cs, 400, seed=5, νmax=60.0)
+    ν0 = 30.0
+    sl.ν[100:140] = ν0
+    sl.ν[:] = np.sort(sl.ν)
+    ν = np.unique(np.concatenate([ν0 + 0.01 * np.arange(-300, 301), [ν0]]))
+    T = np.array([180.0, 296.0, 250.0])
+    P = np.array([1e-5, 1e5, 50.0])
+    Pp = 1e-3 * P
+    for shape, sid in (("lorentz", orc.LORENTZ), ("voigt", orc.VOIGT)):
+        got = cs.xsec(shape, ν, sl, T, P, Pp, 25.0)
+        ref = orc.xsec(sid, sl, ν, T, P, Pp, 25.0, nthreads=0)
+        assert np.all(np.isfinite(got)), shape
+        assert relerr(got, ref, 1e-290) < XSEC_TOL, shape
+
+
 def test_xsec_cutoff_is_inclusive(cs, orc):
     """a point exactly Δνcut away from a line is included (line_shapes.jl:10); the strict prefilter
     (line_shapes.jl:18-22) drops a line sitting exactly at min(ν) - cut"""
