@@ -32,9 +32,9 @@ METRIC = "line×ν×layer evals/s"
 UNIT = "evals/s"
 FLOP_PER_EVAL = 10.0   # Voigt, far-wing dominated
 # dram__bytes_read.sum + dram__bytes_write.sum of the line sum of one gas (101 levels) on C2 = its two launches,
-# line_sum_kernel<VOIGT, COLD> (1.663 + 0.232 GB) + far_fold_kernel<4> (1.069 + 0.233 GB), from the ncu --set full capture
+# line_sum_kernel<VOIGT, COLD> (1.663 + 0.233 GB) + far_fold_kernel<4, 32> (1.066 + 0.238 GB), from the ncu --set full capture
 # summarised in profiles/r2_ncu_full_line_sum_voigt_split.csv
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 1.662985e9 + 0.231875e9 + 1.068747e9 + 0.233475e9
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 1.663275e9 + 0.232875e9 + 1.065617e9 + 0.237670e9
 
 
 # ------------------------------------------------------------------------------------------------
@@ -448,7 +448,7 @@ def run_ours(args):
                 "max_rel_diff_fluxes_vs_resident": float(np.max(np.abs(Fe - F) / np.maximum(np.abs(F), 1e-300)))},
         "gpu_launches": int(launches),
         "clocks": clk.summary(),
-        "roofline": {"bound": "fp64", "kernel": "Voigt line sum = line_sum_kernel<VOIGT, COLD> + far_fold_kernel<4> (two launches per gas)",
+        "roofline": {"bound": "fp64", "kernel": "Voigt line sum = line_sum_kernel<VOIGT, COLD> + far_fold_kernel<4, 32> (two launches per gas)",
                      "achieved": achieved, "peak": fp64_peak / 1e12,
                      "unit": "TFLOP/s", "frac": (achieved / (fp64_peak / 1e12)) if achieved else None,
                      "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH if wl["name"] == "c2" and world == 1 else None,
