@@ -819,16 +819,30 @@ __global__ void __launch_bounds__(RT_THREADS) rcm_rt_kernel(RcmRtArgs a)
     double tau_n = a.tau[j];
 #pragma unroll
     for (int k = 0; k < NSMAX; k++) tn[k] = (k < ns) ? a.tr[(size_t)k * nnu + j] : 0.0;
+    // operands of the layer after next as well: with few wavenumbers per device (a nu slice of an 8-way split) there are only
+    // ~8 warps per SM, and one layer of loads in flight per thread does not cover the HBM latency
+    double tau_n2 = 0.0, tn2[NSMAX];
+#pragma unroll
+    for (int k = 0; k < NSMAX; k++) tn2[k] = 0.0;
+    if (L > 1) {
+        tau_n2 = a.tau[nnu + j];
+#pragma unroll
+        for (int k = 0; k < NSMAX; k++)
+            if (k < ns) tn2[k] = a.tr[((size_t)ns + k) * nnu + j];
+    }
     double Msum = 0.0;
     for (int i = 0; i < L; i++) {
         const double tau = tau_n;
 #pragma unroll
         for (int k = 0; k < NSMAX; k++) tk[k] = tn[k];
-        if (i + 1 < L) {      // next layer's operands, one iteration ahead
-            tau_n = a.tau[(size_t)(i + 1) * nnu + j];
+        tau_n = tau_n2;
+#pragma unroll
+        for (int k = 0; k < NSMAX; k++) tn[k] = tn2[k];
+        if (i + 2 < L) {      // operands two layers ahead
+            tau_n2 = a.tau[(size_t)(i + 2) * nnu + j];
 #pragma unroll
             for (int k = 0; k < NSMAX; k++)
-                if (k < ns) tn[k] = a.tr[((size_t)(i + 1) * ns + k) * nnu + j];
+                if (k < ns) tn2[k] = a.tr[((size_t)(i + 2) * ns + k) * nnu + j];
         }
         const double Bnext = 100.0 * pref / (exp(hcn * skT[i + 1]) - 1.0);
         a.B_s[(size_t)(i + 1) * nnu + j] = Bnext;
@@ -861,16 +875,28 @@ __global__ void __launch_bounds__(RT_THREADS) rcm_rt_kernel(RcmRtArgs a)
     double B_n = a.B_s[(size_t)(L - 1) * nnu + j];
 #pragma unroll
     for (int k = 0; k < NSMAX; k++) tn[k] = (k < ns) ? a.tr[((size_t)(L - 1) * ns + k) * nnu + j] : 0.0;
+    double B_n2 = 0.0;
+    if (L > 1) {
+        tau_n2 = a.tau[(size_t)(L - 2) * nnu + j];
+        B_n2 = a.B_s[(size_t)(L - 2) * nnu + j];
+#pragma unroll
+        for (int k = 0; k < NSMAX; k++)
+            if (k < ns) tn2[k] = a.tr[((size_t)(L - 2) * ns + k) * nnu + j];
+    }
     for (int i = L - 1; i >= 0; i--) {
         const double tau = tau_n, B2 = B_n;
 #pragma unroll
         for (int k = 0; k < NSMAX; k++) tk[k] = tn[k];
-        if (i > 0) {
-            tau_n = a.tau[(size_t)(i - 1) * nnu + j];
-            B_n = a.B_s[(size_t)(i - 1) * nnu + j];
+        tau_n = tau_n2;
+        B_n = B_n2;
+#pragma unroll
+        for (int k = 0; k < NSMAX; k++) tn[k] = tn2[k];
+        if (i > 1) {
+            tau_n2 = a.tau[(size_t)(i - 2) * nnu + j];
+            B_n2 = a.B_s[(size_t)(i - 2) * nnu + j];
 #pragma unroll
             for (int k = 0; k < NSMAX; k++)
-                if (k < ns) tn[k] = a.tr[((size_t)(i - 1) * ns + k) * nnu + j];
+                if (k < ns) tn2[k] = a.tr[((size_t)(i - 2) * ns + k) * nnu + j];
         }
         const double rtau = cs_rcp(tau);
         double Ms = 0.0;
