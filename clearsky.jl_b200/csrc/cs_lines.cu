@@ -20,7 +20,7 @@
 //   predicate |nu - nul| <= cut, line_shapes.jl:10, folded into the numerators), centre close to the tile (near:
 //   Faddeyeva region decided per evaluation), outside (never touched).  All per-chunk index arithmetic is 32-bit and
 //   relative to the first line of the window.
-//   Far-wing Voigt (|z|^2 >= 1.6e4, >99 % of evaluations) is algebraically the Lorentz profile
+//   Far-wing Voigt (|z|^2 >= W985_S1 = 3.8e4, the 1-convergent region of Algorithm 985; >98 % of evaluations) is algebraically the Lorentz profile
 //   S*gamma/(pi*(dnu^2+gamma^2)); four lines share one reciprocal: n1/d1 + n2/d2 = (n1 d2 + n2 d1)/(d1 d2), twice.
 //   Evaluations that need the general Algorithm-985 routine are compacted into a per-warp queue and evaluated with
 //   all lanes busy.  PHCO2 factorises chi into per-point and per-line exponentials (see the kernel).
@@ -250,8 +250,8 @@ __device__ __noinline__ double voigt_near(const double4* __restrict__ slow, int6
     double y = (chi * s.w) * s.x;          // (chi*gamma)*d ; chi == 1 for plain Voigt (line_shapes.jl:373,498)
     double y2 = y * y;
     double sq = fma(x, x, y2);
-    if (sq >= 1.6e4) return s.z * (y * osqpi / sq);
-    if (sq >= 160.0) {
+    if (sq >= W985_S1) return s.z * (y * osqpi / sq);
+    if (sq >= W985_S2) {
         // Re[i z/(sqrt(pi)(z^2-1/2))] = y (s+1/2) / (sqrt(pi) ((s-1/2)^2 + 2 y^2))
         double sm = sq - 0.5;
         return s.z * (osqpi * y * (sq + 0.5) / fma(sm, sm, 2.0 * y2));
@@ -269,16 +269,22 @@ __device__ __forceinline__ double chi_phco2(double adnu, double B1, double B2)
 }
 
 // hi-word thresholds of |z|^2 with a 1e-6 guard band (the hi word of a double resolves 2^-20 ~ 1e-6):
-//   hi(s) >  S1_HI              =>  s > 1.6e4 (1+1e-6)   : 1 convergent, certainly
-//   S2_HI < hi(s) < S1_LO       =>  160 (1+1e-6) < s < 1.6e4 (1-1e-6) : 2 convergents, certainly
+//   hi(s) >  S1_HI              =>  s > S1 (1+1e-6)   : 1 convergent, certainly          (S1, S2 = W985_S1, W985_S2)
+//   S2_HI < hi(s) < S1_LO       =>  S2 (1+1e-6) < s < S1 (1-1e-6) : 2 convergents, certainly
 // anything else is decided by the general routine with the reference's own s = fma(x,x,y^2).
+#if CS_W985_MAP
+#define CS_S1_HI 0x40E28E03   /* hi word of 3.8e4*(1+1.0e-6) rounded up   (3.8e4 = 0x40E28E00 00000000) */
+#define CS_S1_LO 0x40E28DFC   /* hi word of 3.8e4*(1-1.0e-6) rounded down */
+#define CS_S2_HI 0x40700002   /* hi word of 256*(1+1.0e-6) rounded up     (256 = 0x40700000 00000000) */
+#else
 #define CS_S1_HI 0x40CF4004   /* hi word of 1.6e4*(1+1.0e-6) rounded up   (1.6e4 = 0x40CF4000 00000000) */
 #define CS_S1_LO 0x40CF3FFB   /* hi word of 1.6e4*(1-1.0e-6) rounded down */
 #define CS_S2_HI 0x40640002   /* hi word of 160*(1+1.0e-6) rounded up     (160 = 0x40640000 00000000) */
+#endif
 
 // branch-free choice between the 1- and 2-convergent forms, both written in Lorentz variables:
 //   1: K/q          2: K d^2 (s+1/2) / ((s-1/2)^2 + 2 y^2),   s = d^2 q,  y^2 = d^2 gamma^2
-// need = true when neither form is certain (guard bands, |z|^2 < 160): the caller must use the general routine
+// need = true when neither form is certain (guard bands, |z|^2 < W985_S2): the caller must use the general routine
 __device__ __forceinline__ double voigt_12(const double4 rc, double dnu, bool& need)
 {
     double q = fma(dnu, dnu, rc.y);
@@ -435,7 +441,7 @@ __device__ __noinline__ void cold_flush(const WarpCold& w, const double4* st, in
 // ---- the far-wing fold.  G lines per reciprocal, folded left to right: (n, d) <- (n q + K d, d q) costs 3 FP64 operations
 // per line (like a pairwise merge of fractions) but keeps ONE running fraction per point, so the group can be long:
 // 2 G + 3 (G - 1) + 4 operations per G evaluations = 5.06 per evaluation at G = 16 (5.25 for a 2 x 2 tree), with one MUFU
-// seed per 16 evaluations instead of one per 4.  d is a product of G values q >= gamma^2 (and >= 1.6e4 alpha^2 / ln 2 for
+// seed per 16 evaluations instead of one per 4.  d is a product of G values q >= gamma^2 (and >= W985_S1 alpha^2 / ln 2 for
 // Voigt): far from underflow for any physical list.
 template <int R, int G>
 __device__ __forceinline__ void fold_run(const double4* __restrict__ st, int& j, int f1, const double (&nup)[R], double (&acc)[R])
@@ -594,13 +600,13 @@ __device__ __noinline__ int cold_near(const WarpCold& w, const double4* st, int 
     return qn;
 }
 
-// ---- Voigt near band, per point.  The per-tile near range [nlo,nhi) holds every line whose Doppler zone (|z|^2 < 1.6e4)
+// ---- Voigt near band, per point.  The per-tile near range [nlo,nhi) holds every line whose Doppler zone (|z|^2 < W985_S1)
 // touches SOME point of the tile; for one point only the lines with nul (1 - cn) <= nu <= nul (1 + cn) can be inside their
 // zone -- ~1/4 of the (line, point) pairs of the range on the C2 grid.  So the whole range goes through the far-wing fold
 // like any other line (K/q for every pair, no test), and each lane walks the band of ITS points (two binary searches per
 // point, records read straight from L1/L2: the lanes read different lines) adding the difference to the true value:
 //   2 convergents:  K d^2 (s+1/2)/D - K/q = K (3/2 s - 1/4 - 2 y^2)/(q D),  D = (s-1/2)^2 + 2 y^2   (no cancellation)
-//   general routine (|z|^2 < 160 and the guard slivers): w985 value - K/q, deferred to the queue as before.
+//   general routine (|z|^2 < W985_S2 and the guard slivers): w985 value - K/q, deferred to the queue as before.
 // K/q exceeds the true value by at most 1/(sqrt(pi) y) (at the line centre), so the subtraction costs log10 of that in
 // digits: the host only selects this path when y >= 1e-5 for every line of every level of the batch.
 template <int R>
@@ -1851,7 +1857,7 @@ int32_t cs_lines_accumulate(cs_lines* L, int32_t shape, int64_t nnu, const doubl
             // near-centre half width as a fraction of the line position: sqrt(thr_j) = nul_j * f(T, mu_j)
             double vth = sqrt(2.0 * CS_R * lp.T / L->mu_min) / CS_C;
             if (shape == CS_VOIGT || shape == CS_PHCO2)
-                lp.cnear = sqrt(1.6e4 * (1.0 + 1e-9)) / 0.83255461115769775635 * vth * (1.0 + 1e-6);
+                lp.cnear = sqrt(W985_S1 * (1.0 + 1e-9)) / 0.83255461115769775635 * vth * (1.0 + 1e-6);
             else if (shape == CS_DOPPLER)
                 lp.cnear = sqrt(746.0) * vth * (1.0 + 1e-6);
             else

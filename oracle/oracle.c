@@ -114,18 +114,35 @@ double orc_lorentz(double nu, double nul, double S, double gamma)
 /* ------------------------------------------------------------------------------------------------
  * Re w(x+iy) -- restatement of Algorithm 985 (Zaghloul 2017), the arithmetic behind
  * Faddeyeva985.faddeyeva(x,y) called at line_shapes.jl:375.  The package source is not available
- * offline; region borders and formulas are reconstructed from the published algorithm:
- *   |z|^2 >= 1.6e4              1 convergent of the Laplace continued fraction
- *   160  <= |z|^2 < 1.6e4       2 convergents
- *   107  <= |z|^2 < 160         3 convergents
- *   28.5 <= |z|^2 < 107, y^2 >= 6e-14    4 convergents
- *   3.5  <= |z|^2 (< 107), y^2 < 0.026   Humlicek (1982) w4 region-IV form, exp(u) - t P6(u)/Q7(u)
- *   otherwise                   Hui, Armstrong & Wray (1978) p = 6 rational approximation
- * Each border is where the cheaper form reaches ~1e-4 relative error in the real part (verified
- * against scipy.special.wofz in tests/test_oracle_pins.py: max rel. err 1.0e-4 over
- * x in [0,1e5], y in [1e-30,1e5]).  s is formed with an explicit fma so that the CUDA kernel and
- * this oracle take the same branch for the same (x, y).
+ * offline (PARITY UNPINNED until tools/julia_golden.jl has been run); the FORMS are the published ones
+ * (1-4 convergents of the Laplace continued fraction, Humlicek's (1982) w4 region-IV form
+ * exp(u) - t P6(u)/Q7(u), Hui, Armstrong & Wray's (1978) p = 6 rational approximation), the region BORDERS
+ * exist in two self-consistent sets -- in each, every constant sits exactly where the cheaper form reaches the
+ * set's accuracy against an accurate w(z) (scipy.special.wofz; tests/test_oracle_pins.py):
+ *
+ *                    map 1 (default)                        map 0
+ *   1 convergent     |z|^2 >= 3.8e4   (needs 3.73e4)        |z|^2 >= 1.6e4   (needs 1.50e4)
+ *   2 convergents    |z|^2 >= 256     (needs 251)           |z|^2 >= 160     (needs 159.2)
+ *   3 convergents    |z|^2 >= 62                            |z|^2 >= 107
+ *   4 convergents    |z|^2 >= 30, y^2 >= 1e-13              |z|^2 >= 28.5, y^2 >= 6e-14
+ *   Humlicek w4-IV   |z|^2 >= 2.5, y^2 < 0.072              |z|^2 >= 3.5, y^2 < 0.026
+ *   Hui p = 6        otherwise                              otherwise
+ *   max rel. error   4.2e-5 (real and imaginary part)       1.0e-4
+ *
+ * The Algorithm 985 paper states "a maximum relative error less than 4.0e-5 for both real and imaginary parts of w",
+ * and SURVEY.md 8(c) makes agreement with wofz to <= 4e-5 the necessary condition for any restatement: map 1 meets it,
+ * map 0 (SURVEY.md's own recollection of the borders, the default until late in round 2) does not (9.6e-5).  So map 1
+ * is the default; map 0 stays selectable (orc_set_w985_map here, -DCS_W985_MAP=0 for the CUDA library), and
+ * tools/julia_golden.jl samples the real package across the borders of BOTH maps so that one Julia run decides.
+ * s is formed with an explicit fma so that the CUDA kernel and this oracle take the same branch for the same (x, y).
  */
+static int orc_w985_map = 1;
+void orc_set_w985_map(int m) { orc_w985_map = m ? 1 : 0; }
+int orc_get_w985_map(void) { return orc_w985_map; }
+static const double W985[2][7] = {
+    /* S1      S2     S3     S4    Y4     S5   Y5 */
+    {1.6e4, 160.0, 107.0, 28.5, 6e-14, 3.5, 0.026},
+    {3.8e4, 256.0, 62.0, 30.0, 1e-13, 2.5, 0.072}};
 static const double HUI_A[7] = {122.607931777104326, 214.382388694706425, 181.928533092181549,
                                 93.155580458138441, 30.180142196210589, 5.912626209773153,
                                 0.564189583562615};
@@ -135,38 +152,40 @@ static const double HUI_B[7] = {122.607931773875350, 352.730625110963558, 457.33
 
 int orc_faddeyeva985_region(double x, double y)
 {
+    const double* W = W985[orc_w985_map];
     double y2 = y * y;
     double s = fma(x, x, y2);
-    if (s >= 1.6e4) return 1;
-    if (s >= 160.0) return 2;
-    if (s >= 107.0) return 3;
-    if (s >= 28.5 && y2 >= 6e-14) return 4;
-    if (s >= 3.5 && y2 < 0.026) return 5;
+    if (s >= W[0]) return 1;
+    if (s >= W[1]) return 2;
+    if (s >= W[2]) return 3;
+    if (s >= W[3] && y2 >= W[4]) return 4;
+    if (s >= W[5] && y2 < W[6]) return 5;
     return 6;
 }
 
 double orc_faddeyeva985(double x, double y)
 {
+    const double* W = W985[orc_w985_map];
     const double osqpi = 1.0 / sqrt(ORC_PI);
     double y2 = y * y;
     double s = fma(x, x, y2);
     double complex z = x + I * y;
     double complex iosp = I * osqpi;
-    if (s >= 1.6e4) return y * osqpi / s;
-    if (s >= 160.0) {
+    if (s >= W[0]) return y * osqpi / s;
+    if (s >= W[1]) {
         double complex zz = z * z;
         return creal(iosp * z / (zz - 0.5));
     }
-    if (s >= 107.0) {
+    if (s >= W[2]) {
         double complex zz = z * z;
         return creal(iosp * (zz - 1.0) / (z * (zz - 1.5)));
     }
-    if (s >= 28.5 && y2 >= 6e-14) {
+    if (s >= W[3] && y2 >= W[4]) {
         double complex zz = z * z;
         return creal(iosp * z * (zz - 2.5) / (zz * (zz - 3.0) + 0.75));
     }
     double complex t = y - I * x;
-    if (s >= 3.5 && y2 < 0.026) {
+    if (s >= W[5] && y2 < W[6]) {
         double complex u = t * t;
         double complex P = 36183.31 - u * (3321.9905 - u * (1540.787 - u * (219.0313 - u * (35.76683 -
                            u * (1.320522 - u * 0.56419)))));

@@ -201,6 +201,20 @@ def planck(ν, T):
     return out
 
 
+W985_MAPS = {0: dict(S1=1.6e4, S2=160.0, S3=107.0, S4=28.5, Y4=6e-14, S5=3.5, Y5=0.026),
+             1: dict(S1=3.8e4, S2=256.0, S3=62.0, S4=30.0, Y4=1e-13, S5=2.5, Y5=0.072)}
+
+
+def set_w985_map(m):
+    """region borders of the Faddeyeva restatement: 1 (default) = the 4e-5 design the Algorithm 985 paper describes,
+    0 = the 1e-4 design (SURVEY.md 8c's recollection); see the header of orc_faddeyeva985 in oracle.c"""
+    lib().orc_set_w985_map(C.c_int(int(m)))
+
+
+def get_w985_map():
+    return int(lib().orc_get_w985_map())
+
+
 def faddeyeva985(x, y):
     x, y = np.broadcast_arrays(_f(x), _f(y))
     x, y = _f(x), _f(y)

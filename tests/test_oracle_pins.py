@@ -16,25 +16,46 @@ mp.mp.dps = 40
 
 
 def test_faddeyeva985_accuracy(orc):
-    """Algorithm 985 restatement: <= 1.01e-4 relative in Re w over 13 decades of x and 35 of y"""
-    xs = np.concatenate([[0.0], np.logspace(-8, 5, 700)])
-    ys = np.logspace(-30, 5, 500)
-    X, Y = np.meshgrid(xs, ys)
-    w = orc.faddeyeva985(X, Y)
+    """Algorithm 985 restatement against an accurate w(z).  SURVEY.md 8(c) makes agreement with scipy's wofz to <= 4e-5 on a
+    log grid x in [0, 1e5], y in [1e-8, 1e5] the necessary condition for a restatement -- the accuracy the paper states for both
+    parts of w.  The default region map (1) meets it; the earlier map (0, SURVEY's own recollection of the borders) is a 1e-4
+    design and does not, which is why it is no longer the default (oracle.c, orc_faddeyeva985)."""
+    xs = np.concatenate([[0.0], np.logspace(-8, 5, 900)])
+    X, Y = np.meshgrid(xs, np.logspace(-8, 5, 600))
     ref = wofz(X + 1j * Y).real
-    assert np.max(np.abs(w - ref) / np.abs(ref)) < 1.01e-4
+    try:
+        assert orc.get_w985_map() == 1
+        assert np.max(np.abs(orc.faddeyeva985(X, Y) - ref) / np.abs(ref)) < 4.2e-5
+        orc.set_w985_map(0)
+        e0 = np.max(np.abs(orc.faddeyeva985(X, Y) - ref) / np.abs(ref))
+        assert 9e-5 < e0 < 1.01e-4
+        # map 0 down to y = 1e-30 (its 3-convergent border, 107, is safe there; map 1's 62 needs y >~ 1e-21: exp(-x^2) term)
+        X2, Y2 = np.meshgrid(xs, np.logspace(-30, 5, 400))
+        ref2 = wofz(X2 + 1j * Y2).real
+        assert np.max(np.abs(orc.faddeyeva985(X2, Y2) - ref2) / np.abs(ref2)) < 1.01e-4
+    finally:
+        orc.set_w985_map(1)
+    X3, Y3 = np.meshgrid(xs, np.logspace(-20, 5, 500))
+    ref3 = wofz(X3 + 1j * Y3).real
+    assert np.max(np.abs(orc.faddeyeva985(X3, Y3) - ref3) / np.abs(ref3)) < 4.2e-5
 
 
 def test_faddeyeva985_continuity(orc):
-    """each region border is continuous to the algorithm's accuracy"""
-    for s0, y in [(1.6e4, 1.0), (160.0, 0.5), (107.0, 0.3), (28.5, 0.2), (28.5, 1e-8), (3.5, 0.1), (3.5, 1.0)]:
-        x0 = np.sqrt(s0 - y * y)
-        a, b = orc.faddeyeva985(x0 * (1 - 1e-9), y), orc.faddeyeva985(x0 * (1 + 1e-9), y)
-        assert abs(a - b) / abs(b) < 2.1e-4
-    for x in (2.0, 3.0, 5.0):   # y^2 = 0.026 border
-        y0 = np.sqrt(0.026)
-        a, b = orc.faddeyeva985(x, y0 * (1 - 1e-9)), orc.faddeyeva985(x, y0 * (1 + 1e-9))
-        assert abs(a - b) / abs(b) < 2.1e-4
+    """each region border of both maps is continuous to the map's accuracy"""
+    try:
+        for m, tol in ((1, 8.5e-5), (0, 2.1e-4)):
+            orc.set_w985_map(m)
+            W = orc.W985_MAPS[m]
+            for s0, y in [(W["S1"], 1.0), (W["S2"], 0.5), (W["S3"], 0.3), (W["S4"], 0.2), (W["S4"], 1e-8), (W["S5"], 0.1), (W["S5"], 1.0)]:
+                x0 = np.sqrt(s0 - y * y)
+                a, b = orc.faddeyeva985(x0 * (1 - 1e-9), y), orc.faddeyeva985(x0 * (1 + 1e-9), y)
+                assert abs(a - b) / abs(b) < tol, (m, s0, y)
+            for x in (2.0, 3.0, 5.0):   # the y^2 border between Humlicek's and Hui's forms
+                y0 = np.sqrt(W["Y5"])
+                a, b = orc.faddeyeva985(x, y0 * (1 - 1e-9)), orc.faddeyeva985(x, y0 * (1 + 1e-9))
+                assert abs(a - b) / abs(b) < tol, (m, x)
+    finally:
+        orc.set_w985_map(1)
 
 
 def test_voigt_limits(orc):

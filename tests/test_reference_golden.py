@@ -78,13 +78,26 @@ def test_harness_on_mock_vectors(tmp_path):
 
 @needs_ref
 def test_faddeyeva_region_map(orc):
-    """Faddeyeva985.faddeyeva(x, y) on points straddling every border of the reconstructed region map
-    (oracle.c:132-178 <-> line_shapes.jl:375)"""
+    """Faddeyeva985.faddeyeva(x, y) on points straddling every border of BOTH candidate region maps
+    (oracle.c, orc_faddeyeva985 <-> line_shapes.jl:375).  The oracle's default map must be the package's; when the other map is
+    the one that matches, the message says so (orc_set_w985_map(0) / rebuild the CUDA library with -DCS_W985_MAP=0)."""
     x, y, w = ref("fad_x"), ref("fad_y"), ref("fad_w")
-    got = orc.faddeyeva985(x, y)
-    e = np.abs(got - w) / np.maximum(np.abs(w), 1e-300)      # y = 0 in a continued-fraction region gives exactly 0 on both sides
-    worst = int(np.argmax(e))
-    assert e[worst] < TOL_SIGMA, (x[worst], y[worst], got[worst], w[worst])
+    errs = {}
+    try:
+        for m in (1, 0):
+            orc.set_w985_map(m)
+            got = orc.faddeyeva985(x, y)
+            e = np.abs(got - w) / np.maximum(np.abs(w), 1e-300)   # y = 0 in a continued-fraction region gives exactly 0 on both sides
+            worst = int(np.argmax(e))
+            errs[m] = (float(e[worst]), float(x[worst]), float(y[worst]))
+    finally:
+        orc.set_w985_map(1)
+    default = orc.get_w985_map()
+    assert errs[default][0] < TOL_SIGMA, (
+        f"the reference's faddeyeva does not follow the oracle's default region map {default}: max rel. error "
+        f"{errs[default][0]:.2e} at x = {errs[default][1]:.6g}, y = {errs[default][2]:.6g}; the other map gives {errs[1 - default][0]:.2e}"
+        + (" -> it is the package's: switch the default (orc_w985_map in oracle.c, CS_W985_MAP in cs_internal.cuh)"
+           if errs[1 - default][0] < TOL_SIGMA else " -> neither map is the package's"))
 
 
 @needs_ref

@@ -46,16 +46,17 @@ end
 
 # ===================================================================================================================
 # 1. faddeyeva(x, y) as fvoigt calls it (src/absorption/line_shapes.jl:375), on points straddling every border of the
-#    oracle's reconstructed region map (|z|^2 = 3.5, 28.5, 107, 160, 1.6e4; y^2 = 6e-14, 0.026) and on a log grid
+#    BOTH candidate region maps of the oracle (oracle/oracle.c: map 1 |z|^2 = 2.5, 30, 62, 256, 3.8e4; y^2 = 1e-13, 0.072 and
+#    map 0 |z|^2 = 3.5, 28.5, 107, 160, 1.6e4; y^2 = 6e-14, 0.026) and on a log grid: one run decides which map the package uses
 # ===================================================================================================================
 let
     xs, ys = Float64[], Float64[]
     offs = [-1e-1, -1e-3, -1e-6, -1e-9, -1e-12, 0.0, 1e-12, 1e-9, 1e-6, 1e-3, 1e-1]
-    for s in (3.5, 28.5, 107.0, 160.0, 1.6e4), f in offs, φ in range(0.0, π / 2, length=33)
+    for s in (2.5, 3.5, 28.5, 30.0, 62.0, 107.0, 160.0, 256.0, 1.6e4, 3.8e4), f in offs, φ in range(0.0, π / 2, length=33)
         r = sqrt(s * (1 + f))
         push!(xs, r * cos(φ)); push!(ys, r * sin(φ))
     end
-    for y2 in (6e-14, 0.026), f in offs, x in vcat(0.0, 10 .^ range(-3, 5, length=49))
+    for y2 in (6e-14, 1e-13, 0.026, 0.072), f in offs, x in vcat(0.0, 10 .^ range(-3, 5, length=49))
         push!(xs, x); push!(ys, sqrt(y2 * (1 + f)))
     end
     for x in vcat(0.0, 10 .^ range(-6, 5, length=56)), y in 10 .^ range(-30, 5, length=71)

@@ -46,12 +46,12 @@ def main(out):
     # 1. faddeyeva
     xs, ys = [], []
     offs = [-1e-1, -1e-3, -1e-6, -1e-9, -1e-12, 0.0, 1e-12, 1e-9, 1e-6, 1e-3, 1e-1]
-    for s in (3.5, 28.5, 107.0, 160.0, 1.6e4):
+    for s in (2.5, 3.5, 28.5, 30.0, 62.0, 107.0, 160.0, 256.0, 1.6e4, 3.8e4):
         for f in offs:
             for φ in np.linspace(0.0, np.pi / 2, 33):
                 r = np.sqrt(s * (1 + f))
                 xs.append(r * np.cos(φ)); ys.append(r * np.sin(φ))
-    for y2 in (6e-14, 0.026):
+    for y2 in (6e-14, 1e-13, 0.026, 0.072):
         for f in offs:
             for x in np.concatenate([[0.0], 10.0 ** np.linspace(-3, 5, 49)]):
                 xs.append(x); ys.append(np.sqrt(y2 * (1 + f)))
