@@ -32,9 +32,9 @@ METRIC = "line×ν×layer evals/s"
 UNIT = "evals/s"
 FLOP_PER_EVAL = 10.0   # Voigt, far-wing dominated
 # dram__bytes_read.sum + dram__bytes_write.sum of the line sum of one gas (101 levels) on C2 = its two launches,
-# line_sum_kernel<VOIGT, COLD> (1.663 + 0.233 GB) + far_fold_kernel<4, 32> (1.066 + 0.238 GB), from the ncu --set full capture
+# line_sum_kernel<VOIGT, COLD> (1.701 + 0.233 GB) + far_fold_kernel<4, 32> (1.066 + 0.235 GB), from the ncu --set full capture
 # summarised in profiles/r2_ncu_full_line_sum_voigt_split.csv
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 1.663275e9 + 0.232875e9 + 1.065617e9 + 0.237670e9
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 1.701310e9 + 0.232902e9 + 1.065896e9 + 0.234923e9
 
 
 # ------------------------------------------------------------------------------------------------
