@@ -32,7 +32,7 @@ def per_point_counts(ν, νl, cut):
 
 # per-ν cost = evaluations * (1 + kappa * ν): fitted to the per-slice line-sum times of an 8-way split of C2 (tools/slice_balance.py).
 # The slope is the near-centre work (Doppler widths grow with ν); in expansion mode the far wings are nearly free, so it weighs more.
-KAPPA = {"direct": 9.4e-5, "expansion": 3.2e-4}   # direct refitted for the two-launch line sum (per-point band: round 2)
+KAPPA = {"direct": 1.24e-4, "expansion": 3.2e-4}   # direct refitted for the two-launch line sum with the wider near band of the default Faddeyeva borders
 
 
 def slice_cost(ν, line_lists, cut, kappa=None, farfield="direct"):
